@@ -1,0 +1,1 @@
+/* test scaffolding: empty stand-in for <htslib/hfile.h>; only type names from sam.h/kstring.h are needed by the decoder classes */

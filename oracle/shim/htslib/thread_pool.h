@@ -1,0 +1,1 @@
+/* test scaffolding: empty stand-in for <htslib/thread_pool.h>; only type names from sam.h/kstring.h are needed by the decoder classes */
