@@ -1,0 +1,196 @@
+/*  pheniqs_b200.h — C ABI of the B200-native Pheniqs barcode classification path.
+
+    This is the drop-in boundary for ONE path of the reference (Pheniqs 2.1.0): per-read
+    barcode classification by the PAMLD and MDD decoders (plus the bookkeeping of the naive /
+    passthrough decoders) over sample, molecular and cellular barcode sets. Everything the
+    reference does on that path one read at a time through
+
+        Classifier< Barcode >::classify(const Read&, Read&)      classifier.h:78-86
+          <- PamlDecoder::classify / MdDecoder::classify          pamld.cpp:37-123, mdd.cpp:37-86
+          <- TranscodingDecoder::classify                         transcode.h:51-65
+
+    is done here for a whole batch of reads per call on one B200 (sm_100a). File:line
+    citations are relative to the reference tree. Plain pointers and sizes only; no C++,
+    torch or CUDA types appear in any signature (streams travel as void*).
+
+    One handle = the ordered decoder chain of one job (sample, then molecular[], then
+    cellular[]: transcode.h:51-60) on one GPU, owned by one host thread, exactly as one
+    TranscodingThread owns a private TranscodingDecoder (transcode.cpp:2296).
+
+    Every function returns a phq_status whose values are the reference's ErrorCode
+    (error.h:32-44); the message of the last failure is read with phq_last_error().
+*/
+#ifndef PHENIQS_B200_H
+#define PHENIQS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHQ_VERSION "0.1.0"
+#define PHQ_MAX_SEGMENTS 8          /* output segments of one decoder's Observation */
+#define PHQ_MAX_NUCLEOTIDES 32      /* nucleotide cardinality of one decoder (two 16-base words) */
+#define PHQ_ABSENT_QUALITY 0xFF     /* quality byte marking a position the (short) read does not have */
+
+/* error.h:32-44 */
+typedef enum {
+    PHQ_OK                      = 0,
+    PHQ_UNKNOWN_ERROR           = 1,
+    PHQ_INTERNAL_ERROR          = 2,
+    PHQ_CONFIGURATION_ERROR     = 3,
+    PHQ_OUT_OF_MEMORY_ERROR     = 4,
+    PHQ_COMMAND_LINE_ERROR      = 5,
+    PHQ_IO_ERROR                = 6,
+    PHQ_SEQUENCE_ERROR          = 7,
+    PHQ_OVERFLOW_ERROR          = 8
+} phq_status;
+
+/* atom.h:348-355 (Algorithm) and classifier.h:28-33 (ClassifierType) */
+typedef enum { PHQ_PAMLD = 0, PHQ_MDD = 1, PHQ_NAIVE = 2, PHQ_PASSTHROUGH = 3 } phq_algorithm;
+typedef enum { PHQ_SAMPLE = 0, PHQ_MOLECULAR = 1, PHQ_CELLULAR = 2 } phq_topic;
+
+typedef struct phq_handle phq_handle;
+
+/*  Shape of decoder k of the chain, as compiled (decoder.h:44-52, classifier.h:54-60). */
+typedef struct {
+    int32_t algorithm;                  /* phq_algorithm */
+    int32_t topic;                      /* phq_topic */
+    int32_t index;                      /* "index" within its topic */
+    int32_t barcode_cardinality;        /* codec entries, undetermined excluded; barcode rows are 1..N in sorted codec-key order */
+    int32_t segment_cardinality;
+    int32_t nucleotide_cardinality;
+    int32_t segment_length[PHQ_MAX_SEGMENTS];
+    int32_t word_cardinality;           /* ceil(nucleotide_cardinality / 16): uint32 base words and uint16 mask words per read */
+    int32_t quality_word_cardinality;   /* ceil(nucleotide_cardinality / 4): uint32 quality words per read */
+    int32_t has_tile;                   /* 1 when the decoder consumes a phq_tile (PAMLD, MDD), 0 otherwise */
+} phq_decoder_info;
+
+/*  One decoder's view of a batch: the Observation that Rule::apply (transform.h:142-169)
+    extracts, for every read, as three structure-of-arrays planes. Position j of the
+    concatenated observation (segments in order) lives in word j / 16, bit j % 16.
+
+      bases[w * pitch + r]    bits 0..15  = low bit,  bits 16..31 = high bit of the 2-bit code
+                              (A=0, C=1, G=2, T=3) of the 16 bases of word w of read r
+      nmask[w * pitch + r]    bit j set   = base j is not one of A, C, G, T (N, IUPAC, '=' ...)
+      quality[w * pitch + r]  byte k      = Phred value (offset removed) of base 4w + k;
+                              PHQ_ABSENT_QUALITY marks a base a short read does not have (MDD)
+
+    Replaces the byte-per-base Segment / Observation containers of sequence.h:264-300. */
+typedef struct {
+    const uint32_t* bases;
+    const uint16_t* nmask;
+    const uint32_t* quality;
+    int64_t pitch;                      /* elements between consecutive words of a plane (>= n_reads) */
+} phq_tile;
+
+/*  What one decoder decides for one read: decoded->index (0 = undetermined), edit_distance and
+    decoding_confidence (classifier.h:47, decoder.h:34, pamld.h:35). MDD / naive confidence is 0. */
+typedef struct {
+    int32_t index;
+    int32_t distance;
+    double confidence;
+} phq_result;
+
+/* ------------------------------------------------------------------ configuration */
+
+/*  Compile the decoder directives of a job the way Transcode::compile_decoder does
+    (transcode.cpp:735-768, 824-1039; metric.h:87-111, 216-242; defaults configuration.json:368-376,
+    423-501): barcode index by sorted codec key, concentrations normalised to 1 - noise,
+    default random barcode probability 4^-n, default knit, default / validated distance
+    tolerance. Input: {"sample": {...}, "molecular": [...], "cellular": [...]}. The compiled
+    JSON (same keys as the reference's --compile output for those sections) is returned in a
+    buffer the caller releases with phq_free. Host only; no GPU needed. */
+int phq_compile_job(const char* job_json, char** compiled_json);
+void phq_free(void* pointer);
+/* message of the last failure of a call that had no handle to attach it to (calling thread) */
+const char* phq_last_global_error(void);
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/*  Build the decoder chain from COMPILED decoder JSON, as the reference's decoder constructors
+    do from the compiled ontology (classifier.h:54-60, decoder.h:44-52, pamld.cpp:24-31,
+    mdd.cpp:24-27; factory transcode.cpp:66-161), and upload barcode tables, priors and Phred
+    tables to `device`. Fails with PHQ_INTERNAL_ERROR when no CUDA device is usable: there is
+    no CPU fallback. device < 0 builds a host-only handle (configuration + phq_pack only). */
+int phq_create(const char* compiled_job_json, int device, phq_handle** handle);
+void phq_destroy(phq_handle* handle);
+const char* phq_last_error(const phq_handle* handle);
+
+int phq_decoder_count(const phq_handle* handle);
+int phq_decoder_describe(const phq_handle* handle, int decoder, phq_decoder_info* info);
+
+/* ------------------------------------------------------------------ host side of the feed seam */
+
+/*  Rule::apply (transform.h:142-169, token slicing transform.h:65-80, '~' reverse complement
+    iupac.h:107-124) for every tiled decoder over a batch of reads held the way the reference
+    holds them (one BAM 4-bit code byte and one Phred byte per base; segment s of read r is
+    code[s][offset[s][r] .. offset[s][r+1])), packed into caller-provided HOST planes
+    tiles[k] (k over all decoders; entries of untiled decoders are ignored).
+    Short tokens: PAMLD tiles reproduce what a single reference thread sees (terminator, then
+    the bytes left in its Observation by earlier reads, barcode.h:150 / sequence.h:296-300);
+    MDD tiles mark missing positions PHQ_ABSENT_QUALITY (sequence.h:90-98 iterate the observed
+    length). The handle carries the Observation scratch from call to call. */
+int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
+             const uint8_t* const* code, const uint8_t* const* quality, const int64_t* const* offset,
+             const phq_tile* tiles);
+
+/* ------------------------------------------------------------------ classification */
+
+/*  TranscodingDecoder::classify (transcode.h:51-65) for n_reads reads with HOST buffers:
+    tiles[k], results[k] (may be NULL for a decoder whose per-read results are not wanted) and
+    the per-read qcfail flags (qcfail_in may be NULL = all clear; qcfail_out receives the
+    running flag after the whole chain: input flag OR every decoder's verdict, read.h:94-103).
+    Copies host->device, launches the kernels and copies back on internal streams, pipelined
+    over sub-batches; returns when the outputs are in host memory. Accumulates into the
+    handle's device-resident tables. Pinned host memory (phq_host_alloc) makes the copies
+    asynchronous. */
+int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
+                     const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out);
+
+/*  Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t, NULL = default
+    stream): `qcfail` is read and updated in place. Nothing is copied; the caller synchronises. */
+int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
+                            uint8_t* device_qcfail, phq_result* const* device_results, void* stream);
+
+int phq_host_alloc(void** pointer, size_t bytes);       /* pinned host memory */
+void phq_host_free(void* pointer);
+
+/* ------------------------------------------------------------------ accumulators and priors */
+
+/*  Per-barcode accumulators of decoder k (AccumulatingOption, selector.h:32-60), row 0 =
+    undetermined, rows 1..N = barcodes. u64 columns: count, pf_count, accumulated_distance,
+    low_conditional_confidence_count, low_confidence_count, accumulated_pf_distance; f64
+    columns: accumulated_confidence, accumulated_pf_confidence. Synchronises the device. */
+int phq_accumulators(phq_handle* handle, int decoder, uint64_t* u64_table /* [(N+1)*6] */, double* f64_table /* [(N+1)*2] */);
+/* TranscodingDecoder::count / pf_count (transcode.h:44-45) */
+int phq_totals(phq_handle* handle, uint64_t* count, uint64_t* pf_count);
+/*  The device buffer holding ALL accumulators of the handle, laid out as n_u64 unsigned 64-bit
+    integers followed by n_f64 doubles, so the one collective of the path — the sum the
+    reference does thread by thread in collect() (transcode.cpp:162-179, classifier.h:87-93,
+    selector.cpp:68-77) — is one in-place all-reduce(sum) per plane. */
+int phq_accumulator_buffer(phq_handle* handle, void** device_pointer, int64_t* n_u64, int64_t* n_f64);
+int phq_reset_accumulators(phq_handle* handle);
+
+/*  Classifier::finalize prior estimation (classifier.h:94-124 with pamld.h:40-48,
+    decoder.h:77-83, selector.cpp:78-101) from the current accumulators of decoder k. */
+int phq_estimate_priors(phq_handle* handle, int decoder, double* estimated_noise, double* estimated_concentration /* [N] */);
+/*  Install a noise prior and per-barcode concentration priors (taken as already normalised,
+    as Classifier::adjust_prior writes them, classifier.h:125-160) for the next pass. */
+int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* concentration /* [N] */);
+
+/* ------------------------------------------------------------------ instrumentation */
+
+/* kernels launched by this handle so far, and reads whose PAMLD decision fell within 1e-12
+   (relative) of a threshold or needed the exact tie path (diagnostic "band" counters) */
+int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exact_path_reads, uint64_t* threshold_band_reads);
+/* device time (ms) of the kernels of the last phq_decode_batch_device call, measured with CUDA
+   events on the launching stream; synchronises that stream */
+int phq_last_kernel_milliseconds(phq_handle* handle, float* milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHENIQS_B200_H */

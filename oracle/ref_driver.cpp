@@ -238,7 +238,10 @@ void* phq_ref_create(const char* job_json, int32_t input_segment_cardinality, ch
     try {
         h->input_segment_cardinality = input_segment_cardinality;
         h->finalized = false;
-        if(h->job.Parse(job_json).HasParseError()) {
+        /* kParseFullPrecisionFlag: rapidjson's default number parser is off by up to a few ulp, which the
+           reference never sees for compiled values (it compiles and constructs decoders in one process
+           from the same in-memory Document); correctly rounded parsing makes the text round trip exact. */
+        if(h->job.Parse< rapidjson::kParseFullPrecisionFlag >(job_json).HasParseError()) {
             throw ConfigurationError(string("JSON parse error: ") + GetParseError_En(h->job.GetParseError()));
         }
         h->total.reset(new DecoderSet(h->job));

@@ -1,0 +1,678 @@
+/*  api.cu — the C ABI of include/pheniqs_b200.h: handle, device memory, host packer, launches.
+
+    The handle plays the role of one thread's TranscodingDecoder (transcode.h:40-65,
+    transcode.cpp:60-195): it owns the decoder chain, their barcode tables and accumulators.
+    File:line citations are relative to the reference tree.
+*/
+#include "kernels.cuh"
+#include "spec.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace phq;
+
+namespace {
+
+thread_local std::string global_error;
+
+#define PHQ_CUDA(call) do { cudaError_t status_ = (call); if(status_ != cudaSuccess) { \
+    throw phq::Error(status_ == cudaErrorMemoryAllocation ? PHQ_OUT_OF_MEMORY_ERROR : PHQ_INTERNAL_ERROR, \
+        std::string("Internal error : CUDA ") + cudaGetErrorName(status_) + " : " + cudaGetErrorString(status_) + " in " #call); } } while(0)
+
+/* iupac.h:107-124 BamToReverseComplementBam */
+const uint8_t BAM_REVERSE_COMPLEMENT[16] = { 0x0, 0x8, 0x4, 0xc, 0x2, 0xa, 0x6, 0xe, 0x1, 0x9, 0x5, 0xd, 0x3, 0xb, 0x7, 0xf };
+
+/* the per-segment scratch an Observation keeps from read to read (sequence.h:264-300) */
+struct ScratchSegment {
+    std::vector< uint8_t > code;
+    std::vector< uint8_t > quality;
+    int32_t length;
+    ScratchSegment() : code(PHQ_MAX_NUCLEOTIDES * 4 + 64, 0), quality(PHQ_MAX_NUCLEOTIDES * 4 + 64, 0), length(0) {}
+};
+
+template < class T > struct DeviceBuffer {
+    T* pointer;
+    size_t capacity;
+    DeviceBuffer() : pointer(NULL), capacity(0) {}
+    void reserve(size_t count) {
+        if(count > capacity) {
+            release();
+            PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&pointer), count * sizeof(T)));
+            capacity = count;
+        }
+    }
+    void release() {
+        if(pointer != NULL) { cudaFree(pointer); pointer = NULL; capacity = 0; }
+    }
+};
+
+/* device staging of one in-flight sub-batch of phq_decode_batch */
+struct StagingSlot {
+    cudaStream_t stream;
+    cudaEvent_t done;
+    std::vector< DeviceBuffer< uint32_t > > bases;
+    std::vector< DeviceBuffer< uint16_t > > nmask;
+    std::vector< DeviceBuffer< uint32_t > > quality;
+    std::vector< DeviceBuffer< phq_result > > results;
+    DeviceBuffer< uint8_t > qcfail;
+};
+
+constexpr int STAGING_SLOTS = 3;
+constexpr long long SUB_BATCH_READS = 1ll << 22;
+
+}   /* namespace */
+
+struct phq_handle {
+    int device;
+    std::vector< DecoderSpec > chain;
+    std::vector< DecoderParams > params;
+    std::vector< std::vector< ScratchSegment > > scratch;
+    std::vector< BarcodeEntry* > device_barcodes;
+    double* device_phred;
+    unsigned char* device_accumulators;
+    std::vector< int64_t > offset_u64;
+    std::vector< int64_t > offset_f64;
+    int64_t n_u64;
+    int64_t n_f64;
+    LaunchGeometry geometry;
+    StagingSlot slot[STAGING_SLOTS];
+    bool slots_ready;
+    cudaEvent_t timing_start;
+    cudaEvent_t timing_stop;
+    cudaStream_t timing_stream;
+    bool timing_valid;
+    uint64_t kernel_launches;
+    std::string error;
+
+    phq_handle() : device(0), device_phred(NULL), device_accumulators(NULL), n_u64(0), n_f64(0), slots_ready(false),
+        timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0) {}
+
+    unsigned long long* u64_plane() const { return reinterpret_cast< unsigned long long* >(device_accumulators); }
+    double* f64_plane() const { return reinterpret_cast< double* >(device_accumulators + n_u64 * 8); }
+    unsigned long long* totals() const { return u64_plane() + n_u64 - 4; }
+    unsigned long long* diagnostics() const { return u64_plane() + n_u64 - 2; }
+};
+
+namespace {
+
+/* phred.h:33-34, phred.cpp:24-72 with the host libm, then the factored forms the kernels consume */
+void assemble_phred(std::vector< double >& table, double& uniform_quality, double& base) {
+    table.assign(PHRED_TABLE_SIZE, 0.0);
+    uniform_quality = 10.0 * log10(4);
+    base = pow(10.0, -0.1);
+    table[PHRED_MATCH_FACTOR] = 1.0;
+    table[PHRED_MISMATCH_RATIO] = 1.0;
+    for(int q(1); q < 0x80; ++q) {
+        const double false_positive_probability(pow(base, q));
+        const double true_positive_probability(1.0 - false_positive_probability);
+        const double true_positive_quality(-10.0 * log10(true_positive_probability));
+        table[PHRED_TRUE_POSITIVE_QUALITY + q] = true_positive_quality;
+        table[PHRED_MATCH_FACTOR + q] = pow(base, true_positive_quality);
+        table[PHRED_MISMATCH_RATIO + q] = pow(base, static_cast< double >(q) - true_positive_quality);
+    }
+    table[PHRED_UNIFORM_QUALITY] = uniform_quality;
+    table[PHRED_BASE] = base;
+    table[PHRED_UNIFORM_FACTOR] = pow(base, uniform_quality);
+}
+
+void upload_barcodes(phq_handle* h, size_t k) {
+    const DecoderSpec& d(h->chain[k]);
+    std::vector< BarcodeEntry > table(static_cast< size_t >(d.barcode_cardinality));
+    for(int32_t b(0); b < d.barcode_cardinality; ++b) {
+        BarcodeEntry e;
+        e.lo = 0; e.hi = 0;
+        for(int32_t j(0); j < d.nucleotide_cardinality; ++j) {
+            const uint8_t code(d.barcode[static_cast< size_t >(b) * d.nucleotide_cardinality + j]);
+            const uint32_t two(code == 1 ? 0u : code == 2 ? 1u : code == 4 ? 2u : 3u);
+            e.lo |= (two & 1u) << j;
+            e.hi |= (two >> 1) << j;
+        }
+        e.prior = d.concentration[b];
+        table[b] = e;
+    }
+    PHQ_CUDA(cudaMemcpy(h->device_barcodes[k], table.data(), table.size() * sizeof(BarcodeEntry), cudaMemcpyHostToDevice));
+}
+
+void refresh_params(phq_handle* h, size_t k) {
+    const DecoderSpec& d(h->chain[k]);
+    DecoderParams& p(h->params[k]);
+    memset(&p, 0, sizeof(p));
+    p.algorithm = d.algorithm;
+    p.barcode_cardinality = d.barcode_cardinality;
+    p.nucleotide_cardinality = d.nucleotide_cardinality;
+    p.word_cardinality = d.word_cardinality();
+    p.quality_word_cardinality = d.quality_word_cardinality();
+    p.group_cardinality = d.quality_word_cardinality();
+    p.segment_cardinality = d.segment_cardinality;
+    for(int32_t s(0); s < d.segment_cardinality && s < PHQ_MAX_SEGMENTS; ++s) {
+        uint32_t mask(0);
+        for(int32_t j(d.segment_offset[s]); j < d.segment_offset[s + 1]; ++j) { mask |= 1u << j; }
+        p.segment_mask[s] = mask;
+        p.distance_tolerance[s] = d.algorithm == PHQ_MDD ? d.distance_tolerance[s] : 0;
+    }
+    p.high_quality_threshold = d.high_quality_threshold;
+    p.high_quality_distance_threshold = d.high_quality_distance_threshold;
+    p.quality_masking_threshold = d.quality_masking_threshold;
+    p.adjusted_noise_probability = d.noise * d.random_barcode_probability;           /* pamld.cpp:29 */
+    p.confidence_threshold = d.confidence_threshold;
+    p.random_barcode_probability = d.random_barcode_probability;
+    {
+        /* sigma_q of an observation whose every position scores UNIFORM_BASE_QUALITY (barcode.h:147-163) */
+        const double U(10.0 * log10(4));
+        double y(0), t(0), sigma(0), compensation(0);
+        for(int32_t j(0); j < d.nucleotide_cardinality; ++j) {
+            y = U - compensation;
+            t = sigma + y;
+            compensation = (t - sigma) - y;
+            sigma = t;
+        }
+        p.uniform_observation_probability = pow(pow(10.0, -0.1), sigma);
+    }
+    p.barcodes = h->device_barcodes[k];
+    p.phred = h->device_phred;
+    p.acc_u64 = h->u64_plane() + h->offset_u64[k];
+    p.acc_f64 = h->f64_plane() + h->offset_f64[k];
+    p.totals = NULL;
+    p.diagnostics = h->diagnostics();
+}
+
+void destroy(phq_handle* h) {
+    if(h == NULL) { return; }
+    if(h->device < 0) { delete h; return; }
+    cudaSetDevice(h->device);
+    for(auto* p : h->device_barcodes) { if(p != NULL) { cudaFree(p); } }
+    if(h->device_phred != NULL) { cudaFree(h->device_phred); }
+    if(h->device_accumulators != NULL) { cudaFree(h->device_accumulators); }
+    if(h->slots_ready) {
+        for(auto& s : h->slot) {
+            for(auto& b : s.bases) { b.release(); }
+            for(auto& b : s.nmask) { b.release(); }
+            for(auto& b : s.quality) { b.release(); }
+            for(auto& b : s.results) { b.release(); }
+            s.qcfail.release();
+            cudaEventDestroy(s.done);
+            cudaStreamDestroy(s.stream);
+        }
+    }
+    if(h->timing_start != NULL) { cudaEventDestroy(h->timing_start); }
+    if(h->timing_stop != NULL) { cudaEventDestroy(h->timing_stop); }
+    delete h;
+}
+
+/* launch the chain on device-resident planes (TranscodingDecoder::classify order, transcode.h:51-60) */
+void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t* qcfail, phq_result* const* results, cudaStream_t stream) {
+    const size_t n_decoders(h->chain.size());
+    for(size_t k(0); k < n_decoders; ++k) {
+        DecoderParams p(h->params[k]);
+        p.totals = (k + 1 == n_decoders) ? h->totals() : NULL;
+        TileArguments a;
+        memset(&a, 0, sizeof(a));
+        a.n_reads = n_reads;
+        a.qcfail = qcfail;
+        a.results = results != NULL ? results[k] : NULL;
+        cudaError_t status(cudaSuccess);
+        if(h->chain[k].tiled()) {
+            if(tiles == NULL || tiles[k].bases == NULL || tiles[k].nmask == NULL || tiles[k].quality == NULL) {
+                throw InternalError("decoder " + std::to_string(k) + " needs a tile");
+            }
+            if(tiles[k].pitch < n_reads) { throw InternalError("tile pitch is smaller than the number of reads"); }
+            a.bases = tiles[k].bases;
+            a.nmask = tiles[k].nmask;
+            a.quality = tiles[k].quality;
+            a.pitch = tiles[k].pitch;
+            status = h->chain[k].algorithm == PHQ_PAMLD ? launch_pamld(p, a, h->geometry, stream) : launch_mdd(p, a, h->geometry, stream);
+        } else {
+            status = launch_count(p, a, h->geometry, stream);
+        }
+        PHQ_CUDA(status);
+        ++h->kernel_launches;
+    }
+}
+
+void ensure_slots(phq_handle* h) {
+    if(h->slots_ready) { return; }
+    const size_t n(h->chain.size());
+    for(auto& s : h->slot) {
+        PHQ_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        PHQ_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        s.bases.resize(n); s.nmask.resize(n); s.quality.resize(n); s.results.resize(n);
+    }
+    h->slots_ready = true;
+}
+
+template < class F > int guarded(phq_handle* h, F body) {
+    try {
+        if(h == NULL) { throw InternalError("null handle"); }
+        if(h->device < 0) { throw InternalError("this handle was created without a device (host-only); there is no CPU classification path"); }
+        PHQ_CUDA(cudaSetDevice(h->device));
+        body();
+        return PHQ_OK;
+    } catch(const phq::Error& e) {
+        if(h != NULL) { h->error = e.what(); } else { global_error = e.what(); }
+        return e.code;
+    } catch(const JsonError& e) {
+        std::string m(std::string("Configuration error : ") + e.what());
+        if(h != NULL) { h->error = m; } else { global_error = m; }
+        return PHQ_CONFIGURATION_ERROR;
+    } catch(const std::bad_alloc&) {
+        if(h != NULL) { h->error = "Out of memory error"; } else { global_error = "Out of memory error"; }
+        return PHQ_OUT_OF_MEMORY_ERROR;
+    } catch(const std::exception& e) {
+        if(h != NULL) { h->error = e.what(); } else { global_error = e.what(); }
+        return PHQ_UNKNOWN_ERROR;
+    }
+}
+
+}   /* namespace */
+
+extern "C" {
+
+const char* phq_last_global_error(void) { return global_error.c_str(); }
+const char* phq_last_error(const phq_handle* handle) { return handle != NULL ? handle->error.c_str() : global_error.c_str(); }
+void phq_free(void* pointer) { free(pointer); }
+
+int phq_compile_job(const char* job_json, char** compiled_json) {
+    try {
+        if(job_json == NULL || compiled_json == NULL) { throw InternalError("null argument"); }
+        Json compiled(compile_job(Json::parse(job_json)));
+        std::string text(compiled.dump(-1, 4));     /* shortest round-trip decimals: priors must survive the text form bit for bit */
+        char* out(static_cast< char* >(malloc(text.size() + 1)));
+        if(out == NULL) { throw phq::Error(PHQ_OUT_OF_MEMORY_ERROR, "Out of memory error"); }
+        memcpy(out, text.c_str(), text.size() + 1);
+        *compiled_json = out;
+        return PHQ_OK;
+    } catch(const phq::Error& e) { global_error = e.what(); return e.code; }
+    catch(const JsonError& e) { global_error = std::string("Configuration error : ") + e.what(); return PHQ_CONFIGURATION_ERROR; }
+    catch(const std::exception& e) { global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
+}
+
+int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
+    phq_handle* h(NULL);
+    try {
+        if(compiled_job_json == NULL || handle == NULL) { throw InternalError("null argument"); }
+        *handle = NULL;
+        std::vector< DecoderSpec > chain(parse_compiled_job(Json::parse(compiled_job_json)));
+
+        if(device < 0) {
+            /* host-only handle: configuration, phq_pack and phq_decoder_describe work; anything that
+               needs the GPU fails with an internal error. For feed threads and CPU-only tests. */
+            h = new phq_handle();
+            h->device = -1;
+            h->chain = chain;
+            h->scratch.resize(chain.size());
+            for(size_t k(0); k < chain.size(); ++k) { h->scratch[k].resize(static_cast< size_t >(chain[k].segment_cardinality)); }
+            *handle = h;
+            return PHQ_OK;
+        }
+        int device_count(0);
+        cudaError_t status(cudaGetDeviceCount(&device_count));
+        if(status != cudaSuccess || device_count < 1) {
+            throw InternalError(std::string("no usable CUDA device (") + cudaGetErrorString(status) + "); this path has no CPU fallback");
+        }
+        if(device < 0 || device >= device_count) { throw InternalError("device " + std::to_string(device) + " out of range"); }
+        PHQ_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        PHQ_CUDA(cudaGetDeviceProperties(&prop, device));
+        if(prop.major < 10) { throw InternalError(std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only"); }
+
+        h = new phq_handle();
+        h->device = device;
+        h->chain = chain;
+        h->geometry.multiprocessor_count = prop.multiProcessorCount;
+        h->geometry.shared_memory_per_block_optin = prop.sharedMemPerBlockOptin;
+        const size_t n(chain.size());
+        h->params.resize(n);
+        h->device_barcodes.assign(n, NULL);
+        h->scratch.resize(n);
+        h->offset_u64.resize(n);
+        h->offset_f64.resize(n);
+        int64_t at_u(0), at_f(0);
+        for(size_t k(0); k < n; ++k) {
+            h->scratch[k].resize(static_cast< size_t >(chain[k].segment_cardinality));
+            h->offset_u64[k] = at_u;
+            h->offset_f64[k] = at_f;
+            at_u += static_cast< int64_t >(chain[k].barcode_cardinality + 1) * ACC_U64_COLUMNS;
+            at_f += static_cast< int64_t >(chain[k].barcode_cardinality + 1) * ACC_F64_COLUMNS;
+        }
+        h->n_u64 = at_u + 4;        /* + totals count, pf_count + diagnostics exact path, threshold band */
+        h->n_f64 = at_f;
+        PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_accumulators), static_cast< size_t >(h->n_u64 + h->n_f64) * 8));
+        PHQ_CUDA(cudaMemset(h->device_accumulators, 0, static_cast< size_t >(h->n_u64 + h->n_f64) * 8));
+
+        std::vector< double > phred;
+        double uniform_quality, base;
+        assemble_phred(phred, uniform_quality, base);
+        PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_phred), phred.size() * sizeof(double)));
+        PHQ_CUDA(cudaMemcpy(h->device_phred, phred.data(), phred.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+        for(size_t k(0); k < n; ++k) {
+            if(chain[k].tiled()) {
+                PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), static_cast< size_t >(chain[k].barcode_cardinality) * sizeof(BarcodeEntry)));
+                upload_barcodes(h, k);
+            }
+            refresh_params(h, k);
+        }
+        PHQ_CUDA(cudaEventCreate(&h->timing_start));
+        PHQ_CUDA(cudaEventCreate(&h->timing_stop));
+        PHQ_CUDA(prepare_kernels(h->geometry));
+        *handle = h;
+        return PHQ_OK;
+    } catch(const phq::Error& e) { global_error = e.what(); destroy(h); return e.code; }
+    catch(const JsonError& e) { global_error = std::string("Configuration error : ") + e.what(); destroy(h); return PHQ_CONFIGURATION_ERROR; }
+    catch(const std::bad_alloc&) { global_error = "Out of memory error"; destroy(h); return PHQ_OUT_OF_MEMORY_ERROR; }
+    catch(const std::exception& e) { global_error = e.what(); destroy(h); return PHQ_UNKNOWN_ERROR; }
+}
+
+void phq_destroy(phq_handle* handle) { destroy(handle); }
+
+int phq_decoder_count(const phq_handle* handle) { return handle != NULL ? static_cast< int >(handle->chain.size()) : 0; }
+
+int phq_decoder_describe(const phq_handle* handle, int decoder, phq_decoder_info* info) {
+    if(handle == NULL || info == NULL || decoder < 0 || decoder >= static_cast< int >(handle->chain.size())) {
+        global_error = "Internal error : decoder index out of range";
+        return PHQ_INTERNAL_ERROR;
+    }
+    const DecoderSpec& d(handle->chain[decoder]);
+    memset(info, 0, sizeof(*info));
+    info->algorithm = d.algorithm;
+    info->topic = d.topic;
+    info->index = d.index;
+    info->barcode_cardinality = d.barcode_cardinality;
+    info->segment_cardinality = d.segment_cardinality;
+    info->nucleotide_cardinality = d.nucleotide_cardinality;
+    for(int32_t s(0); s < d.segment_cardinality && s < PHQ_MAX_SEGMENTS; ++s) { info->segment_length[s] = d.segment_length[s]; }
+    info->word_cardinality = d.word_cardinality();
+    info->quality_word_cardinality = d.quality_word_cardinality();
+    info->has_tile = d.tiled() ? 1 : 0;
+    return PHQ_OK;
+}
+
+int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
+             const uint8_t* const* code, const uint8_t* const* quality, const int64_t* const* offset,
+             const phq_tile* tiles) {
+    phq_handle* h(handle);
+    try {
+        if(h == NULL) { throw InternalError("null handle"); }
+        if(n_reads < 0 || tiles == NULL) { throw InternalError("illegal argument"); }
+        for(size_t k(0); k < h->chain.size(); ++k) {
+            const DecoderSpec& d(h->chain[k]);
+            if(!d.tiled()) { continue; }
+            const phq_tile& tile(tiles[k]);
+            if(tile.bases == NULL || tile.nmask == NULL || tile.quality == NULL || tile.pitch < n_reads) { throw InternalError("decoder " + std::to_string(k) + " has no host tile to pack into"); }
+            for(const auto& t : d.transform) {
+                if(t.input_segment_index >= n_input_segments) {
+                    throw ConfigurationError("invalid input feed reference " + std::to_string(t.input_segment_index) + " in token " + std::to_string(t.token_index));
+                }
+            }
+            uint32_t* out_bases(const_cast< uint32_t* >(tile.bases));
+            uint16_t* out_nmask(const_cast< uint16_t* >(tile.nmask));
+            uint32_t* out_quality(const_cast< uint32_t* >(tile.quality));
+            std::vector< ScratchSegment >& scratch(h->scratch[k]);
+            const int32_t words(d.word_cardinality());
+            const int32_t quality_words(d.quality_word_cardinality());
+            const bool stale_semantics(d.algorithm == PHQ_PAMLD);
+
+            for(int64_t r(0); r < n_reads; ++r) {
+                /* Observation::clear + Rule::apply (sequence.h:296-300, transform.h:142-169) */
+                for(auto& s : scratch) { s.length = 0; s.code[0] = 0; s.quality[0] = 0; }
+                for(const auto& t : d.transform) {
+                    const int64_t from(offset[t.input_segment_index][r]);
+                    const int32_t from_length(static_cast< int32_t >(offset[t.input_segment_index][r + 1] - from));
+                    const uint8_t* from_code(code[t.input_segment_index] + from);
+                    const uint8_t* from_quality(quality[t.input_segment_index] + from);
+                    ScratchSegment& to(scratch[t.output_segment_index]);
+                    const int32_t start(t.absolute_start(from_length));
+                    const int32_t end(t.absolute_end(from_length));
+                    const int32_t size(end - start);
+                    if(size > 0) {
+                        if(to.length + size + 1 > static_cast< int32_t >(to.code.size())) { throw SequenceError("token extracts more nucleotides than the barcode segment holds"); }
+                        if(!t.reverse_complement) {
+                            memcpy(to.code.data() + to.length, from_code + start, size);
+                            memcpy(to.quality.data() + to.length, from_quality + start, size);
+                        } else {
+                            for(int32_t i(0); i < size; ++i) {
+                                to.code[to.length + i] = BAM_REVERSE_COMPLEMENT[from_code[end - i - 1] & 0xf];
+                                to.quality[to.length + i] = from_quality[end - i - 1];
+                            }
+                        }
+                        to.length += size;
+                        to.code[to.length] = 0;
+                        to.quality[to.length] = 0;
+                    }
+                }
+                /* 2-bit planes + ambiguity mask + Phred bytes */
+                uint32_t lo(0), hi(0), ambiguous(0);
+                uint8_t phred[PHQ_MAX_NUCLEOTIDES];
+                memset(phred, 0, sizeof(phred));
+                for(int32_t s(0); s < d.segment_cardinality; ++s) {
+                    const ScratchSegment& from(scratch[s]);
+                    for(int32_t i(0); i < d.segment_length[s]; ++i) {
+                        const int32_t j(d.segment_offset[s] + i);
+                        if(!stale_semantics && i >= from.length) {
+                            phred[j] = PHQ_ABSENT_QUALITY;      /* Sequence::distance_from stops at the observed length */
+                            continue;
+                        }
+                        /* PAMLD reads the expected length: terminator, then stale bytes (barcode.h:150) */
+                        const uint8_t c(from.code[i]);
+                        switch(c) {
+                            case 1: break;
+                            case 2: lo |= 1u << j; break;
+                            case 4: hi |= 1u << j; break;
+                            case 8: lo |= 1u << j; hi |= 1u << j; break;
+                            default: ambiguous |= 1u << j; break;
+                        }
+                        phred[j] = from.quality[i];
+                    }
+                }
+                for(int32_t w(0); w < words; ++w) {
+                    out_bases[w * tile.pitch + r] = ((lo >> (16 * w)) & 0xffffu) | (((hi >> (16 * w)) & 0xffffu) << 16);
+                    out_nmask[w * tile.pitch + r] = static_cast< uint16_t >((ambiguous >> (16 * w)) & 0xffffu);
+                }
+                for(int32_t w(0); w < quality_words; ++w) {
+                    out_quality[w * tile.pitch + r] = static_cast< uint32_t >(phred[4 * w]) | (static_cast< uint32_t >(phred[4 * w + 1]) << 8)
+                        | (static_cast< uint32_t >(phred[4 * w + 2]) << 16) | (static_cast< uint32_t >(phred[4 * w + 3]) << 24);
+                }
+            }
+        }
+        return PHQ_OK;
+    } catch(const phq::Error& e) { if(h != NULL) { h->error = e.what(); } else { global_error = e.what(); } return e.code; }
+    catch(const std::exception& e) { if(h != NULL) { h->error = e.what(); } else { global_error = e.what(); } return PHQ_UNKNOWN_ERROR; }
+}
+
+int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
+                            uint8_t* device_qcfail, phq_result* const* device_results, void* stream) {
+    return guarded(handle, [&]() {
+        if(n_reads < 0 || n_reads > 0x7fffffffll) { throw OverflowError("a batch holds at most 2^31 - 1 reads"); }
+        if(device_qcfail == NULL) { throw InternalError("device_qcfail is required"); }
+        cudaStream_t s(static_cast< cudaStream_t >(stream));
+        PHQ_CUDA(cudaEventRecord(handle->timing_start, s));
+        launch_chain(handle, n_reads, device_tiles, device_qcfail, device_results, s);
+        PHQ_CUDA(cudaEventRecord(handle->timing_stop, s));
+        handle->timing_stream = s;
+        handle->timing_valid = true;
+    });
+}
+
+int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
+                     const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out) {
+    return guarded(handle, [&]() {
+        phq_handle* h(handle);
+        if(n_reads < 0) { throw InternalError("illegal read count"); }
+        ensure_slots(h);
+        const size_t n_decoders(h->chain.size());
+        const long long sub(n_reads < SUB_BATCH_READS ? (n_reads > 0 ? n_reads : 1) : SUB_BATCH_READS);
+        int turn(0);
+        for(long long begin(0); begin < n_reads; begin += sub, ++turn) {
+            const long long count((n_reads - begin) < sub ? (n_reads - begin) : sub);
+            StagingSlot& s(h->slot[turn % STAGING_SLOTS]);
+            if(turn >= STAGING_SLOTS) { PHQ_CUDA(cudaEventSynchronize(s.done)); }
+            std::vector< phq_tile > device_tiles(n_decoders);
+            std::vector< phq_result* > device_results(n_decoders, static_cast< phq_result* >(NULL));
+            s.qcfail.reserve(static_cast< size_t >(sub));
+            if(qcfail_in != NULL) { PHQ_CUDA(cudaMemcpyAsync(s.qcfail.pointer, qcfail_in + begin, static_cast< size_t >(count), cudaMemcpyHostToDevice, s.stream)); }
+            else { PHQ_CUDA(cudaMemsetAsync(s.qcfail.pointer, 0, static_cast< size_t >(count), s.stream)); }
+            for(size_t k(0); k < n_decoders; ++k) {
+                const DecoderSpec& d(h->chain[k]);
+                memset(&device_tiles[k], 0, sizeof(phq_tile));
+                if(d.tiled()) {
+                    if(tiles == NULL || tiles[k].bases == NULL) { throw InternalError("decoder " + std::to_string(k) + " needs a tile"); }
+                    const int32_t words(d.word_cardinality());
+                    const int32_t quality_words(d.quality_word_cardinality());
+                    s.bases[k].reserve(static_cast< size_t >(sub) * words);
+                    s.nmask[k].reserve(static_cast< size_t >(sub) * words);
+                    s.quality[k].reserve(static_cast< size_t >(sub) * quality_words);
+                    PHQ_CUDA(cudaMemcpy2DAsync(s.bases[k].pointer, static_cast< size_t >(sub) * 4, tiles[k].bases + begin, static_cast< size_t >(tiles[k].pitch) * 4,
+                                               static_cast< size_t >(count) * 4, words, cudaMemcpyHostToDevice, s.stream));
+                    PHQ_CUDA(cudaMemcpy2DAsync(s.nmask[k].pointer, static_cast< size_t >(sub) * 2, tiles[k].nmask + begin, static_cast< size_t >(tiles[k].pitch) * 2,
+                                               static_cast< size_t >(count) * 2, words, cudaMemcpyHostToDevice, s.stream));
+                    PHQ_CUDA(cudaMemcpy2DAsync(s.quality[k].pointer, static_cast< size_t >(sub) * 4, tiles[k].quality + begin, static_cast< size_t >(tiles[k].pitch) * 4,
+                                               static_cast< size_t >(count) * 4, quality_words, cudaMemcpyHostToDevice, s.stream));
+                    device_tiles[k].bases = s.bases[k].pointer;
+                    device_tiles[k].nmask = s.nmask[k].pointer;
+                    device_tiles[k].quality = s.quality[k].pointer;
+                    device_tiles[k].pitch = sub;
+                }
+                if(results != NULL && results[k] != NULL) {
+                    s.results[k].reserve(static_cast< size_t >(sub));
+                    device_results[k] = s.results[k].pointer;
+                }
+            }
+            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, device_results.data(), s.stream);
+            for(size_t k(0); k < n_decoders; ++k) {
+                if(device_results[k] != NULL) {
+                    PHQ_CUDA(cudaMemcpyAsync(results[k] + begin, device_results[k], static_cast< size_t >(count) * sizeof(phq_result), cudaMemcpyDeviceToHost, s.stream));
+                }
+            }
+            if(qcfail_out != NULL) { PHQ_CUDA(cudaMemcpyAsync(qcfail_out + begin, s.qcfail.pointer, static_cast< size_t >(count), cudaMemcpyDeviceToHost, s.stream)); }
+            PHQ_CUDA(cudaEventRecord(s.done, s.stream));
+        }
+        for(int i(0); i < STAGING_SLOTS && i < turn; ++i) { PHQ_CUDA(cudaStreamSynchronize(h->slot[i].stream)); }
+    });
+}
+
+int phq_host_alloc(void** pointer, size_t bytes) {
+    if(pointer == NULL) { return PHQ_INTERNAL_ERROR; }
+    cudaError_t status(cudaHostAlloc(pointer, bytes ? bytes : 1, cudaHostAllocDefault));
+    if(status != cudaSuccess) {
+        global_error = std::string("Out of memory error : ") + cudaGetErrorString(status);
+        return PHQ_OUT_OF_MEMORY_ERROR;
+    }
+    return PHQ_OK;
+}
+void phq_host_free(void* pointer) { if(pointer != NULL) { cudaFreeHost(pointer); } }
+
+int phq_accumulators(phq_handle* handle, int decoder, uint64_t* u64_table, double* f64_table) {
+    return guarded(handle, [&]() {
+        if(decoder < 0 || decoder >= static_cast< int >(handle->chain.size())) { throw InternalError("decoder index out of range"); }
+        PHQ_CUDA(cudaDeviceSynchronize());
+        const size_t rows(static_cast< size_t >(handle->chain[decoder].barcode_cardinality) + 1);
+        if(u64_table != NULL) { PHQ_CUDA(cudaMemcpy(u64_table, handle->u64_plane() + handle->offset_u64[decoder], rows * ACC_U64_COLUMNS * 8, cudaMemcpyDeviceToHost)); }
+        if(f64_table != NULL) { PHQ_CUDA(cudaMemcpy(f64_table, handle->f64_plane() + handle->offset_f64[decoder], rows * ACC_F64_COLUMNS * 8, cudaMemcpyDeviceToHost)); }
+    });
+}
+
+int phq_totals(phq_handle* handle, uint64_t* count, uint64_t* pf_count) {
+    return guarded(handle, [&]() {
+        unsigned long long t[2];
+        PHQ_CUDA(cudaDeviceSynchronize());
+        PHQ_CUDA(cudaMemcpy(t, handle->totals(), sizeof(t), cudaMemcpyDeviceToHost));
+        if(count != NULL) { *count = t[0]; }
+        if(pf_count != NULL) { *pf_count = t[1]; }
+    });
+}
+
+int phq_accumulator_buffer(phq_handle* handle, void** device_pointer, int64_t* n_u64, int64_t* n_f64) {
+    return guarded(handle, [&]() {
+        if(device_pointer != NULL) { *device_pointer = handle->device_accumulators; }
+        if(n_u64 != NULL) { *n_u64 = handle->n_u64; }
+        if(n_f64 != NULL) { *n_f64 = handle->n_f64; }
+    });
+}
+
+int phq_reset_accumulators(phq_handle* handle) {
+    return guarded(handle, [&]() {
+        PHQ_CUDA(cudaDeviceSynchronize());
+        PHQ_CUDA(cudaMemset(handle->device_accumulators, 0, static_cast< size_t >(handle->n_u64 + handle->n_f64) * 8));
+    });
+}
+
+int phq_estimate_priors(phq_handle* handle, int decoder, double* estimated_noise, double* estimated_concentration) {
+    return guarded(handle, [&]() {
+        if(decoder < 0 || decoder >= static_cast< int >(handle->chain.size())) { throw InternalError("decoder index out of range"); }
+        const int32_t N(handle->chain[decoder].barcode_cardinality);
+        std::vector< uint64_t > u(static_cast< size_t >(N + 1) * ACC_U64_COLUMNS);
+        PHQ_CUDA(cudaDeviceSynchronize());
+        PHQ_CUDA(cudaMemcpy(u.data(), handle->u64_plane() + handle->offset_u64[decoder], u.size() * 8, cudaMemcpyDeviceToHost));
+        /* PamlDecoder::finalize (pamld.h:40-48) and Classifier::finalize (classifier.h:94-124) */
+        uint64_t classified_count(0), pf_classified_count(0), low_conditional_confidence_count(0), low_confidence_count(0);
+        for(int32_t i(1); i <= N; ++i) {
+            classified_count += u[i * ACC_U64_COLUMNS + ACC_COUNT];
+            pf_classified_count += u[i * ACC_U64_COLUMNS + ACC_PF_COUNT];
+            if(handle->chain[decoder].algorithm == PHQ_PAMLD) {
+                low_conditional_confidence_count += u[i * ACC_U64_COLUMNS + ACC_LOW_CONDITIONAL];
+                low_confidence_count += u[i * ACC_U64_COLUMNS + ACC_LOW_CONFIDENCE];
+            }
+        }
+        const uint64_t count(classified_count + u[ACC_COUNT]);
+        double estimated_noise_count(low_conditional_confidence_count);
+        double confident_noise_ratio(estimated_noise_count / (estimated_noise_count + pf_classified_count));
+        if(low_confidence_count > 0) {
+            estimated_noise_count += double(low_confidence_count) * confident_noise_ratio;
+        }
+        const double estimated_noise_prior(estimated_noise_count / double(count));
+        const double estimated_not_noise_prior(1.0 - estimated_noise_prior);
+        if(estimated_noise != NULL) { *estimated_noise = estimated_noise_prior; }
+        if(estimated_concentration != NULL) {
+            for(int32_t i(1); i <= N; ++i) {
+                double pf_pooled_classified_fraction(0);
+                const uint64_t pf_count(u[i * ACC_U64_COLUMNS + ACC_PF_COUNT]);
+                if(pf_count > 0 && pf_classified_count > 0) {                      /* selector.cpp:87-99 */
+                    pf_pooled_classified_fraction = double(pf_count) / double(pf_classified_count);
+                }
+                estimated_concentration[i - 1] = estimated_not_noise_prior * pf_pooled_classified_fraction;
+            }
+        }
+    });
+}
+
+int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* concentration) {
+    return guarded(handle, [&]() {
+        if(decoder < 0 || decoder >= static_cast< int >(handle->chain.size())) { throw InternalError("decoder index out of range"); }
+        DecoderSpec& d(handle->chain[decoder]);
+        if(!d.tiled()) { throw ConfigurationError("decoder has no priors"); }
+        if(noise < 0 || noise > 1) { throw ConfigurationError("noise value " + std::to_string(noise) + " not between 0 and 1"); }
+        d.noise = noise;
+        if(concentration != NULL) {
+            for(int32_t i(0); i < d.barcode_cardinality; ++i) { d.concentration[i] = concentration[i]; }
+        }
+        PHQ_CUDA(cudaDeviceSynchronize());
+        upload_barcodes(handle, static_cast< size_t >(decoder));
+        refresh_params(handle, static_cast< size_t >(decoder));
+    });
+}
+
+int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exact_path_reads, uint64_t* threshold_band_reads) {
+    return guarded(handle, [&]() {
+        unsigned long long d[2];
+        PHQ_CUDA(cudaDeviceSynchronize());
+        PHQ_CUDA(cudaMemcpy(d, handle->diagnostics(), sizeof(d), cudaMemcpyDeviceToHost));
+        if(kernel_launches != NULL) { *kernel_launches = handle->kernel_launches; }
+        if(exact_path_reads != NULL) { *exact_path_reads = d[DIAG_EXACT_PATH]; }
+        if(threshold_band_reads != NULL) { *threshold_band_reads = d[DIAG_THRESHOLD_BAND]; }
+    });
+}
+
+int phq_last_kernel_milliseconds(phq_handle* handle, float* milliseconds) {
+    return guarded(handle, [&]() {
+        if(!handle->timing_valid) { throw InternalError("no device batch has been decoded yet"); }
+        PHQ_CUDA(cudaEventSynchronize(handle->timing_stop));
+        PHQ_CUDA(cudaEventElapsedTime(milliseconds, handle->timing_start, handle->timing_stop));
+    });
+}
+
+}   /* extern "C" */

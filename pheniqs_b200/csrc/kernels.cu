@@ -1,0 +1,749 @@
+/*  kernels.cu — hand-written sm_100a kernels of the barcode classification path.
+
+    pamld_kernel   PamlDecoder::classify (pamld.cpp:37-123) with Barcode::compensated_decoding_probability
+                   (barcode.h:131-164), Decoder::classify (decoder.h:68-76) and Classifier::classify
+                   (classifier.h:78-86) for a batch of reads against every barcode of one decoder.
+    mdd_kernel     MdDecoder::classify (mdd.cpp:37-86) with Sequence::distance_from /
+                   ObservedSequence::masked_distance_from (sequence.h:90-98, 321-332).
+    count_kernel   the bookkeeping NaiveMolecularDecoder / passthrough classifiers do (naive.h:40-45).
+
+    Design (DESIGN.md has the long form). One lane owns one read; the barcode table streams
+    through shared memory in 16 KB chunks moved by TMA bulk copies (cp.async.bulk + mbarrier),
+    so every barcode word is a warp-uniform broadcast read. Bases are two 32-position bit
+    planes, so the mismatch mask of a (read, barcode) pair is two LOP3s:
+
+        m = (o_lo ^ e_lo) | (o_hi ^ e_hi) | n_mask
+
+    PAMLD never evaluates pow() per pair. With B = 10^-0.1 the reference's
+
+        P(r|b) = B ^ sum_j s(e_j, o_j, q_j)
+
+    factors into a per-read constant P0 = prod_j B^s(match) times prod_{j in m} w_j with
+    w_j = B^(q_j - tq[q_j]) (1 for N / q = 0 positions), and the product over the mismatch set
+    is looked up four positions at a time in a per-lane table of the 16 subset products held in
+    shared memory ([entry][lane] layout: conflict free). All probability arithmetic is f64.
+    The first-maximum selection of the reference (strict >) is done on the high words of the
+    f64 products; whenever the runner-up is within 2^-19 of the winner (structural ties, which
+    the reference resolves by the rounding of its position-ordered Kahan sums) the warp
+    re-evaluates that read cooperatively with the reference's exact operation order.
+*/
+#include "kernels.cuh"
+
+namespace phq {
+
+namespace {
+
+constexpr int WARP_SIZE = 32;
+constexpr int MAX_WARPS = 12;
+constexpr int STAGE_ENTRIES = 1024;             /* barcodes per staged chunk: 16 KB */
+constexpr int SHARED_ACCUMULATOR_ROWS = 1025;   /* per-CTA accumulators live in shared memory up to N + 1 = 1025 rows */
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+/* ------------------------------------------------------------------ shared memory plan (host and device agree) */
+struct SharedPlan {
+    int stage_capacity;         /* entries per stage buffer */
+    int stage_buffers;          /* 1 when the whole table fits one chunk, else 2 */
+    int accumulator_rows;       /* N + 1 when accumulators are staged in shared memory, else 0 */
+    unsigned off_stage, off_phred, off_acc_f64, off_acc_u32, off_misc, off_mbarrier, off_tables;
+    unsigned fixed_bytes;       /* everything except the per-warp tables */
+};
+__host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool phred_tables) {
+    SharedPlan p;
+    p.stage_capacity = barcode_cardinality < STAGE_ENTRIES ? barcode_cardinality : STAGE_ENTRIES;
+    p.stage_buffers = barcode_cardinality <= STAGE_ENTRIES ? 1 : 2;
+    p.accumulator_rows = (barcode_cardinality + 1 <= SHARED_ACCUMULATOR_ROWS) ? barcode_cardinality + 1 : 0;
+    unsigned at = 0;
+    p.off_stage = at;       at += align_up(unsigned(p.stage_capacity) * unsigned(p.stage_buffers) * 16u, 128u);
+    p.off_phred = at;       at += phred_tables ? 256u * 8u : 0u;
+    p.off_acc_f64 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_F64_COLUMNS * 8u, 16u);
+    p.off_acc_u32 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_U64_COLUMNS * 4u, 16u);
+    p.off_misc = at;        at += 16u;          /* totals count, pf_count; diagnostics exact, band */
+    p.off_mbarrier = at;    at += 16u;
+    p.off_tables = align_up(at, 256u);
+    p.fixed_bytes = p.off_tables;
+    return p;
+}
+
+/* ------------------------------------------------------------------ PTX helpers: mbarrier + TMA bulk copy */
+__device__ __forceinline__ uint32_t shared_address(const void* p) { return static_cast< uint32_t >(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(shared_address(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbarrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(shared_address(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(shared_address(bar)), "r"(parity) : "memory");
+}
+/* 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier */
+__device__ __forceinline__ void tma_bulk_load(void* destination, const void* source, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(shared_address(destination)), "l"(source), "r"(bytes), "r"(shared_address(bar)) : "memory");
+}
+
+/* streaming loads / stores: tiles and results are touched once */
+__device__ __forceinline__ uint32_t load_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t load_stream(const uint16_t* p) { return static_cast< uint32_t >(__ldcs(reinterpret_cast< const unsigned short* >(p))); }
+__device__ __forceinline__ void store_result(phq_result* results, long long r, int32_t index, int32_t distance, double confidence) {
+    int4 v;
+    v.x = index;
+    v.y = distance;
+    v.z = __double2loint(confidence);
+    v.w = __double2hiint(confidence);
+    __stcs(reinterpret_cast< int4* >(results) + r, v);
+}
+
+/* ------------------------------------------------------------------ per-CTA accumulators
+   AccumulatingOption (selector.h:32-60). Staged in shared memory (u32 counters, f64 sums) when the
+   table is small, flushed with one global atomic per non-zero cell; straight to global otherwise. */
+struct Accumulator {
+    uint32_t* shared_u32;
+    double* shared_f64;
+    unsigned long long* global_u64;
+    double* global_f64;
+    __device__ __forceinline__ void add(int row, int column, uint32_t value) const {
+        if(shared_u32 != nullptr) { atomicAdd(&shared_u32[row * ACC_U64_COLUMNS + column], value); }
+        else { atomicAdd(&global_u64[static_cast< long long >(row) * ACC_U64_COLUMNS + column], static_cast< unsigned long long >(value)); }
+    }
+    __device__ __forceinline__ void add(int row, int column, double value) const {
+        if(shared_f64 != nullptr) { atomicAdd(&shared_f64[row * ACC_F64_COLUMNS + column], value); }
+        else { atomicAdd(&global_f64[static_cast< long long >(row) * ACC_F64_COLUMNS + column], value); }
+    }
+};
+
+struct BlockState {
+    SharedPlan plan;
+    BarcodeEntry* stage;
+    double* phred;
+    uint32_t* misc;             /* [0] count [1] pf_count [2] exact path [3] band */
+    uint64_t* mbarrier;
+    Accumulator accumulator;
+};
+
+__device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const DecoderParams& P, bool phred_tables) {
+    BlockState s;
+    s.plan = make_plan(P.barcode_cardinality, phred_tables);
+    s.stage = reinterpret_cast< BarcodeEntry* >(smem + s.plan.off_stage);
+    s.phred = reinterpret_cast< double* >(smem + s.plan.off_phred);
+    s.misc = reinterpret_cast< uint32_t* >(smem + s.plan.off_misc);
+    s.mbarrier = reinterpret_cast< uint64_t* >(smem + s.plan.off_mbarrier);
+    s.accumulator.global_u64 = P.acc_u64;
+    s.accumulator.global_f64 = P.acc_f64;
+    s.accumulator.shared_u32 = s.plan.accumulator_rows ? reinterpret_cast< uint32_t* >(smem + s.plan.off_acc_u32) : nullptr;
+    s.accumulator.shared_f64 = s.plan.accumulator_rows ? reinterpret_cast< double* >(smem + s.plan.off_acc_f64) : nullptr;
+
+    const int tid = threadIdx.x;
+    if(phred_tables) {
+        for(int i = tid; i < 256; i += blockDim.x) { s.phred[i] = P.phred[i]; }
+    }
+    for(int i = tid; i < s.plan.accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) { s.accumulator.shared_u32[i] = 0; }
+    for(int i = tid; i < s.plan.accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) { s.accumulator.shared_f64[i] = 0.0; }
+    if(tid < 4) { s.misc[tid] = 0; }
+    if(tid == 0) {
+        mbarrier_init(&s.mbarrier[0], 1);
+        mbarrier_init(&s.mbarrier[1], 1);
+        fence_mbarrier_init();
+    }
+    __syncthreads();
+    return s;
+}
+
+__device__ __forceinline__ void block_epilogue(const BlockState& s, const DecoderParams& P) {
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for(int i = tid; i < s.plan.accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) {
+        const uint32_t v = s.accumulator.shared_u32[i];
+        if(v) { atomicAdd(&P.acc_u64[i], static_cast< unsigned long long >(v)); }
+    }
+    for(int i = tid; i < s.plan.accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) {
+        const double v = s.accumulator.shared_f64[i];
+        if(v != 0.0) { atomicAdd(&P.acc_f64[i], v); }
+    }
+    if(tid < 2 && P.totals != nullptr && s.misc[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(s.misc[tid])); }
+    if(tid >= 2 && tid < 4 && P.diagnostics != nullptr && s.misc[tid]) { atomicAdd(&P.diagnostics[tid - 2], static_cast< unsigned long long >(s.misc[tid])); }
+}
+
+/* the barcode table as a sequence of TMA-staged chunks; `iteration` counts chunks over the whole CTA lifetime */
+struct BarcodeStream {
+    const BlockState& s;
+    const DecoderParams& P;
+    int chunk_cardinality;
+    __device__ __forceinline__ BarcodeStream(const BlockState& s, const DecoderParams& P) : s(s), P(P) {
+        chunk_cardinality = (P.barcode_cardinality + s.plan.stage_capacity - 1) / s.plan.stage_capacity;
+    }
+    __device__ __forceinline__ int count(int chunk) const {
+        const int remaining = P.barcode_cardinality - chunk * s.plan.stage_capacity;
+        return remaining < s.plan.stage_capacity ? remaining : s.plan.stage_capacity;
+    }
+    /* one elected thread: arm the barrier of the buffer with the byte count and start the bulk copy */
+    __device__ __forceinline__ void issue(unsigned iteration) const {
+        const int chunk = iteration % chunk_cardinality;
+        const int buffer = (s.plan.stage_buffers == 1) ? 0 : (iteration & 1u);
+        const uint32_t bytes = static_cast< uint32_t >(count(chunk)) * 16u;
+        mbarrier_expect_tx(&s.mbarrier[buffer], bytes);
+        tma_bulk_load(s.stage + static_cast< size_t >(buffer) * s.plan.stage_capacity,
+                      P.barcodes + static_cast< size_t >(chunk) * s.plan.stage_capacity, bytes, &s.mbarrier[buffer]);
+    }
+    __device__ __forceinline__ const BarcodeEntry* wait(unsigned iteration) const {
+        const int buffer = (s.plan.stage_buffers == 1) ? 0 : (iteration & 1u);
+        const uint32_t use = (s.plan.stage_buffers == 1) ? iteration : (iteration >> 1);
+        mbarrier_wait(&s.mbarrier[buffer], use & 1u);
+        return s.stage + static_cast< size_t >(buffer) * s.plan.stage_capacity;
+    }
+};
+
+/* ------------------------------------------------------------------ PAMLD exact tie path
+   One read (broadcast from lane `source`) against all barcodes, 32 barcodes per step. Barcodes whose
+   prior adjusted probability is within 2^-18 of the best are re-evaluated the way the reference does:
+   sigma_q is the position ordered Kahan sum of the substitution lookup (barcode.h:147-162,
+   phred.cpp:39-72), bit for bit. Among equal priors the smaller sigma wins and equal sigmas keep the
+   first index, which is what strict > over p = pow(B, sigma) * prior yields (pamld.cpp:68-79). */
+struct Candidate {
+    double prior;
+    double sigma;
+    double probability;     /* pow(B, sigma) * prior with the device pow: only consulted across different priors */
+    int index;              /* -1 = none */
+};
+__device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b) {
+    if(a.index < 0) { return false; }
+    if(b.index < 0) { return true; }
+    if(a.prior == b.prior) {
+        return a.sigma < b.sigma || (a.sigma == b.sigma && a.index < b.index);
+    }
+    return a.probability > b.probability || (a.probability == b.probability && a.index < b.index);
+}
+
+template < int G >
+__device__ __noinline__ int resolve_exact(const DecoderParams& P, const double* __restrict__ phred_shared,
+                                          uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t (&quality)[G], double threshold) {
+    const int lane = threadIdx.x & 31;
+    const int L = P.nucleotide_cardinality;
+    const double* __restrict__ tq = P.phred + PHRED_TRUE_POSITIVE_QUALITY;
+    const double U = P.phred[PHRED_UNIFORM_QUALITY];
+    const double B = P.phred[PHRED_BASE];
+    Candidate best;
+    best.prior = 0; best.sigma = 0; best.probability = 0; best.index = -1;
+
+    for(int base = 0; base < P.barcode_cardinality; base += WARP_SIZE) {
+        const int b = base + lane;
+        if(b < P.barcode_cardinality) {
+            const BarcodeEntry e = P.barcodes[b];
+            const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
+            double t = 1.0;
+            #pragma unroll
+            for(int g = 0; g < G; ++g) {
+                #pragma unroll
+                for(int k = 0; k < 4; ++k) {
+                    const int j = g * 4 + k;
+                    uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
+                    q = q > 127u ? 127u : q;
+                    const bool plain = ((nmask >> j) & 1u) == 0u && q != 0u;
+                    if(((m >> j) & 1u) && plain) { t *= phred_shared[PHRED_MISMATCH_RATIO + q]; }
+                }
+            }
+            const double p = t * e.prior;
+            if(p >= threshold) {
+                double sigma = 0.0, compensation = 0.0;
+                #pragma unroll
+                for(int g = 0; g < G; ++g) {
+                    #pragma unroll
+                    for(int k = 0; k < 4; ++k) {
+                        const int j = g * 4 + k;
+                        if(j < L) {
+                            uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
+                            q = q > 127u ? 127u : q;
+                            double value;
+                            if(q == 0u) { value = 0.0; }
+                            else if((nmask >> j) & 1u) { value = U; }
+                            else if((m >> j) & 1u) { value = static_cast< double >(q); }
+                            else { value = tq[q]; }
+                            const double y = __dsub_rn(value, compensation);
+                            const double s = __dadd_rn(sigma, y);
+                            compensation = __dsub_rn(__dsub_rn(s, sigma), y);
+                            sigma = s;
+                        }
+                    }
+                }
+                Candidate c;
+                c.prior = e.prior;
+                c.sigma = sigma;
+                c.probability = pow(B, sigma) * e.prior;
+                c.index = b;
+                if(beats(c, best)) { best = c; }
+            }
+        }
+    }
+    #pragma unroll
+    for(int offset = 16; offset > 0; offset >>= 1) {
+        Candidate other;
+        other.prior = __shfl_xor_sync(FULL_MASK, best.prior, offset);
+        other.sigma = __shfl_xor_sync(FULL_MASK, best.sigma, offset);
+        other.probability = __shfl_xor_sync(FULL_MASK, best.probability, offset);
+        other.index = __shfl_xor_sync(FULL_MASK, best.index, offset);
+        if(beats(other, best)) { best = other; }
+    }
+    return best.index;
+}
+
+/* ------------------------------------------------------------------ PAMLD */
+template < int G >
+__global__ void __launch_bounds__(MAX_WARPS * WARP_SIZE, 1)
+pamld_kernel(const DecoderParams P, const TileArguments A) {
+    extern __shared__ __align__(256) unsigned char smem[];
+    const BlockState S = block_prologue(smem, P, true);
+    const BarcodeStream stream(S, P);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    /* per-lane subset product tables: entry (g, subset) of this lane at [(g * 16 + subset) * 32 + lane] */
+    double* const table = reinterpret_cast< double* >(smem + S.plan.off_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE) + lane;
+    const double* const match_factor = S.phred + PHRED_MATCH_FACTOR;
+    const double* const mismatch_ratio = S.phred + PHRED_MISMATCH_RATIO;
+    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
+    const int L = P.nucleotide_cardinality;
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * stream.chunk_cardinality;
+    unsigned iteration = 0;
+    if(tid == 0 && total_iterations > 0) { stream.issue(0); }
+    const bool resident = stream.chunk_cardinality == 1;     /* whole table staged once */
+    const BarcodeEntry* resident_stage = nullptr;
+    if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
+
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+
+        /* ---- load the observation of this lane's read */
+        uint32_t o_lo = 0, o_hi = 0, nmask = 0;
+        uint32_t quality[G];
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { quality[g] = 0; }
+        uint32_t qcfail = 0;
+        if(valid) {
+            const uint32_t w0 = load_stream(A.bases + r);
+            o_lo = w0 & 0xffffu;
+            o_hi = w0 >> 16;
+            nmask = load_stream(A.nmask + r);
+            if(G > 4) {
+                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
+                o_lo |= w1 << 16;
+                o_hi |= w1 & 0xffff0000u;
+                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
+            }
+            #pragma unroll
+            for(int g = 0; g < G; ++g) { quality[g] = load_stream(A.quality + g * A.pitch + r); }
+            qcfail = A.qcfail[r];
+        }
+
+        /* ---- per-read constant P0, subset product tables, high quality mask */
+        double base_probability = 1.0;
+        uint32_t high_quality_mask = 0;
+        int uniform_positions = 0;
+        #pragma unroll
+        for(int g = 0; g < G; ++g) {
+            double w[4];
+            #pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                const int j = g * 4 + k;
+                uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
+                if(static_cast< int >(q) >= P.high_quality_threshold) { high_quality_mask |= 1u << j; }
+                q = q > 127u ? 127u : q;
+                const bool ambiguous = (nmask >> j) & 1u;
+                double factor = match_factor[q];
+                double ratio = mismatch_ratio[q];
+                if(ambiguous && q != 0u) { factor = uniform_factor; ++uniform_positions; }
+                if(ambiguous) { ratio = 1.0; }
+                base_probability *= factor;
+                w[k] = ratio;
+            }
+            double* const t = table + g * 16 * WARP_SIZE;
+            const double w01 = w[0] * w[1];
+            const double w02 = w[0] * w[2];
+            const double w12 = w[1] * w[2];
+            const double w012 = w01 * w[2];
+            t[0 * WARP_SIZE] = 1.0;
+            t[1 * WARP_SIZE] = w[0];
+            t[2 * WARP_SIZE] = w[1];
+            t[3 * WARP_SIZE] = w01;
+            t[4 * WARP_SIZE] = w[2];
+            t[5 * WARP_SIZE] = w02;
+            t[6 * WARP_SIZE] = w12;
+            t[7 * WARP_SIZE] = w012;
+            t[8 * WARP_SIZE] = w[3];
+            t[9 * WARP_SIZE] = w[0] * w[3];
+            t[10 * WARP_SIZE] = w[1] * w[3];
+            t[11 * WARP_SIZE] = w01 * w[3];
+            t[12 * WARP_SIZE] = w[2] * w[3];
+            t[13 * WARP_SIZE] = w02 * w[3];
+            t[14 * WARP_SIZE] = w12 * w[3];
+            t[15 * WARP_SIZE] = w012 * w[3];
+        }
+        high_quality_mask &= (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+        __syncwarp();
+
+        /* ---- score every barcode: sum of prior adjusted probabilities and first maximum */
+        double sum = 0.0;
+        int best_high = 0, second_high = 0, best_index = 0;
+        for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
+            const BarcodeEntry* stage;
+            if(resident) {
+                stage = resident_stage;
+            } else {
+                if(tid == 0 && iteration + 1 < total_iterations) { stream.issue(iteration + 1); }
+                stage = stream.wait(iteration);
+            }
+            const int count = stream.count(chunk);
+            const int first = chunk * S.plan.stage_capacity;
+            #pragma unroll 4
+            for(int i = 0; i < count; ++i) {
+                const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
+                const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
+                double t = table[(m & 15u) * WARP_SIZE];
+                #pragma unroll
+                for(int g = 1; g < G; ++g) {
+                    t *= table[(g * 16 + ((m >> (4 * g)) & 15u)) * WARP_SIZE];
+                }
+                const double p = t * __hiloint2double(raw.w, raw.z);
+                sum += p;
+                const int high = __double2hiint(p);
+                const bool greater = high > best_high;
+                second_high = max(second_high, greater ? best_high : high);
+                best_index = greater ? first + i : best_index;
+                best_high = max(best_high, high);
+            }
+            if(!resident) {
+                __syncthreads();
+                ++iteration;
+            }
+        }
+
+        /* ---- structural ties: exact re-evaluation, one flagged read at a time, whole warp cooperating */
+        const bool tied = valid && (second_high + 1 >= best_high);
+        unsigned pending = __ballot_sync(FULL_MASK, tied);
+        if(pending) {
+            if(lane == 0) { atomicAdd(&S.misc[2], static_cast< uint32_t >(__popc(pending))); }
+            while(pending) {
+                const int source = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t s_lo = __shfl_sync(FULL_MASK, o_lo, source);
+                const uint32_t s_hi = __shfl_sync(FULL_MASK, o_hi, source);
+                const uint32_t s_nmask = __shfl_sync(FULL_MASK, nmask, source);
+                uint32_t s_quality[G];
+                #pragma unroll
+                for(int g = 0; g < G; ++g) { s_quality[g] = __shfl_sync(FULL_MASK, quality[g], source); }
+                const int s_high = __shfl_sync(FULL_MASK, best_high, source);
+                /* lower bound of the best product, widened by 2^-18 */
+                const double threshold = __hiloint2double(s_high, 0) * (1.0 - 3.814697265625e-06);
+                const int winner = resolve_exact< G >(P, S.phred, s_lo, s_hi, s_nmask, s_quality, threshold);
+                if(lane == source && winner >= 0) { best_index = winner; }
+            }
+        }
+
+        /* ---- decision for this lane's read (pamld.cpp:87-122) */
+        if(valid) {
+            const BarcodeEntry e = P.barcodes[best_index];
+            const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
+            double t = table[(m & 15u) * WARP_SIZE];
+            #pragma unroll
+            for(int g = 1; g < G; ++g) {
+                t *= table[(g * 16 + ((m >> (4 * g)) & 15u)) * WARP_SIZE];
+            }
+            /* when every position scores UNIFORM_BASE_QUALITY all barcodes share sigma = L x U and the
+               reference's P(r|b) is the host libm constant */
+            const bool uniform = uniform_positions == L;
+            if(uniform) { base_probability = P.uniform_observation_probability; }
+            const double conditional_probability = base_probability * t;
+            const double p = conditional_probability * e.prior;
+            const double sigma_p = base_probability * sum + P.adjusted_noise_probability;
+            double confidence = p / sigma_p;
+            int distance = __popc(m);
+            const int high_quality_distance = __popc(m & high_quality_mask);
+            int decoded = best_index + 1;
+            const int best_row = best_index + 1;
+
+            bool band = fabs(confidence - P.confidence_threshold) <= 1e-12;
+            if(!uniform) { band = band || fabs(conditional_probability - P.random_barcode_probability) <= 1e-12 * P.random_barcode_probability; }
+            if(band) { atomicAdd(&S.misc[3], 1u); }
+
+            if(conditional_probability > P.random_barcode_probability) {
+                if(confidence > P.confidence_threshold) {
+                    S.accumulator.add(best_row, ACC_CONFIDENCE, confidence);
+                    if(P.high_quality_distance_threshold > 0 && high_quality_distance >= P.high_quality_distance_threshold) { qcfail = 1; }
+                    if(!qcfail) { S.accumulator.add(best_row, ACC_PF_CONFIDENCE, confidence); }
+                } else {
+                    S.accumulator.add(best_row, ACC_LOW_CONFIDENCE, 1u);
+                    qcfail = 1;
+                }
+            } else {
+                S.accumulator.add(best_row, ACC_LOW_CONDITIONAL, 1u);
+                qcfail = 1;
+                decoded = 0;
+                distance = 0;
+                confidence = 0.0;
+            }
+            /* Decoder::classify (decoder.h:68-76), Classifier::classify (classifier.h:78-86) */
+            if(decoded > 0 && distance > 0) {
+                S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
+                if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
+            }
+            S.accumulator.add(decoded, ACC_COUNT, 1u);
+            if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
+
+            A.qcfail[r] = static_cast< uint8_t >(qcfail);
+            if(A.results != nullptr) { store_result(A.results, r, decoded, distance, confidence); }
+        }
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, valid);
+            const unsigned pass = __ballot_sync(FULL_MASK, valid && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
+            }
+        }
+        __syncwarp();
+    }
+    block_epilogue(S, P);
+}
+
+/* ------------------------------------------------------------------ MDD */
+template < int SEGMENTS >      /* 0 = run-time segment count */
+__global__ void __launch_bounds__(MAX_WARPS * WARP_SIZE, 2)
+mdd_kernel(const DecoderParams P, const TileArguments A) {
+    extern __shared__ __align__(256) unsigned char smem[];
+    const BlockState S = block_prologue(smem, P, false);
+    const BarcodeStream stream(S, P);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int L = P.nucleotide_cardinality;
+    const int segment_cardinality = SEGMENTS > 0 ? SEGMENTS : P.segment_cardinality;
+    const uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * stream.chunk_cardinality;
+    unsigned iteration = 0;
+    if(tid == 0 && total_iterations > 0) { stream.issue(0); }
+    const bool resident = stream.chunk_cardinality == 1;
+    const BarcodeEntry* resident_stage = nullptr;
+    if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
+
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+        uint32_t o_lo = 0, o_hi = 0, nmask = 0, present = 0, masked = 0, qcfail = 0;
+        if(valid) {
+            const uint32_t w0 = load_stream(A.bases + r);
+            o_lo = w0 & 0xffffu;
+            o_hi = w0 >> 16;
+            nmask = load_stream(A.nmask + r);
+            if(P.word_cardinality > 1) {
+                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
+                o_lo |= w1 << 16;
+                o_hi |= w1 & 0xffff0000u;
+                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
+            }
+            for(int g = 0; g < P.quality_word_cardinality; ++g) {
+                const uint32_t qw = load_stream(A.quality + g * A.pitch + r);
+                #pragma unroll
+                for(int k = 0; k < 4; ++k) {
+                    const uint32_t q = (qw >> (8 * k)) & 0xffu;
+                    const int j = g * 4 + k;
+                    if(q != PHQ_ABSENT_QUALITY) { present |= 1u << j; }
+                    if(static_cast< int >(q) < P.quality_masking_threshold) { masked |= 1u << j; }
+                }
+            }
+            present &= all_positions;
+            masked &= present;
+            if(P.quality_masking_threshold <= 0) { masked = 0; }
+            qcfail = A.qcfail[r];
+        }
+        const bool complete = present == all_positions;
+
+        /* exact match first (mdd.cpp:44-46), else the first barcode within tolerance in every segment (mdd.cpp:50-80) */
+        int exact_index = -1, found_index = -1, found_distance = 0;
+        for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
+            const BarcodeEntry* stage;
+            if(resident) {
+                stage = resident_stage;
+            } else {
+                if(tid == 0 && iteration + 1 < total_iterations) { stream.issue(iteration + 1); }
+                stage = stream.wait(iteration);
+            }
+            const int count = stream.count(chunk);
+            const int first = chunk * S.plan.stage_capacity;
+            #pragma unroll 4
+            for(int i = 0; i < count; ++i) {
+                const uint2 raw = *reinterpret_cast< const uint2* >(stage + i);
+                const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
+                const uint32_t error = (m | masked) & present;
+                bool within = true;
+                #pragma unroll
+                for(int s = 0; s < (SEGMENTS > 0 ? SEGMENTS : PHQ_MAX_SEGMENTS); ++s) {
+                    if(s < segment_cardinality) {
+                        within = within && (__popc(error & P.segment_mask[s]) <= P.distance_tolerance[s]);
+                    }
+                }
+                if(complete && m == 0u && exact_index < 0) { exact_index = first + i; }
+                if(within && found_index < 0) { found_index = first + i; found_distance = __popc(error); }
+            }
+            if(!resident) {
+                __syncthreads();
+                ++iteration;
+            }
+        }
+
+        if(valid) {
+            int decoded = 0, distance = 0;
+            if(exact_index >= 0) { decoded = exact_index + 1; }
+            else if(found_index >= 0) { decoded = found_index + 1; distance = found_distance; }
+            if(decoded == 0) { qcfail = 1; }
+            if(decoded > 0 && distance > 0) {
+                S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
+                if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
+            }
+            S.accumulator.add(decoded, ACC_COUNT, 1u);
+            if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
+            A.qcfail[r] = static_cast< uint8_t >(qcfail);
+            if(A.results != nullptr) { store_result(A.results, r, decoded, distance, 0.0); }
+        }
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, valid);
+            const unsigned pass = __ballot_sync(FULL_MASK, valid && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
+            }
+        }
+    }
+    block_epilogue(S, P);
+}
+
+/* ------------------------------------------------------------------ naive / passthrough bookkeeping */
+__global__ void __launch_bounds__(256)
+count_kernel(const DecoderParams P, const TileArguments A) {
+    __shared__ unsigned long long block_count[2];
+    if(threadIdx.x < 2) { block_count[threadIdx.x] = 0; }
+    __syncthreads();
+    unsigned long long live = 0, pass = 0;
+    for(long long r = static_cast< long long >(blockIdx.x) * blockDim.x + threadIdx.x; r < A.n_reads; r += static_cast< long long >(gridDim.x) * blockDim.x) {
+        ++live;
+        if(!A.qcfail[r]) { ++pass; }
+        if(A.results != nullptr) { store_result(A.results, r, 0, 0, 0.0); }
+    }
+    #pragma unroll
+    for(int offset = 16; offset > 0; offset >>= 1) {
+        live += __shfl_xor_sync(FULL_MASK, live, offset);
+        pass += __shfl_xor_sync(FULL_MASK, pass, offset);
+    }
+    if((threadIdx.x & 31) == 0) {
+        atomicAdd(&block_count[0], live);
+        atomicAdd(&block_count[1], pass);
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        if(P.acc_u64 != nullptr) {
+            if(block_count[0]) { atomicAdd(&P.acc_u64[ACC_COUNT], block_count[0]); }
+            if(block_count[1]) { atomicAdd(&P.acc_u64[ACC_PF_COUNT], block_count[1]); }
+        }
+        if(P.totals != nullptr) {
+            if(block_count[0]) { atomicAdd(&P.totals[0], block_count[0]); }
+            if(block_count[1]) { atomicAdd(&P.totals[1], block_count[1]); }
+        }
+    }
+}
+
+template < int G >
+cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    const SharedPlan plan = make_plan(params.barcode_cardinality, true);
+    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double);
+    if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
+    warps = warps > MAX_WARPS ? MAX_WARPS : warps;
+    const size_t bytes = plan.fixed_bytes + per_warp * warps;
+    cudaError_t status = cudaFuncSetAttribute(pamld_kernel< G >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    if(status != cudaSuccess) { return status; }
+    const int threads = warps * WARP_SIZE;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
+    pamld_kernel< G ><<< grid, threads, bytes, stream >>>(params, tile);
+    return cudaGetLastError();
+}
+
+}   /* namespace */
+
+cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    if(tile.n_reads <= 0) { return cudaSuccess; }
+    switch(params.group_cardinality) {
+        case 1: return launch_pamld_groups< 1 >(params, tile, geometry, stream);
+        case 2: return launch_pamld_groups< 2 >(params, tile, geometry, stream);
+        case 3: return launch_pamld_groups< 3 >(params, tile, geometry, stream);
+        case 4: return launch_pamld_groups< 4 >(params, tile, geometry, stream);
+        case 5: return launch_pamld_groups< 5 >(params, tile, geometry, stream);
+        case 6: return launch_pamld_groups< 6 >(params, tile, geometry, stream);
+        case 7: return launch_pamld_groups< 7 >(params, tile, geometry, stream);
+        case 8: return launch_pamld_groups< 8 >(params, tile, geometry, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    if(tile.n_reads <= 0) { return cudaSuccess; }
+    const SharedPlan plan = make_plan(params.barcode_cardinality, false);
+    const size_t bytes = plan.fixed_bytes;
+    const int threads = 256;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const long long resident = static_cast< long long >(geometry.multiprocessor_count) * 4;
+    const int grid = static_cast< int >(tiles < resident ? tiles : resident);
+    cudaError_t status;
+    switch(params.segment_cardinality) {
+        case 1:
+            status = cudaFuncSetAttribute(mdd_kernel< 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+            if(status != cudaSuccess) { return status; }
+            mdd_kernel< 1 ><<< grid, threads, bytes, stream >>>(params, tile);
+            break;
+        case 2:
+            status = cudaFuncSetAttribute(mdd_kernel< 2 >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+            if(status != cudaSuccess) { return status; }
+            mdd_kernel< 2 ><<< grid, threads, bytes, stream >>>(params, tile);
+            break;
+        default:
+            status = cudaFuncSetAttribute(mdd_kernel< 0 >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+            if(status != cudaSuccess) { return status; }
+            mdd_kernel< 0 ><<< grid, threads, bytes, stream >>>(params, tile);
+            break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    if(tile.n_reads <= 0) { return cudaSuccess; }
+    const int threads = 256;
+    const long long blocks = (tile.n_reads + threads - 1) / threads;
+    const long long resident = static_cast< long long >(geometry.multiprocessor_count) * 8;
+    const int grid = static_cast< int >(blocks < resident ? blocks : resident);
+    count_kernel<<< grid, threads, 0, stream >>>(params, tile);
+    return cudaGetLastError();
+}
+
+cudaError_t prepare_kernels(const LaunchGeometry&) {
+    return cudaSuccess;
+}
+
+}   /* namespace phq */

@@ -1,0 +1,90 @@
+/*  kernels.cuh — device-side data layout and launch interface of the classification kernels.
+
+    HBM layout:
+      tiles        structure-of-arrays planes, read index fastest (phq_tile in pheniqs_b200.h)
+      barcodes     one 16-byte entry per barcode: low bit-plane, high bit-plane (32 positions
+                   each, position j = bit j) and the f64 prior  -> replaces vector< Barcode >
+                   (classifier.h:49) for the scoring loop
+      phred        f64 tables derived on the host with libm exactly as phred.cpp:24-72 does
+      accumulators [(N+1)][6] u64 then [(N+1)][2] f64 per decoder, inside one buffer per handle
+*/
+#ifndef PHQ_KERNELS_CUH
+#define PHQ_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pheniqs_b200.h"
+
+namespace phq {
+
+struct __align__(16) BarcodeEntry {
+    uint32_t lo;            /* bit j = low bit of the 2-bit code of barcode position j */
+    uint32_t hi;            /* bit j = high bit */
+    double prior;           /* Barcode::concentration (barcode.h:37) */
+};
+
+/* offsets into the f64 Phred table uploaded once per handle */
+enum {
+    PHRED_MATCH_FACTOR   = 0,       /* [128]  B ^ true_positive_quality[q]      (q = 0 -> 1)            */
+    PHRED_MISMATCH_RATIO = 128,     /* [128]  B ^ (q - true_positive_quality[q]) (q = 0 -> 1)           */
+    PHRED_TRUE_POSITIVE_QUALITY = 256, /* [128] phred.cpp:34-38, used by the exact tie path            */
+    PHRED_UNIFORM_QUALITY = 384,    /* UNIFORM_BASE_QUALITY, phred.h:33                                  */
+    PHRED_BASE = 385,               /* PHRED_PROBABILITY_BASE, phred.h:34                                */
+    PHRED_UNIFORM_FACTOR = 386,     /* B ^ UNIFORM_BASE_QUALITY                                          */
+    PHRED_TABLE_SIZE = 388
+};
+
+enum { ACC_COUNT = 0, ACC_PF_COUNT = 1, ACC_DISTANCE = 2, ACC_LOW_CONDITIONAL = 3, ACC_LOW_CONFIDENCE = 4, ACC_PF_DISTANCE = 5, ACC_U64_COLUMNS = 6 };
+enum { ACC_CONFIDENCE = 0, ACC_PF_CONFIDENCE = 1, ACC_F64_COLUMNS = 2 };
+enum { DIAG_EXACT_PATH = 0, DIAG_THRESHOLD_BAND = 1, DIAG_COLUMNS = 2 };
+
+struct DecoderParams {
+    int32_t algorithm;
+    int32_t barcode_cardinality;
+    int32_t nucleotide_cardinality;
+    int32_t word_cardinality;
+    int32_t quality_word_cardinality;
+    int32_t group_cardinality;                  /* ceil(nucleotide_cardinality / 4) */
+    int32_t segment_cardinality;
+    uint32_t segment_mask[PHQ_MAX_SEGMENTS];    /* positions of each segment in the concatenated observation */
+    int32_t distance_tolerance[PHQ_MAX_SEGMENTS];
+    int32_t high_quality_threshold;
+    int32_t high_quality_distance_threshold;
+    int32_t quality_masking_threshold;
+    double adjusted_noise_probability;          /* noise * random barcode probability, pamld.cpp:29 */
+    double confidence_threshold;
+    double random_barcode_probability;
+    double uniform_observation_probability;     /* pow(B, Kahan sum of L copies of U) computed with the host libm */
+    const BarcodeEntry* barcodes;               /* [N] device */
+    const double* phred;                        /* [PHRED_TABLE_SIZE] device */
+    unsigned long long* acc_u64;                /* [(N+1)][6] device */
+    double* acc_f64;                            /* [(N+1)][2] device */
+    unsigned long long* totals;                 /* [2] count, pf_count; NULL unless this is the last decoder of the chain */
+    unsigned long long* diagnostics;            /* [DIAG_COLUMNS] */
+};
+
+struct TileArguments {
+    const uint32_t* bases;
+    const uint16_t* nmask;
+    const uint32_t* quality;
+    long long pitch;
+    long long n_reads;
+    uint8_t* qcfail;                            /* in/out running flag, [n_reads] */
+    phq_result* results;                        /* may be NULL */
+};
+
+struct LaunchGeometry {
+    int multiprocessor_count;
+    size_t shared_memory_per_block_optin;
+};
+
+/* each returns the CUDA error of the launch; all are asynchronous on `stream` */
+cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
+cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
+/* naive / passthrough bookkeeping: count and pf_count of the undetermined row (and the chain totals) */
+cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
+cudaError_t prepare_kernels(const LaunchGeometry& geometry);
+
+}   /* namespace phq */
+#endif

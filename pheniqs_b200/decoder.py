@@ -1,0 +1,242 @@
+"""decoder.py — host-side mirror of the reference's decoder interface over the C ABI.
+
+`DecoderChain` stands where one thread's `TranscodingDecoder` stands in the reference
+(transcode.h:40-65): it is built from the compiled decoder ontology, classifies reads
+(a batch per call instead of one read per call), owns per-barcode accumulators, is merged
+with its peers by `collect` (here: one all-reduce over NVLink instead of a serial loop over
+threads, transcode.cpp:162-179) and estimates priors in `finalize` (classifier.h:94-124).
+
+All arithmetic happens inside libpheniqs_b200.so; this file only marshals buffers.
+PyTorch is used for device memory, streams and torch.distributed, nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import binding
+from .binding import DecoderInfo, Tile, check, library
+
+RESULT_DTYPE = np.dtype([("index", np.int32), ("distance", np.int32), ("confidence", np.float64)])
+ACC_U64_COLUMNS = ("count", "pf count", "accumulated distance", "low conditional confidence count", "low confidence count", "accumulated pf distance")
+ACC_F64_COLUMNS = ("accumulated confidence", "accumulated pf confidence")
+
+
+def compile_job(job) -> dict:
+    """Transcode::compile for the decoder sections (phq_compile_job). Host only."""
+    lib = library()
+    text = job if isinstance(job, (str, bytes)) else json.dumps(job)
+    if isinstance(text, str):
+        text = text.encode()
+    out = C.c_void_p()
+    check(lib.phq_compile_job(text, C.byref(out)))
+    try:
+        return json.loads(C.string_at(out).decode())
+    finally:
+        lib.phq_free(out)
+
+
+def shard_range(n_reads: int, rank: int, world_size: int):
+    """Contiguous read range of one rank, as the reference slices nothing but threads pull in turn
+    (transcode.cpp:287-316); reads are independent, any partition is valid."""
+    return n_reads * rank // world_size, n_reads * (rank + 1) // world_size
+
+
+class HostTile:
+    """Host planes of one decoder for n_reads reads (numpy arrays, optionally pinned)."""
+
+    def __init__(self, info: DecoderInfo, n_reads: int, pinned: bool = False):
+        self.n_reads = n_reads
+        self.pitch = max(n_reads, 1)
+        self.words = info.word_cardinality
+        self.quality_words = info.quality_word_cardinality
+        self._pinned = []
+        self.bases = self._allocate((self.words, self.pitch), np.uint32, pinned)
+        self.nmask = self._allocate((self.words, self.pitch), np.uint16, pinned)
+        self.quality = self._allocate((self.quality_words, self.pitch), np.uint32, pinned)
+
+    def _allocate(self, shape, dtype, pinned):
+        if not pinned:
+            return np.zeros(shape, dtype=dtype)
+        import torch
+        t = torch.zeros(shape, dtype={np.uint32: torch.int32, np.uint16: torch.int16}[dtype]).pin_memory()
+        self._pinned.append(t)
+        return t.numpy().view(dtype)
+
+    def as_struct(self) -> Tile:
+        return Tile(self.bases.ctypes.data, self.nmask.ctypes.data, self.quality.ctypes.data, self.pitch)
+
+
+class DecoderChain:
+    def __init__(self, compiled_job, device: int = 0):
+        self.lib = library()
+        text = compiled_job if isinstance(compiled_job, (str, bytes)) else json.dumps(compiled_job)
+        if isinstance(text, str):
+            text = text.encode()
+        self.handle = C.c_void_p()
+        self.device = device
+        check(self.lib.phq_create(text, device, C.byref(self.handle)))
+        self.n_decoders = self.lib.phq_decoder_count(self.handle)
+        self.info = []
+        for k in range(self.n_decoders):
+            info = DecoderInfo()
+            check(self.lib.phq_decoder_describe(self.handle, k, C.byref(info)), self.handle)
+            self.info.append(info)
+
+    @classmethod
+    def from_job(cls, job, device: int = 0) -> "DecoderChain":
+        return cls(compile_job(job), device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.phq_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ feed seam
+    def allocate_tiles(self, n_reads: int, pinned: bool = False):
+        return [HostTile(info, n_reads, pinned) if info.has_tile else None for info in self.info]
+
+    def _tile_array(self, tiles):
+        array = (Tile * self.n_decoders)()
+        for k, t in enumerate(tiles):
+            if t is not None:
+                array[k] = t if isinstance(t, Tile) else t.as_struct()
+        return array
+
+    def pack(self, code, quality, offset, tiles=None, pinned: bool = False):
+        """Rule::apply + packing for a batch held as per-segment flat arrays (phq_pack)."""
+        n_segments = len(code)
+        n_reads = int(offset[0].shape[0] - 1)
+        if tiles is None:
+            tiles = self.allocate_tiles(n_reads, pinned)
+        code = [np.ascontiguousarray(c, dtype=np.uint8) for c in code]
+        quality = [np.ascontiguousarray(q, dtype=np.uint8) for q in quality]
+        offset = [np.ascontiguousarray(o, dtype=np.int64) for o in offset]
+        pc = (C.c_void_p * n_segments)(*[c.ctypes.data for c in code])
+        pq = (C.c_void_p * n_segments)(*[q.ctypes.data for q in quality])
+        po = (C.c_void_p * n_segments)(*[o.ctypes.data for o in offset])
+        check(self.lib.phq_pack(self.handle, n_reads, n_segments, pc, pq, po, self._tile_array(tiles)), self.handle)
+        return tiles
+
+    # ------------------------------------------------------------------ classification
+    def decode(self, tiles, n_reads: int, qcfail_in=None, want_results: bool = True, results=None, qcfail_out=None):
+        """TranscodingDecoder::classify over host buffers (phq_decode_batch)."""
+        if results is None:
+            results = [np.zeros(n_reads, dtype=RESULT_DTYPE) if want_results else None for _ in range(self.n_decoders)]
+        if qcfail_out is None:
+            qcfail_out = np.zeros(n_reads, dtype=np.uint8)
+        pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
+        qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
+        check(self.lib.phq_decode_batch(self.handle, n_reads, self._tile_array(tiles), None if qin is None else qin.ctypes.data,
+                                        pointers, qcfail_out.ctypes.data), self.handle)
+        return results, qcfail_out
+
+    def decode_device(self, device_tiles, n_reads: int, qcfail, results=None, stream=None):
+        """Same over device-resident torch tensors; asynchronous on `stream` (phq_decode_batch_device).
+
+        device_tiles[k] = (bases int32 [words, pitch], nmask int16 [words, pitch], quality int32 [qwords, pitch]) or None."""
+        array = (Tile * self.n_decoders)()
+        for k, t in enumerate(device_tiles):
+            if t is not None:
+                bases, nmask, quality = t
+                array[k] = Tile(bases.data_ptr(), nmask.data_ptr(), quality.data_ptr(), bases.shape[-1])
+        pointers = (C.c_void_p * self.n_decoders)(*[None if (results is None or r is None) else r.data_ptr() for r in (results or [None] * self.n_decoders)])
+        handle = 0 if stream is None else stream.cuda_stream
+        check(self.lib.phq_decode_batch_device(self.handle, n_reads, array, qcfail.data_ptr(), pointers, C.c_void_p(handle)), self.handle)
+
+    def upload(self, tiles, n_reads: int):
+        """Host tiles -> device tensors (torch), for keeping a batch resident in HBM."""
+        import torch
+        device = torch.device("cuda", self.device)
+        out = []
+        for t in tiles:
+            if t is None:
+                out.append(None)
+                continue
+            out.append((torch.from_numpy(t.bases.view(np.int32)).to(device), torch.from_numpy(t.nmask.view(np.int16)).to(device),
+                        torch.from_numpy(t.quality.view(np.int32)).to(device)))
+        return out
+
+    def last_kernel_milliseconds(self) -> float:
+        ms = C.c_float()
+        check(self.lib.phq_last_kernel_milliseconds(self.handle, C.byref(ms)), self.handle)
+        return ms.value
+
+    # ------------------------------------------------------------------ accumulators / priors
+    def accumulators(self, k: int):
+        rows = self.info[k].barcode_cardinality + 1
+        u = np.zeros((rows, 6), dtype=np.uint64)
+        f = np.zeros((rows, 2), dtype=np.float64)
+        check(self.lib.phq_accumulators(self.handle, k, u.ctypes.data, f.ctypes.data), self.handle)
+        return u, f
+
+    def totals(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.lib.phq_totals(self.handle, C.byref(a), C.byref(b)), self.handle)
+        return a.value, b.value
+
+    def reset(self):
+        check(self.lib.phq_reset_accumulators(self.handle), self.handle)
+
+    def accumulator_tensors(self):
+        """The handle's accumulator buffer as two torch views (int64 bit pattern of the u64 plane, float64 plane)."""
+        import torch
+        pointer, n_u64, n_f64 = C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self.lib.phq_accumulator_buffer(self.handle, C.byref(pointer), C.byref(n_u64), C.byref(n_f64)), self.handle)
+
+        class _Raw:
+            def __init__(self, address, count, typestr):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (address, False), "version": 2}
+        device = torch.device("cuda", self.device)
+        u = torch.as_tensor(_Raw(pointer.value, n_u64.value, "<i8"), device=device)
+        f = torch.as_tensor(_Raw(pointer.value + 8 * n_u64.value, n_f64.value, "<f8"), device=device)
+        return u, f
+
+    def collect(self, group=None):
+        """Classifier::collect across ranks (classifier.h:87-93): one all-reduce(sum) per plane, in place."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        u, f = self.accumulator_tensors()
+        torch.cuda.current_stream(u.device).synchronize()
+        all_reduce_accumulators(u, f, group)
+
+    def estimate_priors(self, k: int):
+        noise = C.c_double()
+        concentration = np.zeros(self.info[k].barcode_cardinality, dtype=np.float64)
+        check(self.lib.phq_estimate_priors(self.handle, k, C.byref(noise), concentration.ctypes.data), self.handle)
+        return noise.value, concentration
+
+    def set_priors(self, k: int, noise: float, concentration):
+        c = np.ascontiguousarray(concentration, dtype=np.float64)
+        check(self.lib.phq_set_priors(self.handle, k, float(noise), c.ctypes.data), self.handle)
+
+    def adjust_priors(self):
+        """The two-pass workflow of docs/pamld.md:38-44 / Classifier::adjust_prior (classifier.h:125-160):
+        replace every PAMLD decoder's priors by the estimates from the accumulated (collected) counts."""
+        for k, info in enumerate(self.info):
+            if info.algorithm == 0:
+                noise, concentration = self.estimate_priors(k)
+                self.set_priors(k, noise, concentration)
+
+    def statistics(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self.lib.phq_statistics(self.handle, C.byref(a), C.byref(b), C.byref(c)), self.handle)
+        return {"kernel_launches": a.value, "exact_path_reads": b.value, "threshold_band_reads": c.value}
+
+
+def all_reduce_accumulators(u64_plane, f64_plane, group=None):
+    """Sum the accumulator planes of all ranks in place. u64 counters travel as int64 bit patterns
+    (two's complement addition is the same operation); works for NCCL (device tensors) and gloo (CPU)."""
+    import torch.distributed as dist
+    dist.all_reduce(u64_plane, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(f64_plane, op=dist.ReduceOp.SUM, group=group)
