@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py — reads/s decoded on the barcode classification path, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1] [--reads R] [--impl reference]
+
+One "step" is one pass of the hot path over one batch of synthetic reads resident in HBM:
+reset accumulators -> classify every read of the batch against every barcode of every decoder of
+the workload (one kernel per decoder) -> all-reduce the accumulators across ranks (the path's only
+collective). Reads are sharded per rank (weak scaling: --reads is per GPU). The default workload
+is BASELINE.json's PAMLD headline configuration, c1 (96 x [8,8] dual index).
+
+Prints ONE JSON line (rank 0). `value` is device-timed (CUDA events on the launching stream, max
+over ranks); `e2e` is the same metric through the host-buffer C-ABI call phq_decode_batch (pinned
+host tiles in, results + qcfail out, copies inside the timed region); `roofline` relates the
+dominant kernel to the measured HBM peak; `cpu_baseline` is the reference's own decoder classes
+(oracle/_ref, else the C port) timed on this host's cores on a bounded sample of the same reads.
+
+`--impl reference` times only that CPU implementation (all host threads), same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec decoded (PAMLD)"
+UNIT = "reads/s"
+DEFAULT_READS = {"c1": 1 << 28, "c2": 1 << 28, "c3": 1 << 26, "c4": 1 << 26, "c5": 1 << 17}
+WORKLOAD_LABEL = {
+    "c1": "C1: Illumina dual-index (i7+i5, 8 bp each) 96-sample PAMLD, noise 0.05, confidence threshold 0.95",
+    "c2": "C2: same 96-sample dual-index set, MDD, distance tolerance [1,1]",
+    "c3": "C3: SPLiT-seq 3 x 96 x [8] + 4 x [6] PAMLD cellular + naive 10 bp UMI",
+    "c4": "C4: sci-RNA-seq 96 x [10] + 196 x [10,10] PAMLD cellular + naive 8 bp UMI",
+    "c5": "C5: 16 bp cellular PAMLD against a 737,280 barcode whitelist + naive 12 bp UMI",
+}
+
+
+def algorithmic_bytes_per_read(chain) -> int:
+    """per tiled decoder ceil(L/4) + ceil(L/8) + L bytes in and 16 bytes out; + 1 byte qcfail per read."""
+    total = 1
+    for info in chain.info:
+        if info.has_tile:
+            L = info.nucleotide_cardinality
+            total += (L + 3) // 4 + (L + 7) // 8 + L + 16
+    return total
+
+
+def pair_words_per_read(chain) -> int:
+    return sum(info.barcode_cardinality for info in chain.info if info.has_tile)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_sample(compiled, spec, n_reads, seed):
+    from pheniqs_b200 import workload
+    return workload.synthesize(compiled, spec["input segment length"], n_reads, seed=seed, sampling="zipf" if spec["name"] == "c4" else "prior")
+
+
+def time_cpu(compiled, spec, seconds_target=12.0, threads=None, seed=99):
+    """The reference's CPU implementation of the path on this host's cores, on a bounded sample."""
+    from oracle import oracle as O
+    threads = threads or (os.cpu_count() or 1)
+    probe_n = 2000 if spec["name"] != "c5" else 16
+    code, quality, offset, _ = host_sample(compiled, spec, probe_n, seed)
+    checker = O.best_oracle(compiled, len(code))
+    probe = checker.decode(O.ReadBatch(code, quality, offset), threads=1, want_outputs=False)
+    rate = probe_n / max(probe.seconds, 1e-9)
+    n = int(min(max(rate * threads * seconds_target, threads * 4), 4e7))
+    code, quality, offset, _ = host_sample(compiled, spec, n, seed + 1)
+    checker = O.best_oracle(compiled, len(code))
+    out = checker.decode(O.ReadBatch(code, quality, offset), threads=threads, want_outputs=False)
+    return {"value": n / out.seconds, "unit": UNIT, "cores": threads, "kind": checker.kind,
+            "sample": "%d synthetic reads of the same workload, %d threads each with private decoders (transcode.cpp:2296), %.1f s" % (n, threads, out.seconds)}, n, out.seconds
+
+
+def run_reference(args, rank, world):
+    from pheniqs_b200 import compile_job, workload
+    if rank != 0:
+        return
+    spec = workload.load(args.workload)
+    compiled = compile_job(spec["job"])
+    per_step = max(4.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    values = []
+    for step in range(args.warmup + args.steps):
+        baseline, n, seconds = time_cpu(compiled, spec, seconds_target=per_step, seed=1000 + step)
+        if step >= args.warmup:
+            values.append((n, seconds, baseline))
+    total_reads = sum(v[0] for v in values)
+    total_seconds = sum(v[1] for v in values)
+    baseline = values[-1][2]
+    value = total_reads / total_seconds
+    baseline["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_seconds / max(len(values), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD_LABEL[args.workload], "reads_per_step": total_reads // max(len(values), 1)},
+            "cpu_baseline": baseline, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=10)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--workload", default="c1", choices=sorted(DEFAULT_READS))
+    parser.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: per workload)")
+    parser.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU per end-to-end step (default min(reads, 2^26))")
+    parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-e2e", action="store_true")
+    args = parser.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pheniqs_b200 import DecoderChain, compile_job, workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the classification path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    spec = workload.load(args.workload)
+    compiled = compile_job(spec["job"])
+    chain = DecoderChain(compiled, device=local_rank)
+    n = args.reads or DEFAULT_READS[args.workload]
+    sampling = "zipf" if args.workload == "c4" else "prior"
+    tiles = workload.synthesize_device_tiles(chain, compiled, n, device, seed=workload.SEED + 17 * rank, sampling=sampling)
+    flags = torch.zeros(n, dtype=torch.uint8, device=device)
+    results = [torch.empty((n, 2), dtype=torch.float64, device=device) if info.has_tile else None for info in chain.info]
+    stream = torch.cuda.current_stream(device)
+    u64_plane, f64_plane = chain.accumulator_tensors()
+
+    def step():
+        flags.zero_()
+        u64_plane.zero_()
+        f64_plane.zero_()
+        chain.decode_device(tiles, n, flags, results, stream)
+        if world > 1:
+            dist.all_reduce(u64_plane)
+            dist.all_reduce(f64_plane)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches_before = chain.statistics()["kernel_launches"]
+    kernel_ms = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        torch.cuda.nvtx.range_push("timed")
+        start.record(stream)
+        for _ in range(args.steps):
+            step()
+        stop.record(stream)
+        barrier()
+        torch.cuda.nvtx.range_pop()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = chain.statistics()["kernel_launches"] - launches_before
+    # the dominant kernel alone, timed live with CUDA events on the launching stream (phq_last_kernel_milliseconds)
+    for _ in range(min(args.steps, 5)):
+        flags.zero_()
+        u64_plane.zero_()
+        f64_plane.zero_()
+        chain.decode_device(tiles, n, flags, results, stream)
+        kernel_ms.append(chain.last_kernel_milliseconds())
+    kernel_ms_mean = float(np.mean(kernel_ms))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = n * world * args.steps / (elapsed_ms * 1e-3)
+
+    # sanity on the timed work: every read was classified
+    if world == 1:
+        u, _ = chain.accumulators(next(k for k, info in enumerate(chain.info) if info.has_tile))
+        assert int(u[:, 0].sum()) == n, "accumulators do not cover the batch"
+
+    bytes_per_read = algorithmic_bytes_per_read(chain)
+    peak, peak_source = measured_peaks()
+    achieved = bytes_per_read * n / (kernel_ms_mean * 1e-3) / 1e9
+    pairs = pair_words_per_read(chain)
+    clock_summary = clocks.summary()
+    sm_mhz = clock_summary.get("sm_mhz") or 0
+    sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_source, "kernel": "pamld_kernel" if chain.info[0].algorithm == 0 or args.workload != "c2" else "mdd_kernel",
+                "kernel_ms_per_launch_set": kernel_ms_mean, "algorithmic_bytes_per_read": bytes_per_read,
+                "pair_words_per_read": pairs, "pair_words_per_s": pairs * n / (kernel_ms_mean * 1e-3),
+                "pair_words_per_clk_per_sm": (pairs * n / (kernel_ms_mean * 1e-3)) / (sm_mhz * 1e6 * sm_count) if sm_mhz else None,
+                "note": "the path is issue/shared-memory bound, not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the contract asks"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_LABEL[args.workload], "reads_per_gpu": n, "decoders": chain.n_decoders, "barcodes": [info.barcode_cardinality for info in chain.info],
+                       "l2": "inputs (%d MB per GPU) exceed L2; no flush needed" % (bytes_per_read * n >> 20), "parallelism": "reads sharded x%d, accumulators all-reduced" % world},
+            "roofline": roofline, "gpu_launches": int(launches), "clocks": clock_summary}
+
+    # ---------------------------------------------------------------- end to end through the host-buffer C-ABI call
+    if not args.no_e2e:
+        m = args.e2e_reads or min(n, 1 << 26)
+        host_tiles = chain.allocate_tiles(m, pinned=True)
+        for k, t in enumerate(tiles):
+            if t is None:
+                continue
+            host_tiles[k].bases[:] = t[0][:, :m].cpu().numpy().view(np.uint32)
+            host_tiles[k].nmask[:] = t[1][:, :m].cpu().numpy().view(np.uint16)
+            host_tiles[k].quality[:] = t[2][:, :m].cpu().numpy().view(np.uint32)
+        from pheniqs_b200 import RESULT_DTYPE
+        host_results = []
+        keep = []
+        for info in chain.info:
+            if info.has_tile:
+                buffer = torch.zeros((m, 2), dtype=torch.float64).pin_memory()
+                keep.append(buffer)
+                host_results.append(buffer.numpy().view(RESULT_DTYPE).reshape(-1))
+            else:
+                host_results.append(None)
+        qc_buffer = torch.zeros(m, dtype=torch.uint8).pin_memory()
+        qc_out = qc_buffer.numpy()
+        h2d = sum((info.word_cardinality * 6 + info.quality_word_cardinality * 4) * m for info in chain.info if info.has_tile)
+        d2h = sum(16 * m for info in chain.info if info.has_tile) + m
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            chain.decode(host_tiles, m, None, results=host_results, qcfail_out=qc_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            chain.decode(host_tiles, m, None, results=host_results, qcfail_out=qc_out)
+        torch.cuda.synchronize(device)
+        seconds = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([seconds], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            seconds = float(t.item())
+        line["e2e"] = {"value": m * world * e2e_steps / seconds, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "reads_per_gpu_per_step": m, "steps": e2e_steps, "call": "phq_decode_batch (pinned host tiles in; results + qcfail out)"}
+        del host_tiles, host_results, keep
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        baseline, _, _ = time_cpu(compiled, spec)
+        line["cpu_baseline"] = baseline
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,7 @@ constexpr int MAX_WARPS = 12;
 constexpr int STAGE_ENTRIES = 1024;             /* barcodes per staged chunk: 16 KB */
 constexpr int SHARED_ACCUMULATOR_ROWS = 1025;   /* per-CTA accumulators live in shared memory up to N + 1 = 1025 rows */
 constexpr unsigned FULL_MASK = 0xffffffffu;
+#define TIE_SCRATCH_BYTES(G) ((G) * 16 * 8 + 32 * 4)
 
 /* ------------------------------------------------------------------ shared memory plan (host and device agree) */
 struct SharedPlan {
@@ -60,8 +61,11 @@ __host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool ph
     p.off_acc_u32 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_U64_COLUMNS * 4u, 16u);
     p.off_misc = at;        at += 16u;          /* totals count, pf_count; diagnostics exact, band */
     p.off_mbarrier = at;    at += 16u;
+    /* The per-warp table blocks follow, 4 KB aligned IN THE SHARED WINDOW (lookup addresses are formed with one
+       LOP3); dynamic shared memory does not start at window offset 0, so the kernel aligns at run time and the
+       host reserves 4 KB of slack. */
     p.off_tables = align_up(at, 256u);
-    p.fixed_bytes = p.off_tables;
+    p.fixed_bytes = p.off_tables + 4096u;
     return p;
 }
 
@@ -208,96 +212,203 @@ struct BarcodeStream {
 };
 
 /* ------------------------------------------------------------------ PAMLD exact tie path
-   One read (broadcast from lane `source`) against all barcodes, 32 barcodes per step. Barcodes whose
-   prior adjusted probability is within 2^-18 of the best are re-evaluated the way the reference does:
-   sigma_q is the position ordered Kahan sum of the substitution lookup (barcode.h:147-162,
-   phred.cpp:39-72), bit for bit. Among equal priors the smaller sigma wins and equal sigmas keep the
-   first index, which is what strict > over p = pow(B, sigma) * prior yields (pamld.cpp:68-79). */
+   Structural ties (equal multisets of mismatch qualities under equal priors) are common for noise reads.
+   The reference resolves them by the rounding of its position ordered Kahan sums (barcode.h:147-162) and
+   then keeps the first maximum (pamld.cpp:73), so they are re-evaluated here in exactly that operation
+   order. The warp works on ONE flagged read at a time, lanes = barcodes:
+
+     1. the read's subset product tables are copied from the owner lane's column to a small linear block
+        (any lane -> entry mapping is then conflict free or a broadcast);
+     2. every barcode's product is recomputed, 32 per step; those within 2^-18 of the best are candidates
+        and are compacted into a list;
+     3. each candidate's sigma_q is evaluated bit for bit as the reference does; among equal priors the
+        smaller sigma wins and equal sigmas keep the lower index, which is what strict > over
+        p = pow(B, sigma) * prior yields. pow() is only consulted across different priors.
+
+   The code is deliberately rolled: it runs for ~2 % of the reads and must not evict the scan loop from
+   the instruction cache. */
 struct Candidate {
     double prior;
     double sigma;
-    double probability;     /* pow(B, sigma) * prior with the device pow: only consulted across different priors */
     int index;              /* -1 = none */
 };
-__device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b) {
+struct TieScratch {
+    double* table;          /* [G * 16] linear copy of the flagged read's subset products */
+    int* list;              /* [32] candidate barcode indices */
+};
+
+__device__ __noinline__ double adjusted_probability(double base, double sigma, double prior) {
+    return pow(base, sigma) * prior;
+}
+__device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, double base) {
     if(a.index < 0) { return false; }
     if(b.index < 0) { return true; }
     if(a.prior == b.prior) {
         return a.sigma < b.sigma || (a.sigma == b.sigma && a.index < b.index);
     }
-    return a.probability > b.probability || (a.probability == b.probability && a.index < b.index);
+    const double pa = adjusted_probability(base, a.sigma, a.prior);
+    const double pb = adjusted_probability(base, b.sigma, b.prior);
+    return pa > pb || (pa == pb && a.index < b.index);
+}
+
+/* sigma_q of one barcode exactly as Barcode::compensated_decoding_probability accumulates it */
+__device__ __noinline__ double exact_sigma(const double* __restrict__ phred_global, int L, uint32_t m, uint32_t nmask, const uint32_t* quality) {
+    const double* __restrict__ tq = phred_global + PHRED_TRUE_POSITIVE_QUALITY;
+    const double U = phred_global[PHRED_UNIFORM_QUALITY];
+    double sigma = 0.0, compensation = 0.0;
+    #pragma unroll 1
+    for(int j = 0; j < L; ++j) {
+        uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        q = q > 127u ? 127u : q;
+        double value;
+        if(q == 0u) { value = 0.0; }
+        else if((nmask >> j) & 1u) { value = U; }
+        else if((m >> j) & 1u) { value = static_cast< double >(q); }
+        else { value = tq[q]; }
+        const double y = __dsub_rn(value, compensation);
+        const double t = __dadd_rn(sigma, y);
+        compensation = __dsub_rn(__dsub_rn(t, sigma), y);
+        sigma = t;
+    }
+    return sigma;
+}
+
+__device__ __noinline__ void evaluate_candidates(Candidate& best, const BarcodeEntry* __restrict__ barcodes, const double* __restrict__ phred_global,
+                                                 int L, const int* list, int count, uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t* quality) {
+    const int lane = threadIdx.x & 31;
+    if(lane < count) {
+        Candidate c;
+        c.index = list[lane];
+        const BarcodeEntry e = barcodes[c.index];
+        const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
+        c.prior = e.prior;
+        c.sigma = exact_sigma(phred_global, L, m, nmask, quality);
+        if(beats(c, best, phred_global[PHRED_BASE])) { best = c; }
+    }
 }
 
 template < int G >
-__device__ __noinline__ int resolve_exact(const DecoderParams& P, const double* __restrict__ phred_shared,
-                                          uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t (&quality)[G], double threshold) {
+__device__ __noinline__ int resolve_ties(const BarcodeEntry* __restrict__ barcodes, int barcode_cardinality, int L,
+                                         const double* __restrict__ phred_global, TieScratch scratch, const double* owner_column,
+                                         uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t (&quality)[G], double threshold) {
     const int lane = threadIdx.x & 31;
-    const int L = P.nucleotide_cardinality;
-    const double* __restrict__ tq = P.phred + PHRED_TRUE_POSITIVE_QUALITY;
-    const double U = P.phred[PHRED_UNIFORM_QUALITY];
-    const double B = P.phred[PHRED_BASE];
-    Candidate best;
-    best.prior = 0; best.sigma = 0; best.probability = 0; best.index = -1;
+    for(int e = lane; e < G * 16; e += WARP_SIZE) { scratch.table[e] = owner_column[e * WARP_SIZE]; }
+    __syncwarp();
 
-    for(int base = 0; base < P.barcode_cardinality; base += WARP_SIZE) {
+    Candidate best;
+    best.prior = 0; best.sigma = 0; best.index = -1;
+    int count = 0;
+    #pragma unroll 1
+    for(int base = 0; base < barcode_cardinality; base += WARP_SIZE) {
         const int b = base + lane;
-        if(b < P.barcode_cardinality) {
-            const BarcodeEntry e = P.barcodes[b];
+        bool candidate = false;
+        if(b < barcode_cardinality) {
+            const BarcodeEntry e = barcodes[b];
             const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
-            double t = 1.0;
+            double t = e.prior;
             #pragma unroll
-            for(int g = 0; g < G; ++g) {
-                #pragma unroll
-                for(int k = 0; k < 4; ++k) {
-                    const int j = g * 4 + k;
-                    uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
-                    q = q > 127u ? 127u : q;
-                    const bool plain = ((nmask >> j) & 1u) == 0u && q != 0u;
-                    if(((m >> j) & 1u) && plain) { t *= phred_shared[PHRED_MISMATCH_RATIO + q]; }
-                }
+            for(int g = 0; g < G; ++g) { t *= scratch.table[g * 16 + ((m >> (4 * g)) & 15u)]; }
+            candidate = t >= threshold;
+        }
+        const unsigned found = __ballot_sync(FULL_MASK, candidate);
+        if(found) {
+            const int fresh = __popc(found);
+            if(count + fresh > WARP_SIZE) {
+                evaluate_candidates(best, barcodes, phred_global, L, scratch.list, count, o_lo, o_hi, nmask, quality);
+                count = 0;
+                __syncwarp();
             }
-            const double p = t * e.prior;
-            if(p >= threshold) {
-                double sigma = 0.0, compensation = 0.0;
-                #pragma unroll
-                for(int g = 0; g < G; ++g) {
-                    #pragma unroll
-                    for(int k = 0; k < 4; ++k) {
-                        const int j = g * 4 + k;
-                        if(j < L) {
-                            uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
-                            q = q > 127u ? 127u : q;
-                            double value;
-                            if(q == 0u) { value = 0.0; }
-                            else if((nmask >> j) & 1u) { value = U; }
-                            else if((m >> j) & 1u) { value = static_cast< double >(q); }
-                            else { value = tq[q]; }
-                            const double y = __dsub_rn(value, compensation);
-                            const double s = __dadd_rn(sigma, y);
-                            compensation = __dsub_rn(__dsub_rn(s, sigma), y);
-                            sigma = s;
-                        }
-                    }
-                }
-                Candidate c;
-                c.prior = e.prior;
-                c.sigma = sigma;
-                c.probability = pow(B, sigma) * e.prior;
-                c.index = b;
-                if(beats(c, best)) { best = c; }
-            }
+            if(candidate) { scratch.list[count + __popc(found & ((1u << lane) - 1u))] = b; }
+            count += fresh;
+            __syncwarp();
         }
     }
-    #pragma unroll
+    if(count) { evaluate_candidates(best, barcodes, phred_global, L, scratch.list, count, o_lo, o_hi, nmask, quality); }
+    const double base = phred_global[PHRED_BASE];
+    #pragma unroll 1
     for(int offset = 16; offset > 0; offset >>= 1) {
         Candidate other;
         other.prior = __shfl_xor_sync(FULL_MASK, best.prior, offset);
         other.sigma = __shfl_xor_sync(FULL_MASK, best.sigma, offset);
-        other.probability = __shfl_xor_sync(FULL_MASK, best.probability, offset);
         other.index = __shfl_xor_sync(FULL_MASK, best.index, offset);
-        if(beats(other, best)) { best = other; }
+        if(beats(other, best, base)) { best = other; }
     }
+    __syncwarp();
     return best.index;
+}
+
+/* ------------------------------------------------------------------ PAMLD hot loop pieces */
+
+/* m = (o_lo ^ e_lo) | (o_hi ^ e_hi) | n_mask as two LOP3 (truth table 0xBE = (a ^ b) | c) */
+__device__ __forceinline__ uint32_t mismatch_mask(uint32_t o_lo, uint32_t o_hi, uint32_t nmask, uint32_t e_lo, uint32_t e_hi) {
+    uint32_t t, m;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(t) : "r"(o_hi), "r"(e_hi), "r"(nmask));
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(m) : "r"(o_lo), "r"(e_lo), "r"(t));
+    return m;
+}
+/*  Subset product of group g for mismatch mask m. The lane's table block is 4 KB aligned per group with
+    entry e at byte e * 256 + lane * 8, so the address is (nibble g of m, moved to bits 8..11) | base:
+    one shift and one LOP3 (truth table 0xEA = (a & b) | c), the group offset rides in the immediate. */
+template < int g >
+__device__ __forceinline__ double table_lookup(uint32_t base, uint32_t m) {
+    const uint32_t moved = (g < 2) ? (m << (8 - 4 * g)) : (m >> (4 * g - 8));
+    uint32_t address;
+    asm("lop3.b32 %0, %1, 0xF00, %2, 0xEA;" : "=r"(address) : "r"(moved), "r"(base));
+    double value;
+    /* volatile: must stay behind the table stores of this tile (the compiler cannot see through the address) */
+    asm volatile("ld.shared.f64 %0, [%1 + %2];" : "=d"(value) : "r"(address), "n"(g * 4096));
+    return value;
+}
+template < int G >
+__device__ __forceinline__ double subset_product(uint32_t base, uint32_t m) {
+    /* ((T0 * T1) * T2) * ... : a fixed order, so equal mismatch sets give bit-equal products */
+    double t = table_lookup< 0 >(base, m);
+    if(G > 1) { t *= table_lookup< (G > 1 ? 1 : 0) >(base, m); }
+    if(G > 2) { t *= table_lookup< (G > 2 ? 2 : 0) >(base, m); }
+    if(G > 3) { t *= table_lookup< (G > 3 ? 3 : 0) >(base, m); }
+    if(G > 4) { t *= table_lookup< (G > 4 ? 4 : 0) >(base, m); }
+    if(G > 5) { t *= table_lookup< (G > 5 ? 5 : 0) >(base, m); }
+    if(G > 6) { t *= table_lookup< (G > 6 ? 6 : 0) >(base, m); }
+    if(G > 7) { t *= table_lookup< (G > 7 ? 7 : 0) >(base, m); }
+    return t;
+}
+
+/*  Running selection state of one read. `best` is the first maximum seen so far (compared on the high
+    words of the f64 products, strict >, earlier index wins), `rest` the sum of everything else, `second`
+    the largest high word among the values that lost a comparison (tie detection). */
+struct Selection {
+    double best;
+    double rest;
+    int index;
+    int second;
+};
+/* the larger of (a, ia) and (b, ib) with a the earlier one; the loser is returned in `low` */
+__device__ __forceinline__ void duel(double a, int ia, double b, int ib, double& high, int& ihigh, double& low) {
+    const bool later = __double2hiint(b) > __double2hiint(a);
+    high = later ? b : a;
+    ihigh = later ? ib : ia;
+    low = later ? a : b;
+}
+__device__ __forceinline__ void select_one(Selection& s, double p, int i) {
+    double high, low; int ihigh;
+    duel(s.best, s.index, p, i, high, ihigh, low);
+    s.best = high; s.index = ihigh;
+    s.rest += low;
+    s.second = max(s.second, __double2hiint(low));
+}
+/* four candidates reduced as a tree, then one merge with the running state: one serial step per four pairs */
+__device__ __forceinline__ void select_four(Selection& s, double p0, double p1, double p2, double p3, int i) {
+    double a, b, c, la, lb, lc, low; int ia, ib, ic, ihigh;
+    duel(p0, i, p1, i + 1, a, ia, la);
+    duel(p2, i + 2, p3, i + 3, b, ib, lb);
+    duel(a, ia, b, ib, c, ic, lc);
+    const double losers = (la + lb) + lc;
+    const int second = max(max(__double2hiint(la), __double2hiint(lb)), __double2hiint(lc));
+    double high;
+    duel(s.best, s.index, c, ic, high, ihigh, low);
+    s.best = high; s.index = ihigh;
+    s.rest += losers + low;
+    s.second = max(max(s.second, second), __double2hiint(low));
 }
 
 /* ------------------------------------------------------------------ PAMLD */
@@ -311,7 +422,19 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     const int lane = tid & 31;
     const int warp = tid >> 5;
     /* per-lane subset product tables: entry (g, subset) of this lane at [(g * 16 + subset) * 32 + lane] */
-    double* const table = reinterpret_cast< double* >(smem + S.plan.off_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE) + lane;
+    const uint32_t window = shared_address(smem);
+    const uint32_t aligned_tables = ((window + S.plan.off_tables + 4095u) & ~4095u) - window;
+    const int warp_cardinality = blockDim.x >> 5;
+    double* const warp_table = reinterpret_cast< double* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE);
+    double* const table = warp_table + lane;
+    const uint32_t table_base = shared_address(table);
+    /* behind the tables of all warps: per warp a linear table copy and a candidate list for the tie path */
+    TieScratch tie_scratch;
+    {
+        unsigned char* const behind = smem + aligned_tables + static_cast< size_t >(warp_cardinality) * (G * 16 * WARP_SIZE * 8);
+        tie_scratch.table = reinterpret_cast< double* >(behind + static_cast< size_t >(warp) * TIE_SCRATCH_BYTES(G));
+        tie_scratch.list = reinterpret_cast< int* >(tie_scratch.table + G * 16);
+    }
     const double* const match_factor = S.phred + PHRED_MATCH_FACTOR;
     const double* const mismatch_ratio = S.phred + PHRED_MISMATCH_RATIO;
     const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
@@ -398,9 +521,12 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
         high_quality_mask &= (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
         __syncwarp();
 
-        /* ---- score every barcode: sum of prior adjusted probabilities and first maximum */
-        double sum = 0.0;
-        int best_high = 0, second_high = 0, best_index = 0;
+        /* ---- score every barcode. The reference Kahan-sums p over the barcodes (pamld.cpp:68-72); here the
+           running maximum is kept out of the sum (`rest` only ever receives the loser of a comparison), so no
+           small term is absorbed by a dominant one and best + rest is accurate to an ulp without
+           compensation. The first maximum (strict >, pamld.cpp:73) is tracked on the high words. */
+        Selection selection;
+        selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
         for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
             const BarcodeEntry* stage;
             if(resident) {
@@ -411,28 +537,33 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
             }
             const int count = stream.count(chunk);
             const int first = chunk * S.plan.stage_capacity;
-            #pragma unroll 4
-            for(int i = 0; i < count; ++i) {
-                const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
-                const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
-                double t = table[(m & 15u) * WARP_SIZE];
+            int i = 0;
+            #pragma unroll 2
+            for(; i + 4 <= count; i += 4) {
+                double p[4];
                 #pragma unroll
-                for(int g = 1; g < G; ++g) {
-                    t *= table[(g * 16 + ((m >> (4 * g)) & 15u)) * WARP_SIZE];
+                for(int u = 0; u < 4; ++u) {
+                    const uint4 raw = *reinterpret_cast< const uint4* >(stage + i + u);
+                    const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
+                    p[u] = subset_product< G >(table_base, m) * __hiloint2double(raw.w, raw.z);
                 }
-                const double p = t * __hiloint2double(raw.w, raw.z);
-                sum += p;
-                const int high = __double2hiint(p);
-                const bool greater = high > best_high;
-                second_high = max(second_high, greater ? best_high : high);
-                best_index = greater ? first + i : best_index;
-                best_high = max(best_high, high);
+                select_four(selection, p[0], p[1], p[2], p[3], first + i);
+            }
+            for(; i < count; ++i) {
+                const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
+                const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
+                select_one(selection, subset_product< G >(table_base, m) * __hiloint2double(raw.w, raw.z), first + i);
             }
             if(!resident) {
                 __syncthreads();
                 ++iteration;
             }
         }
+        const double best_p = selection.best;
+        const double rest = selection.rest;
+        const int second_high = selection.second;
+        int best_index = selection.index;
+        const int best_high = __double2hiint(best_p);
 
         /* ---- structural ties: exact re-evaluation, one flagged read at a time, whole warp cooperating */
         const bool tied = valid && (second_high + 1 >= best_high);
@@ -451,7 +582,7 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
                 const int s_high = __shfl_sync(FULL_MASK, best_high, source);
                 /* lower bound of the best product, widened by 2^-18 */
                 const double threshold = __hiloint2double(s_high, 0) * (1.0 - 3.814697265625e-06);
-                const int winner = resolve_exact< G >(P, S.phred, s_lo, s_hi, s_nmask, s_quality, threshold);
+                const int winner = resolve_ties< G >(P.barcodes, P.barcode_cardinality, L, P.phred, tie_scratch, warp_table + source, s_lo, s_hi, s_nmask, s_quality, threshold);
                 if(lane == source && winner >= 0) { best_index = winner; }
             }
         }
@@ -459,19 +590,16 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
         /* ---- decision for this lane's read (pamld.cpp:87-122) */
         if(valid) {
             const BarcodeEntry e = P.barcodes[best_index];
-            const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
-            double t = table[(m & 15u) * WARP_SIZE];
-            #pragma unroll
-            for(int g = 1; g < G; ++g) {
-                t *= table[(g * 16 + ((m >> (4 * g)) & 15u)) * WARP_SIZE];
-            }
+            const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, e.lo, e.hi);
+            const double t = subset_product< G >(table_base, m);
             /* when every position scores UNIFORM_BASE_QUALITY all barcodes share sigma = L x U and the
                reference's P(r|b) is the host libm constant */
             const bool uniform = uniform_positions == L;
             if(uniform) { base_probability = P.uniform_observation_probability; }
             const double conditional_probability = base_probability * t;
-            const double p = conditional_probability * e.prior;
-            const double sigma_p = base_probability * sum + P.adjusted_noise_probability;
+            /* confidence = p / sigma_p (pamld.cpp:92) with the per-read constant P0 divided out of both */
+            const double p = t * e.prior;
+            const double sigma_p = best_p + (rest + P.adjusted_noise_probability / base_probability);
             double confidence = p / sigma_p;
             int distance = __popc(m);
             const int high_quality_distance = __popc(m & high_quality_mask);
@@ -672,7 +800,7 @@ count_kernel(const DecoderParams P, const TileArguments A) {
 template < int G >
 cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     const SharedPlan plan = make_plan(params.barcode_cardinality, true);
-    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double);
+    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double) + TIE_SCRATCH_BYTES(G);
     if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
     int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
     warps = warps > MAX_WARPS ? MAX_WARPS : warps;

@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle. Run on the B200 box: pytest -m gpu.
+
+Bar (BASELINE.json north_star): barcode index, distance and qcfail bit-exact for MDD and
+PAMLD; PAMLD posterior within 1e-6 in log space (and the error probability 1 - conf within 1e-6 relative,
+floored at the 2^-53 quantum of the reference's own `1.0 - confidence`); u64 accumulators identical;
+f64 accumulators and estimated priors within 1e-9 relative."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle as O
+from pheniqs_b200 import DecoderChain, compile_job, workload
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(job, code, quality, offset, qcfail=None, compiled=None, device_path=False):
+    compiled = compiled or compile_job(job)
+    n = int(offset[0].shape[0] - 1)
+    chain = DecoderChain(compiled, device=0)
+    tiles = chain.pack(code, quality, offset)
+    if device_path:
+        import torch
+        device_tiles = chain.upload(tiles, n)
+        flags = torch.zeros(n, dtype=torch.uint8, device="cuda:0") if qcfail is None else torch.from_numpy(np.ascontiguousarray(qcfail)).to("cuda:0")
+        device_results = [torch.zeros((n, 2), dtype=torch.float64, device="cuda:0") for _ in range(chain.n_decoders)]
+        chain.decode_device(device_tiles, n, flags, device_results)
+        torch.cuda.synchronize()
+        from pheniqs_b200 import RESULT_DTYPE
+        results = [r.cpu().numpy().view(RESULT_DTYPE).reshape(-1) for r in device_results]
+        flags_out = flags.cpu().numpy()
+    else:
+        results, flags_out = chain.decode(tiles, n, qcfail)
+    checker = O.best_oracle(compiled, len(code))
+    expected = checker.decode(O.ReadBatch(code, quality, offset, qcfail))
+    return chain, checker, results, flags_out, expected
+
+
+def check(chain, checker, results, flags_out, expected):
+    for k, info in enumerate(chain.info):
+        label = "decoder %d" % k
+        if info.algorithm == 0:
+            helpers.compare_pamld(results[k], expected.index[:, k], expected.distance[:, k], expected.confidence[:, k], label)
+        else:
+            assert np.array_equal(results[k]["index"], expected.index[:, k]), label
+            assert np.array_equal(results[k]["distance"], expected.distance[:, k]), label
+            assert np.all(results[k]["confidence"] == 0), label
+        u, f = chain.accumulators(k)
+        eu, ef = checker.accumulators(k)
+        assert np.array_equal(u, eu), label + " integer accumulators"
+        assert np.allclose(f, ef, rtol=1e-9, atol=0), label + " confidence accumulators"
+        if info.algorithm == 0:
+            noise, concentration = chain.estimate_priors(k)
+            enoise, econcentration = checker.estimate_priors(k)
+            assert noise == pytest.approx(enoise, rel=1e-9)
+            assert np.allclose(concentration, econcentration, rtol=1e-9, atol=0)
+    assert np.array_equal(flags_out, expected.qcfail)
+    assert chain.totals() == checker.totals()
+
+
+@pytest.mark.parametrize("device_path", [False, True])
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+def test_baseline_configs(name, device_path):
+    spec = workload.load(name)
+    compiled = compile_job(spec["job"])
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 60000, seed=21, sampling="zipf" if name == "c4" else "prior")
+    state = run_both(None, code, quality, offset, compiled=compiled, device_path=device_path)
+    check(*state)
+    assert state[0].statistics()["kernel_launches"] == state[0].n_decoders
+
+
+def test_whitelist_config_reduced():
+    """Config 5's shape (16 bp cellular barcodes, chunked TMA staging of the table, global accumulators) on a 20,000 barcode whitelist."""
+    spec = workload.load("c5", whitelist_cardinality=20000)
+    compiled = compile_job(spec["job"])
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 3000, seed=4)
+    check(*run_both(None, code, quality, offset, compiled=compiled))
+
+
+def test_bdggg_golden_through_the_gpu():
+    batch, decoders, expected = helpers.bdggg()
+    compiled = compile_job(decoders)
+    chain, checker, results, flags, oracle_out = run_both(None, batch.code, batch.quality, batch.offset, batch.qcfail, compiled=compiled)
+    check(chain, checker, results, flags, oracle_out)
+    rg = ["undetermined"] + [k[1:] for k in sorted(compiled["sample"]["codec"])]
+    for i, e in enumerate(expected):
+        assert (589 if flags[i] else 77) == e["flag"], e["name"]
+        assert rg[results[0]["index"][i]] == e["RG"].split(":")[-1], e["name"]
+        # Read-level confidence of one decoder per type = the decoder's confidence (read.h:279-285)
+        assert helpers.error_tag(results[0]["confidence"][i]) == e["XB"], e["name"]
+        assert helpers.error_tag(results[2]["confidence"][i]) == e["XC"], e["name"]
+    report = helpers.golden("bdggg_report.json")
+    noise, concentration = chain.estimate_priors(0)
+    assert noise == pytest.approx(report["sample"]["estimated noise"], abs=2e-15)
+
+
+@pytest.mark.parametrize("short", [0.0, 0.2])
+@pytest.mark.parametrize("variant", ["pamld", "pamld_hq", "pamld_rc2", "pamld_long", "mdd", "mdd_masked", "mdd_rc", "mdd_3seg"])
+def test_random_decoders(variant, short):
+    rng = np.random.default_rng(abs(hash(variant)) % 1000 + 1)
+    if variant == "pamld":
+        decoder = helpers.random_job(rng, "pamld", (8,), 24)
+    elif variant == "pamld_hq":
+        decoder = helpers.random_job(rng, "pamld", (6, 7), 40, **{"high quality threshold": 20, "high quality distance threshold": 1})
+    elif variant == "pamld_rc2":
+        decoder = helpers.random_job(rng, "pamld", (10, 10), 60, reverse=True)
+    elif variant == "pamld_long":
+        decoder = helpers.random_job(rng, "pamld", (16, 15), 50, minimum_distance=6)
+    elif variant == "mdd":
+        decoder = helpers.random_job(rng, "mdd", (8, 8), 48, minimum_distance=3)
+    elif variant == "mdd_masked":
+        decoder = helpers.random_job(rng, "mdd", (9,), 30, minimum_distance=5, **{"quality masking threshold": 13})
+    elif variant == "mdd_rc":
+        decoder = helpers.random_job(rng, "mdd", (7, 5), 20, reverse=True, minimum_distance=3)
+    else:
+        decoder = helpers.random_job(rng, "mdd", (6, 12, 9), 64, minimum_distance=3)
+    job = {"sample": decoder, "molecular": [{"algorithm": "naive", "transform": {"token": ["0::4"]}}],
+           "cellular": [helpers.random_job(rng, "pamld", (8,), 12), helpers.random_job(rng, "mdd", (8,), 12, minimum_distance=3)]}
+    job["cellular"][0]["transform"]["token"] = ["0:3:11"]
+    job["cellular"][1]["transform"]["token"] = ["1:0:8"]
+    compiled = compile_job(job)
+    n = 20000
+    code, quality, offset, _ = workload.synthesize(compiled, [0], n, seed=5, short_fraction=short)
+    qcfail = (rng.random(n) < 0.1).astype(np.uint8)
+    check(*run_both(None, code, quality, offset, qcfail, compiled=compiled))
+
+
+def test_structural_ties_take_the_exact_path():
+    """Uniform priors + all-N / low quality observations: many exactly tied barcodes; first maximum must match."""
+    rng = np.random.default_rng(3)
+    job = {"sample": helpers.random_job(rng, "pamld", (8,), 10, minimum_distance=2)}
+    for record in job["sample"]["codec"].values():
+        record["concentration"] = 1
+    n = 4096
+    code = np.full((n, 10), 15, dtype=np.uint8)
+    quality = np.full((n, 10), 30, dtype=np.uint8)
+    code[1024:2048] = 1
+    quality[1024:2048] = 0
+    pattern = np.array([1, 2, 4, 8, 1, 2, 4, 8, 1, 2], dtype=np.uint8)
+    code[2048:3072] = pattern
+    quality[2048:3072] = 2
+    code[3072:] = np.array([1, 2, 4, 8], dtype=np.uint8)[rng.integers(0, 4, size=(1024, 10))]
+    quality[3072:] = np.array([37, 2], dtype=np.uint8)[rng.integers(0, 2, size=(1024, 10))]
+    batch = O.ReadBatch.from_fixed([code], [quality])
+    state = run_both(job, batch.code, batch.quality, batch.offset)
+    check(*state)
+    assert state[0].statistics()["exact_path_reads"] >= 2048
+
+
+def test_two_pass_prior_estimation():
+    """Config 4's workflow: pass 1 with uniform priors, estimate, pass 2 with the estimated priors (docs/pamld.md:38-44)."""
+    spec = workload.load("c4")
+    compiled = compile_job(spec["job"])
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 40000, seed=9, sampling="zipf")
+    chain, checker, results, flags, expected = run_both(None, code, quality, offset, compiled=compiled)
+    check(chain, checker, results, flags, expected)
+    # oracle side of pass 2: rewrite the compiled priors with the oracle's own estimates (classifier.h:125-160)
+    adjusted = O.compile_job(spec["job"])
+    for k, (topic, decoder) in enumerate(O.decoder_chain(adjusted)):
+        if decoder["algorithm"] != "pamld":
+            continue
+        noise, concentration = checker.estimate_priors(k)
+        decoder["noise"] = noise
+        decoder["undetermined"]["concentration"] = noise
+        for record in decoder["codec"].values():
+            record["concentration"] = float(concentration[record["index"] - 1])
+    chain.adjust_priors()
+    chain.reset()
+    tiles = chain.pack(code, quality, offset)
+    results2, flags2 = chain.decode(tiles, 40000)
+    second = O.best_oracle(adjusted, len(code))
+    expected2 = second.decode(O.ReadBatch(code, quality, offset))
+    check(chain, second, results2, flags2, expected2)
+    assert not np.array_equal(results2[1]["confidence"], results[1]["confidence"])
+
+
+def test_large_batch_properties():
+    """Size-independent properties on a batch far beyond what the oracle finishes in seconds (2^22 reads):
+    every read lands in exactly one accumulator row, pf <= count, totals match, decode is idempotent, and a
+    random slice of it is bit-compared with the oracle."""
+    import torch
+    spec = workload.load("c1")
+    compiled = compile_job(spec["job"])
+    chain = DecoderChain(compiled, device=0)
+    n = 1 << 22
+    tiles = workload.synthesize_device_tiles(chain, compiled, n, torch.device("cuda:0"), seed=77)
+    flags = torch.zeros(n, dtype=torch.uint8, device="cuda:0")
+    results = [torch.zeros((n, 2), dtype=torch.float64, device="cuda:0")]
+    chain.decode_device(tiles, n, flags, results)
+    torch.cuda.synchronize()
+    u, f = chain.accumulators(0)
+    assert int(u[:, 0].sum()) == n and chain.totals()[0] == n
+    assert np.all(u[:, 1] <= u[:, 0])
+    assert chain.totals()[1] == int((flags == 0).sum().item())
+    first = results[0].clone()
+    flags.zero_()
+    chain.decode_device(tiles, n, flags, results)
+    torch.cuda.synchronize()
+    assert torch.equal(first, results[0])
+    from pheniqs_b200 import RESULT_DTYPE
+    begin = 1234567
+    count = 50000
+    bases, nmask, quality = [t[:, begin:begin + count].cpu().numpy() for t in tiles[0]]
+    code, q = workload.unpack_tile(bases, nmask, quality, 16)
+    batch = O.ReadBatch.from_fixed([np.zeros((count, 0), np.uint8), code[:, :8], code[:, 8:], np.zeros((count, 0), np.uint8)],
+                                   [np.zeros((count, 0), np.uint8), q[:, :8], q[:, 8:], np.zeros((count, 0), np.uint8)])
+    expected = O.best_oracle(compiled, 4).decode(batch)
+    got = results[0][begin:begin + count].cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+    helpers.compare_pamld(got, expected.index[:, 0], expected.distance[:, 0], expected.confidence[:, 0], "slice")
+    assert np.array_equal(flags[begin:begin + count].cpu().numpy(), expected.qcfail)
