@@ -60,6 +60,7 @@ struct StagingSlot {
     std::vector< DeviceBuffer< uint32_t > > quality;
     std::vector< DeviceBuffer< phq_result > > results;
     DeviceBuffer< uint8_t > qcfail;
+    DeviceBuffer< unsigned char > tie_list;  /* queue of the PAMLD tie pass: counter, read indices, records */
 };
 
 constexpr int STAGING_SLOTS = 3;
@@ -82,6 +83,7 @@ struct phq_handle {
     LaunchGeometry geometry;
     StagingSlot slot[STAGING_SLOTS];
     bool slots_ready;
+    DeviceBuffer< unsigned char > tie_list;  /* tie queue of the device path (one batch in flight per handle) */
     cudaEvent_t timing_start;
     cudaEvent_t timing_stop;
     cudaStream_t timing_stream;
@@ -195,21 +197,33 @@ void destroy(phq_handle* h) {
             for(auto& b : s.quality) { b.release(); }
             for(auto& b : s.results) { b.release(); }
             s.qcfail.release();
+            s.tie_list.release();
             cudaEventDestroy(s.done);
             cudaStreamDestroy(s.stream);
         }
     }
+    h->tie_list.release();
     if(h->timing_start != NULL) { cudaEventDestroy(h->timing_start); }
     if(h->timing_stop != NULL) { cudaEventDestroy(h->timing_stop); }
     delete h;
 }
 
 /* launch the chain on device-resident planes (TranscodingDecoder::classify order, transcode.h:51-60) */
-void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t* qcfail, phq_result* const* results, cudaStream_t stream) {
+void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t* qcfail, phq_result* const* results, DeviceBuffer< unsigned char >& tie_list, cudaStream_t stream) {
     const size_t n_decoders(h->chain.size());
+    bool needs_queue(false);
+    for(const auto& d : h->chain) { needs_queue = needs_queue || d.algorithm == PHQ_PAMLD; }
+    /* layout: [16 bytes: counter][n_reads TieRecord][n_reads int] */
+    const size_t record_bytes(static_cast< size_t >(n_reads) * sizeof(TieRecord));
+    if(needs_queue) { tie_list.reserve(16 + record_bytes + static_cast< size_t >(n_reads) * sizeof(int)); }
     for(size_t k(0); k < n_decoders; ++k) {
         DecoderParams p(h->params[k]);
         p.totals = (k + 1 == n_decoders) ? h->totals() : NULL;
+        if(tie_list.pointer != NULL) {
+            p.tie_count = reinterpret_cast< unsigned* >(tie_list.pointer);
+            p.tie_record = reinterpret_cast< TieRecord* >(tie_list.pointer + 16);
+            p.tie_list = reinterpret_cast< int* >(tie_list.pointer + 16 + record_bytes);
+        }
         TileArguments a;
         memset(&a, 0, sizeof(a));
         a.n_reads = n_reads;
@@ -230,7 +244,7 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
             status = launch_count(p, a, h->geometry, stream);
         }
         PHQ_CUDA(status);
-        ++h->kernel_launches;
+        h->kernel_launches += h->chain[k].algorithm == PHQ_PAMLD ? PAMLD_KERNEL_LAUNCHES : 1;
     }
 }
 
@@ -491,7 +505,7 @@ int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile*
         if(device_qcfail == NULL) { throw InternalError("device_qcfail is required"); }
         cudaStream_t s(static_cast< cudaStream_t >(stream));
         PHQ_CUDA(cudaEventRecord(handle->timing_start, s));
-        launch_chain(handle, n_reads, device_tiles, device_qcfail, device_results, s);
+        launch_chain(handle, n_reads, device_tiles, device_qcfail, device_results, handle->tie_list, s);
         PHQ_CUDA(cudaEventRecord(handle->timing_stop, s));
         handle->timing_stream = s;
         handle->timing_valid = true;
@@ -542,7 +556,7 @@ int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
                     device_results[k] = s.results[k].pointer;
                 }
             }
-            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, device_results.data(), s.stream);
+            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, device_results.data(), s.tie_list, s.stream);
             for(size_t k(0); k < n_decoders; ++k) {
                 if(device_results[k] != NULL) {
                     PHQ_CUDA(cudaMemcpyAsync(results[k] + begin, device_results[k], static_cast< size_t >(count) * sizeof(phq_result), cudaMemcpyDeviceToHost, s.stream));

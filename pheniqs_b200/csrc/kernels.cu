@@ -38,7 +38,6 @@ constexpr int MAX_WARPS = 12;
 constexpr int STAGE_ENTRIES = 1024;             /* barcodes per staged chunk: 16 KB */
 constexpr int SHARED_ACCUMULATOR_ROWS = 1025;   /* per-CTA accumulators live in shared memory up to N + 1 = 1025 rows */
 constexpr unsigned FULL_MASK = 0xffffffffu;
-#define TIE_SCRATCH_BYTES(G) ((G) * 16 * 8 + 32 * 4)
 
 /* ------------------------------------------------------------------ shared memory plan (host and device agree) */
 struct SharedPlan {
@@ -211,132 +210,6 @@ struct BarcodeStream {
     }
 };
 
-/* ------------------------------------------------------------------ PAMLD exact tie path
-   Structural ties (equal multisets of mismatch qualities under equal priors) are common for noise reads.
-   The reference resolves them by the rounding of its position ordered Kahan sums (barcode.h:147-162) and
-   then keeps the first maximum (pamld.cpp:73), so they are re-evaluated here in exactly that operation
-   order. The warp works on ONE flagged read at a time, lanes = barcodes:
-
-     1. the read's subset product tables are copied from the owner lane's column to a small linear block
-        (any lane -> entry mapping is then conflict free or a broadcast);
-     2. every barcode's product is recomputed, 32 per step; those within 2^-18 of the best are candidates
-        and are compacted into a list;
-     3. each candidate's sigma_q is evaluated bit for bit as the reference does; among equal priors the
-        smaller sigma wins and equal sigmas keep the lower index, which is what strict > over
-        p = pow(B, sigma) * prior yields. pow() is only consulted across different priors.
-
-   The code is deliberately rolled: it runs for ~2 % of the reads and must not evict the scan loop from
-   the instruction cache. */
-struct Candidate {
-    double prior;
-    double sigma;
-    int index;              /* -1 = none */
-};
-struct TieScratch {
-    double* table;          /* [G * 16] linear copy of the flagged read's subset products */
-    int* list;              /* [32] candidate barcode indices */
-};
-
-__device__ __noinline__ double adjusted_probability(double base, double sigma, double prior) {
-    return pow(base, sigma) * prior;
-}
-__device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, double base) {
-    if(a.index < 0) { return false; }
-    if(b.index < 0) { return true; }
-    if(a.prior == b.prior) {
-        return a.sigma < b.sigma || (a.sigma == b.sigma && a.index < b.index);
-    }
-    const double pa = adjusted_probability(base, a.sigma, a.prior);
-    const double pb = adjusted_probability(base, b.sigma, b.prior);
-    return pa > pb || (pa == pb && a.index < b.index);
-}
-
-/* sigma_q of one barcode exactly as Barcode::compensated_decoding_probability accumulates it */
-__device__ __noinline__ double exact_sigma(const double* __restrict__ phred_global, int L, uint32_t m, uint32_t nmask, const uint32_t* quality) {
-    const double* __restrict__ tq = phred_global + PHRED_TRUE_POSITIVE_QUALITY;
-    const double U = phred_global[PHRED_UNIFORM_QUALITY];
-    double sigma = 0.0, compensation = 0.0;
-    #pragma unroll 1
-    for(int j = 0; j < L; ++j) {
-        uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        q = q > 127u ? 127u : q;
-        double value;
-        if(q == 0u) { value = 0.0; }
-        else if((nmask >> j) & 1u) { value = U; }
-        else if((m >> j) & 1u) { value = static_cast< double >(q); }
-        else { value = tq[q]; }
-        const double y = __dsub_rn(value, compensation);
-        const double t = __dadd_rn(sigma, y);
-        compensation = __dsub_rn(__dsub_rn(t, sigma), y);
-        sigma = t;
-    }
-    return sigma;
-}
-
-__device__ __noinline__ void evaluate_candidates(Candidate& best, const BarcodeEntry* __restrict__ barcodes, const double* __restrict__ phred_global,
-                                                 int L, const int* list, int count, uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t* quality) {
-    const int lane = threadIdx.x & 31;
-    if(lane < count) {
-        Candidate c;
-        c.index = list[lane];
-        const BarcodeEntry e = barcodes[c.index];
-        const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
-        c.prior = e.prior;
-        c.sigma = exact_sigma(phred_global, L, m, nmask, quality);
-        if(beats(c, best, phred_global[PHRED_BASE])) { best = c; }
-    }
-}
-
-template < int G >
-__device__ __noinline__ int resolve_ties(const BarcodeEntry* __restrict__ barcodes, int barcode_cardinality, int L,
-                                         const double* __restrict__ phred_global, TieScratch scratch, const double* owner_column,
-                                         uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t (&quality)[G], double threshold) {
-    const int lane = threadIdx.x & 31;
-    for(int e = lane; e < G * 16; e += WARP_SIZE) { scratch.table[e] = owner_column[e * WARP_SIZE]; }
-    __syncwarp();
-
-    Candidate best;
-    best.prior = 0; best.sigma = 0; best.index = -1;
-    int count = 0;
-    #pragma unroll 1
-    for(int base = 0; base < barcode_cardinality; base += WARP_SIZE) {
-        const int b = base + lane;
-        bool candidate = false;
-        if(b < barcode_cardinality) {
-            const BarcodeEntry e = barcodes[b];
-            const uint32_t m = ((o_lo ^ e.lo) | (o_hi ^ e.hi)) | nmask;
-            double t = e.prior;
-            #pragma unroll
-            for(int g = 0; g < G; ++g) { t *= scratch.table[g * 16 + ((m >> (4 * g)) & 15u)]; }
-            candidate = t >= threshold;
-        }
-        const unsigned found = __ballot_sync(FULL_MASK, candidate);
-        if(found) {
-            const int fresh = __popc(found);
-            if(count + fresh > WARP_SIZE) {
-                evaluate_candidates(best, barcodes, phred_global, L, scratch.list, count, o_lo, o_hi, nmask, quality);
-                count = 0;
-                __syncwarp();
-            }
-            if(candidate) { scratch.list[count + __popc(found & ((1u << lane) - 1u))] = b; }
-            count += fresh;
-            __syncwarp();
-        }
-    }
-    if(count) { evaluate_candidates(best, barcodes, phred_global, L, scratch.list, count, o_lo, o_hi, nmask, quality); }
-    const double base = phred_global[PHRED_BASE];
-    #pragma unroll 1
-    for(int offset = 16; offset > 0; offset >>= 1) {
-        Candidate other;
-        other.prior = __shfl_xor_sync(FULL_MASK, best.prior, offset);
-        other.sigma = __shfl_xor_sync(FULL_MASK, best.sigma, offset);
-        other.index = __shfl_xor_sync(FULL_MASK, best.index, offset);
-        if(beats(other, best, base)) { best = other; }
-    }
-    __syncwarp();
-    return best.index;
-}
-
 /* ------------------------------------------------------------------ PAMLD hot loop pieces */
 
 /* m = (o_lo ^ e_lo) | (o_hi ^ e_hi) | n_mask as two LOP3 (truth table 0xBE = (a ^ b) | c) */
@@ -411,7 +284,81 @@ __device__ __forceinline__ void select_four(Selection& s, double p0, double p1, 
     s.second = max(max(s.second, second), __double2hiint(low));
 }
 
-/* ------------------------------------------------------------------ PAMLD */
+/* ------------------------------------------------------------------ PAMLD decision
+   pamld.cpp:87-122 followed by Decoder::classify (decoder.h:68-76) and Classifier::classify
+   (classifier.h:78-86) for one read whose winner is known. `t` is the winner's subset product and
+   `others` the sum of the prior adjusted products of all other barcodes, both relative to the per-read
+   constant `base_probability` (P0), which is divided out of confidence = p / sigma_p (pamld.cpp:92). */
+struct Verdict {
+    int decoded;
+    int distance;
+    double confidence;
+    uint32_t qcfail;
+};
+__device__ __forceinline__ Verdict pamld_decide(const DecoderParams& P, const Accumulator& accumulator, uint32_t* band_counter,
+                                                int best_index, uint32_t m, double t, double prior, double others,
+                                                double base_probability, bool uniform, uint32_t high_quality_mask, uint32_t qcfail) {
+    /* when every position scores UNIFORM_BASE_QUALITY all barcodes share sigma = L x U and the
+       reference's P(r|b) is the host libm constant */
+    if(uniform) { base_probability = P.uniform_observation_probability; }
+    const double conditional_probability = base_probability * t;
+    const double p = t * prior;
+    const double sigma_p = p + (others + P.adjusted_noise_probability / base_probability);
+    Verdict v;
+    v.confidence = p / sigma_p;
+    v.distance = __popc(m);
+    v.decoded = best_index + 1;
+    v.qcfail = qcfail;
+    const int high_quality_distance = __popc(m & high_quality_mask);
+    const int best_row = best_index + 1;
+
+    bool band = fabs(v.confidence - P.confidence_threshold) <= 1e-12;
+    if(!uniform) { band = band || fabs(conditional_probability - P.random_barcode_probability) <= 1e-12 * P.random_barcode_probability; }
+    if(band) { atomicAdd(band_counter, 1u); }
+
+    if(conditional_probability > P.random_barcode_probability) {
+        if(v.confidence > P.confidence_threshold) {
+            accumulator.add(best_row, ACC_CONFIDENCE, v.confidence);
+            if(P.high_quality_distance_threshold > 0 && high_quality_distance >= P.high_quality_distance_threshold) { v.qcfail = 1; }
+            if(!v.qcfail) { accumulator.add(best_row, ACC_PF_CONFIDENCE, v.confidence); }
+        } else {
+            accumulator.add(best_row, ACC_LOW_CONFIDENCE, 1u);
+            v.qcfail = 1;
+        }
+    } else {
+        accumulator.add(best_row, ACC_LOW_CONDITIONAL, 1u);
+        v.qcfail = 1;
+        v.decoded = 0;
+        v.distance = 0;
+        v.confidence = 0.0;
+    }
+    if(v.decoded > 0 && v.distance > 0) {
+        accumulator.add(v.decoded, ACC_DISTANCE, static_cast< uint32_t >(v.distance));
+        if(!v.qcfail) { accumulator.add(v.decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(v.distance)); }
+    }
+    accumulator.add(v.decoded, ACC_COUNT, 1u);
+    if(!v.qcfail) { accumulator.add(v.decoded, ACC_PF_COUNT, 1u); }
+    return v;
+}
+
+/* per-position factors of an observation: what one base contributes to P0 and to a mismatch product */
+struct PositionFactor {
+    double factor;          /* B ^ s(match)    : match_factor[q], B^U for an ambiguous base, 1 for q = 0 */
+    double ratio;           /* B ^ (s(mismatch) - s(match)) : mismatch_ratio[q], 1 for ambiguous / q = 0 */
+    bool uniform;           /* scores UNIFORM_BASE_QUALITY */
+};
+__device__ __forceinline__ PositionFactor position_factor(const double* __restrict__ phred_shared, double uniform_factor, uint32_t q, bool ambiguous) {
+    PositionFactor f;
+    q = q > 127u ? 127u : q;
+    f.factor = phred_shared[PHRED_MATCH_FACTOR + q];
+    f.ratio = phred_shared[PHRED_MISMATCH_RATIO + q];
+    f.uniform = ambiguous && q != 0u;
+    if(f.uniform) { f.factor = uniform_factor; }
+    if(ambiguous) { f.ratio = 1.0; }
+    return f;
+}
+
+/* ------------------------------------------------------------------ PAMLD scan kernel */
 template < int G >
 __global__ void __launch_bounds__(MAX_WARPS * WARP_SIZE, 1)
 pamld_kernel(const DecoderParams P, const TileArguments A) {
@@ -424,19 +371,8 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     /* per-lane subset product tables: entry (g, subset) of this lane at [(g * 16 + subset) * 32 + lane] */
     const uint32_t window = shared_address(smem);
     const uint32_t aligned_tables = ((window + S.plan.off_tables + 4095u) & ~4095u) - window;
-    const int warp_cardinality = blockDim.x >> 5;
-    double* const warp_table = reinterpret_cast< double* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE);
-    double* const table = warp_table + lane;
+    double* const table = reinterpret_cast< double* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE) + lane;
     const uint32_t table_base = shared_address(table);
-    /* behind the tables of all warps: per warp a linear table copy and a candidate list for the tie path */
-    TieScratch tie_scratch;
-    {
-        unsigned char* const behind = smem + aligned_tables + static_cast< size_t >(warp_cardinality) * (G * 16 * WARP_SIZE * 8);
-        tie_scratch.table = reinterpret_cast< double* >(behind + static_cast< size_t >(warp) * TIE_SCRATCH_BYTES(G));
-        tie_scratch.list = reinterpret_cast< int* >(tie_scratch.table + G * 16);
-    }
-    const double* const match_factor = S.phred + PHRED_MATCH_FACTOR;
-    const double* const mismatch_ratio = S.phred + PHRED_MISMATCH_RATIO;
     const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
     const int L = P.nucleotide_cardinality;
 
@@ -485,16 +421,12 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
             #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 const int j = g * 4 + k;
-                uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
+                const uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
                 if(static_cast< int >(q) >= P.high_quality_threshold) { high_quality_mask |= 1u << j; }
-                q = q > 127u ? 127u : q;
-                const bool ambiguous = (nmask >> j) & 1u;
-                double factor = match_factor[q];
-                double ratio = mismatch_ratio[q];
-                if(ambiguous && q != 0u) { factor = uniform_factor; ++uniform_positions; }
-                if(ambiguous) { ratio = 1.0; }
-                base_probability *= factor;
-                w[k] = ratio;
+                const PositionFactor f = position_factor(S.phred, uniform_factor, q, (nmask >> j) & 1u);
+                uniform_positions += f.uniform ? 1 : 0;
+                base_probability *= f.factor;
+                w[k] = f.ratio;
             }
             double* const t = table + g * 16 * WARP_SIZE;
             const double w01 = w[0] * w[1];
@@ -559,87 +491,43 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
                 ++iteration;
             }
         }
-        const double best_p = selection.best;
-        const double rest = selection.rest;
-        const int second_high = selection.second;
-        int best_index = selection.index;
-        const int best_high = __double2hiint(best_p);
 
-        /* ---- structural ties: exact re-evaluation, one flagged read at a time, whole warp cooperating */
-        const bool tied = valid && (second_high + 1 >= best_high);
-        unsigned pending = __ballot_sync(FULL_MASK, tied);
-        if(pending) {
-            if(lane == 0) { atomicAdd(&S.misc[2], static_cast< uint32_t >(__popc(pending))); }
-            while(pending) {
-                const int source = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const uint32_t s_lo = __shfl_sync(FULL_MASK, o_lo, source);
-                const uint32_t s_hi = __shfl_sync(FULL_MASK, o_hi, source);
-                const uint32_t s_nmask = __shfl_sync(FULL_MASK, nmask, source);
-                uint32_t s_quality[G];
-                #pragma unroll
-                for(int g = 0; g < G; ++g) { s_quality[g] = __shfl_sync(FULL_MASK, quality[g], source); }
-                const int s_high = __shfl_sync(FULL_MASK, best_high, source);
-                /* lower bound of the best product, widened by 2^-18 */
-                const double threshold = __hiloint2double(s_high, 0) * (1.0 - 3.814697265625e-06);
-                const int winner = resolve_ties< G >(P.barcodes, P.barcode_cardinality, L, P.phred, tie_scratch, warp_table + source, s_lo, s_hi, s_nmask, s_quality, threshold);
-                if(lane == source && winner >= 0) { best_index = winner; }
+        /* ---- structural ties (runner-up within 2^-19 of the winner) are resolved by the reference through the
+           rounding of its Kahan sums; pamld_tie_kernel reproduces that. Such reads are only queued here. */
+        const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
+        const unsigned queued = __ballot_sync(FULL_MASK, tied);
+        if(queued) {
+            unsigned slot = 0;
+            if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
+            slot = __shfl_sync(FULL_MASK, slot, 0);
+            if(tied) {
+                const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
+                P.tie_list[at] = static_cast< int >(r);
+                TieRecord record;
+                record.best = selection.best;
+                record.rest = selection.rest;
+                record.base_probability = base_probability;
+                record.high_quality_mask = high_quality_mask;
+                record.uniform = uniform_positions == L ? 1u : 0u;
+                P.tie_record[at] = record;
             }
         }
 
-        /* ---- decision for this lane's read (pamld.cpp:87-122) */
-        if(valid) {
-            const BarcodeEntry e = P.barcodes[best_index];
+        /* ---- decision for this lane's read */
+        const bool decided = valid && !tied;
+        if(decided) {
+            const BarcodeEntry e = P.barcodes[selection.index];
             const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, e.lo, e.hi);
             const double t = subset_product< G >(table_base, m);
-            /* when every position scores UNIFORM_BASE_QUALITY all barcodes share sigma = L x U and the
-               reference's P(r|b) is the host libm constant */
-            const bool uniform = uniform_positions == L;
-            if(uniform) { base_probability = P.uniform_observation_probability; }
-            const double conditional_probability = base_probability * t;
-            /* confidence = p / sigma_p (pamld.cpp:92) with the per-read constant P0 divided out of both */
-            const double p = t * e.prior;
-            const double sigma_p = best_p + (rest + P.adjusted_noise_probability / base_probability);
-            double confidence = p / sigma_p;
-            int distance = __popc(m);
-            const int high_quality_distance = __popc(m & high_quality_mask);
-            int decoded = best_index + 1;
-            const int best_row = best_index + 1;
-
-            bool band = fabs(confidence - P.confidence_threshold) <= 1e-12;
-            if(!uniform) { band = band || fabs(conditional_probability - P.random_barcode_probability) <= 1e-12 * P.random_barcode_probability; }
-            if(band) { atomicAdd(&S.misc[3], 1u); }
-
-            if(conditional_probability > P.random_barcode_probability) {
-                if(confidence > P.confidence_threshold) {
-                    S.accumulator.add(best_row, ACC_CONFIDENCE, confidence);
-                    if(P.high_quality_distance_threshold > 0 && high_quality_distance >= P.high_quality_distance_threshold) { qcfail = 1; }
-                    if(!qcfail) { S.accumulator.add(best_row, ACC_PF_CONFIDENCE, confidence); }
-                } else {
-                    S.accumulator.add(best_row, ACC_LOW_CONFIDENCE, 1u);
-                    qcfail = 1;
-                }
-            } else {
-                S.accumulator.add(best_row, ACC_LOW_CONDITIONAL, 1u);
-                qcfail = 1;
-                decoded = 0;
-                distance = 0;
-                confidence = 0.0;
-            }
-            /* Decoder::classify (decoder.h:68-76), Classifier::classify (classifier.h:78-86) */
-            if(decoded > 0 && distance > 0) {
-                S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
-                if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
-            }
-            S.accumulator.add(decoded, ACC_COUNT, 1u);
-            if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
-
-            A.qcfail[r] = static_cast< uint8_t >(qcfail);
-            if(A.results != nullptr) { store_result(A.results, r, decoded, distance, confidence); }
+            const Verdict v = pamld_decide(P, S.accumulator, &S.misc[3], selection.index, m, t, e.prior, selection.rest, base_probability,
+                                           uniform_positions == L, high_quality_mask, qcfail);
+            qcfail = v.qcfail;
+            A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
+            if(A.results != nullptr) { store_result(A.results, r, v.decoded, v.distance, v.confidence); }
         }
         if(P.totals != nullptr) {
-            const unsigned live = __ballot_sync(FULL_MASK, valid);
-            const unsigned pass = __ballot_sync(FULL_MASK, valid && !qcfail);
+            const unsigned live = __ballot_sync(FULL_MASK, decided);
+            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
             if(lane == 0) {
                 atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
                 atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
@@ -648,6 +536,200 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
         __syncwarp();
     }
     block_epilogue(S, P);
+}
+
+/* ------------------------------------------------------------------ PAMLD tie kernel
+   Structural ties (equal multisets of mismatch qualities under equal priors) are common for noise reads
+   (~2 % of the synthetic workloads). The reference resolves them by the rounding of its position ordered
+   Kahan sums (barcode.h:147-162) and then keeps the first maximum (pamld.cpp:73), so the queued reads are
+   re-decoded here in exactly that operation order. One warp per read, lanes = barcodes:
+
+     1. the read's per-position factors and its subset product table (linear, so any lane -> entry mapping
+        is conflict free or a broadcast) are rebuilt in shared memory;
+     2. every barcode's prior adjusted product is computed, 32 per step; the warp keeps the maximum and the
+        sum of everything else;
+     3. barcodes within 2^-18 of the maximum are candidates; each candidate's sigma_q is evaluated bit for
+        bit as the reference does; among equal priors the smaller sigma wins and equal sigmas keep the
+        lower index, which is what strict > over p = pow(B, sigma) * prior yields. pow() is only consulted
+        across different priors;
+     4. lane 0 takes the decision and updates the accumulators.
+
+   Full occupancy (no per-lane tables) hides the latency of the serial Kahan chains. */
+struct Candidate {
+    double prior;
+    double sigma;
+    int index;              /* -1 = none */
+};
+__device__ __noinline__ double adjusted_probability(double base, double sigma, double prior) {
+    return pow(base, sigma) * prior;
+}
+__device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, double base) {
+    if(a.index < 0) { return false; }
+    if(b.index < 0) { return true; }
+    if(a.prior == b.prior) {
+        return a.sigma < b.sigma || (a.sigma == b.sigma && a.index < b.index);
+    }
+    const double pa = adjusted_probability(base, a.sigma, a.prior);
+    const double pb = adjusted_probability(base, b.sigma, b.prior);
+    return pa > pb || (pa == pb && a.index < b.index);
+}
+
+constexpr int TIE_WARPS = 8;
+constexpr int TIE_STAGE_ENTRIES = 1024;
+
+template < int G >
+__global__ void __launch_bounds__(TIE_WARPS * WARP_SIZE, 4)
+pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
+    extern __shared__ __align__(16) unsigned char tie_smem[];   /* barcode table when it fits TIE_STAGE_ENTRIES */
+    __shared__ double phred_shared[PHRED_TABLE_SIZE];
+    __shared__ double table_shared[TIE_WARPS][G * 16];
+    __shared__ double value_shared[TIE_WARPS][3][G * 4];         /* per position: match score, mismatch score (phred.cpp:39-72), mismatch ratio */
+    __shared__ uint32_t block_counter[4];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int N = P.barcode_cardinality;
+    const unsigned tie_cardinality = *P.tie_count;
+    if(blockIdx.x * TIE_WARPS >= tie_cardinality) { return; }
+
+    const bool staged = N <= TIE_STAGE_ENTRIES;
+    const BarcodeEntry* barcodes = P.barcodes;
+    if(staged) {
+        uint4* const stage = reinterpret_cast< uint4* >(tie_smem);
+        for(int i = tid; i < N; i += blockDim.x) { stage[i] = reinterpret_cast< const uint4* >(P.barcodes)[i]; }
+        barcodes = reinterpret_cast< const BarcodeEntry* >(tie_smem);
+    }
+    for(int i = tid; i < PHRED_TABLE_SIZE; i += blockDim.x) { phred_shared[i] = P.phred[i]; }
+    if(tid < 4) { block_counter[tid] = 0; }
+    __syncthreads();
+
+    Accumulator accumulator;
+    accumulator.shared_u32 = nullptr;
+    accumulator.shared_f64 = nullptr;
+    accumulator.global_u64 = P.acc_u64;
+    accumulator.global_f64 = P.acc_f64;
+    const int L = P.nucleotide_cardinality;
+    const double uniform_quality = phred_shared[PHRED_UNIFORM_QUALITY];
+    const double base = phred_shared[PHRED_BASE];
+    double* const table = table_shared[warp];
+    double* const match_value = value_shared[warp][0];
+    double* const mismatch_value = value_shared[warp][1];
+    double* const ratio_value = value_shared[warp][2];
+    const unsigned warp_cardinality = gridDim.x * TIE_WARPS;
+
+    for(unsigned item = blockIdx.x * TIE_WARPS + warp; item < tie_cardinality; item += warp_cardinality) {
+        const long long r = P.tie_list[item];
+        const TieRecord record = P.tie_record[item];
+        /* ---- the observation (every lane reads the same words: broadcast) */
+        uint32_t o_lo, o_hi, nmask;
+        {
+            const uint32_t w0 = A.bases[r];
+            o_lo = w0 & 0xffffu;
+            o_hi = w0 >> 16;
+            nmask = A.nmask[r];
+            if(G > 4) {
+                const uint32_t w1 = A.bases[A.pitch + r];
+                o_lo |= w1 << 16;
+                o_hi |= w1 & 0xffff0000u;
+                nmask |= static_cast< uint32_t >(A.nmask[A.pitch + r]) << 16;
+            }
+        }
+        /* ---- per-position scores: lane j owns position j */
+        if(lane < G * 4) {
+            uint32_t q = (A.quality[(lane >> 2) * A.pitch + r] >> (8 * (lane & 3))) & 0xffu;
+            q = q > 127u ? 127u : q;
+            const bool ambiguous = (nmask >> lane) & 1u;
+            match_value[lane] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : phred_shared[PHRED_TRUE_POSITIVE_QUALITY + q]);
+            mismatch_value[lane] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : static_cast< double >(q));
+            ratio_value[lane] = ambiguous ? 1.0 : phred_shared[PHRED_MISMATCH_RATIO + q];
+        }
+        __syncwarp();
+        /* subset product table (linear: any lane -> entry mapping is conflict free or a broadcast), same
+           association as the scan kernel: ((w0 w1) w2) w3 */
+        #pragma unroll
+        for(int e = lane; e < G * 16; e += WARP_SIZE) {
+            const int g = e >> 4;
+            double t = 1.0;
+            #pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                if((e >> k) & 1) { t *= ratio_value[g * 4 + k]; }
+            }
+            table[e] = t;
+        }
+        __syncwarp();
+
+        /* ---- candidates: barcodes within 2^-18 of the scan's maximum; each one's sigma_q exactly */
+        const double threshold = __hiloint2double(__double2hiint(record.best), 0) * (1.0 - 3.814697265625e-06);
+        Candidate best;
+        best.prior = 0; best.sigma = 0; best.index = -1;
+        #pragma unroll 1
+        for(int first = 0; first < N; first += WARP_SIZE) {
+            const int b = first + lane;
+            bool candidate = false;
+            uint32_t m = 0;
+            double prior = 0.0;
+            if(b < N) {
+                const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
+                m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
+                prior = __hiloint2double(raw.w, raw.z);
+                double p = table[m & 15u];
+                #pragma unroll
+                for(int g = 1; g < G; ++g) { p *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
+                candidate = p * prior >= threshold;
+            }
+            if(__any_sync(FULL_MASK, candidate)) {
+                if(candidate) {
+                    /* Barcode::compensated_decoding_probability's accumulation, bit for bit (barcode.h:147-162) */
+                    double sigma = 0.0, compensation = 0.0;
+                    #pragma unroll 4
+                    for(int j = 0; j < L; ++j) {
+                        const double value = ((m >> j) & 1u) ? mismatch_value[j] : match_value[j];
+                        const double y = __dsub_rn(value, compensation);
+                        const double t = __dadd_rn(sigma, y);
+                        compensation = __dsub_rn(__dsub_rn(t, sigma), y);
+                        sigma = t;
+                    }
+                    Candidate c;
+                    c.prior = prior; c.sigma = sigma; c.index = b;
+                    if(beats(c, best, base)) { best = c; }
+                }
+                __syncwarp();
+            }
+        }
+        #pragma unroll 1
+        for(int offset = 16; offset > 0; offset >>= 1) {
+            Candidate other;
+            other.prior = __shfl_xor_sync(FULL_MASK, best.prior, offset);
+            other.sigma = __shfl_xor_sync(FULL_MASK, best.sigma, offset);
+            other.index = __shfl_xor_sync(FULL_MASK, best.index, offset);
+            if(beats(other, best, base)) { best = other; }
+        }
+
+        if(lane == 0) {
+            const int winner = best.index >= 0 ? best.index : 0;
+            const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + winner);
+            const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
+            const double prior = __hiloint2double(raw.w, raw.z);
+            double t = table[m & 15u];
+            #pragma unroll
+            for(int g = 1; g < G; ++g) { t *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
+            /* everything but the winner: the scan's total minus the winner. The winner is within 2^-18 of
+               the scan's maximum, so the first difference is exact (Sterbenz) and nothing cancels. */
+            const double others = (record.best - t * prior) + record.rest;
+            const uint32_t qcfail = A.qcfail[r];
+            const Verdict v = pamld_decide(P, accumulator, &block_counter[3], winner, m, t, prior, others, record.base_probability,
+                                           record.uniform != 0u, record.high_quality_mask, qcfail);
+            A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
+            if(A.results != nullptr) { store_result(A.results, r, v.decoded, v.distance, v.confidence); }
+            atomicAdd(&block_counter[0], 1u);
+            if(!v.qcfail) { atomicAdd(&block_counter[1], 1u); }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if(tid < 2 && P.totals != nullptr && block_counter[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(block_counter[tid])); }
+    if(tid == 3 && P.diagnostics != nullptr && block_counter[3]) { atomicAdd(&P.diagnostics[DIAG_THRESHOLD_BAND], static_cast< unsigned long long >(block_counter[3])); }
+    if(tid == 2 && P.diagnostics != nullptr && blockIdx.x == 0 && tie_cardinality) { atomicAdd(&P.diagnostics[DIAG_EXACT_PATH], static_cast< unsigned long long >(tie_cardinality)); }
 }
 
 /* ------------------------------------------------------------------ MDD */
@@ -800,7 +882,7 @@ count_kernel(const DecoderParams P, const TileArguments A) {
 template < int G >
 cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     const SharedPlan plan = make_plan(params.barcode_cardinality, true);
-    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double) + TIE_SCRATCH_BYTES(G);
+    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double);
     if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
     int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
     warps = warps > MAX_WARPS ? MAX_WARPS : warps;
@@ -810,7 +892,14 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
     const int threads = warps * WARP_SIZE;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
+    status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
+    if(status != cudaSuccess) { return status; }
     pamld_kernel< G ><<< grid, threads, bytes, stream >>>(params, tile);
+    status = cudaGetLastError();
+    if(status != cudaSuccess) { return status; }
+    /* the queue length is only known on the device: a fixed grid strides over it */
+    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
+    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, TIE_WARPS * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     return cudaGetLastError();
 }
 

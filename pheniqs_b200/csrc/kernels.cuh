@@ -39,6 +39,15 @@ enum { ACC_COUNT = 0, ACC_PF_COUNT = 1, ACC_DISTANCE = 2, ACC_LOW_CONDITIONAL = 
 enum { ACC_CONFIDENCE = 0, ACC_PF_CONFIDENCE = 1, ACC_F64_COLUMNS = 2 };
 enum { DIAG_EXACT_PATH = 0, DIAG_THRESHOLD_BAND = 1, DIAG_COLUMNS = 2 };
 
+/* what the scan kernel hands to the tie kernel for a queued read */
+struct __align__(16) TieRecord {
+    double best;                /* the scan's maximum prior adjusted product (relative to P0) */
+    double rest;                /* the scan's sum of all other products */
+    double base_probability;    /* P0 */
+    uint32_t high_quality_mask;
+    uint32_t uniform;
+};
+
 struct DecoderParams {
     int32_t algorithm;
     int32_t barcode_cardinality;
@@ -62,6 +71,9 @@ struct DecoderParams {
     double* acc_f64;                            /* [(N+1)][2] device */
     unsigned long long* totals;                 /* [2] count, pf_count; NULL unless this is the last decoder of the chain */
     unsigned long long* diagnostics;            /* [DIAG_COLUMNS] */
+    int* tie_list;                              /* [n_reads] reads whose winner needs the exact tie path (PAMLD) */
+    TieRecord* tie_record;                      /* [n_reads] parallel to tie_list */
+    unsigned* tie_count;                        /* length of tie_list, reset before every scan */
 };
 
 struct TileArguments {
@@ -79,7 +91,9 @@ struct LaunchGeometry {
     size_t shared_memory_per_block_optin;
 };
 
-/* each returns the CUDA error of the launch; all are asynchronous on `stream` */
+/* each returns the CUDA error of the launch; all are asynchronous on `stream`.
+   launch_pamld launches two kernels (scan, then the tie pass over the reads the scan queued). */
+enum { PAMLD_KERNEL_LAUNCHES = 2, MDD_KERNEL_LAUNCHES = 1, COUNT_KERNEL_LAUNCHES = 1 };
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 /* naive / passthrough bookkeeping: count and pf_count of the undetermined row (and the chain totals) */

@@ -66,7 +66,8 @@ def test_baseline_configs(name, device_path):
     code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 60000, seed=21, sampling="zipf" if name == "c4" else "prior")
     state = run_both(None, code, quality, offset, compiled=compiled, device_path=device_path)
     check(*state)
-    assert state[0].statistics()["kernel_launches"] == state[0].n_decoders
+    # one kernel per decoder, plus the tie pass of every PAMLD decoder
+    assert state[0].statistics()["kernel_launches"] == sum(2 if info.algorithm == 0 else 1 for info in state[0].info)
 
 
 def test_whitelist_config_reduced():
