@@ -60,43 +60,57 @@ def pair_words_per_read(chain) -> int:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one
+    `nvidia-smi -lms 100` process streaming CSV lines while the timed steps run."""
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index = index
         self.samples = []
-        self.stop = threading.Event()
+        self.process = None
         self.thread = None
+        self.active = threading.Event()
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        for line in self.process.stdout:
+            if self.active.is_set():
+                self.samples.append([x.strip() for x in line.strip().split(",")])
 
     def __enter__(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        try:
+            self.process = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+            time.sleep(0.35)            # let the first samples arrive before the timed region starts
+        except Exception:
+            self.process = None
         return self
 
+    def begin(self):
+        self.active.set()
+
+    def end(self):
+        self.active.clear()
+
     def __exit__(self, *a):
-        self.stop.set()
-        self.thread.join(timeout=6)
+        if self.process is not None:
+            self.process.terminate()
+            try:
+                self.process.wait(timeout=5)
+            except Exception:
+                self.process.kill()
 
     def summary(self):
-        if not self.samples:
+        rows = [s for s in self.samples if len(s) >= 7 and s[0].replace(".", "").isdigit()]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        sm = sorted(float(s[0]) for s in rows)
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in rows)]
+        power = [float(s[2]) for s in rows if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(power) if power else None}
 
 
 def measured_peaks():
@@ -107,6 +121,17 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(workload_name, n_reads):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/traffic.json: bytes per read), scaled to this launch; None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        per_read = json.load(open(path))[workload_name]["dram_bytes_per_read"]
+        return per_read * n_reads
+    except Exception:
+        return None
 
 
 def host_sample(compiled, spec, n_reads, seed):
@@ -221,6 +246,7 @@ def main():
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
+        clocks.begin()
         torch.cuda.nvtx.range_push("timed")
         start.record(stream)
         for _ in range(args.steps):
@@ -228,6 +254,15 @@ def main():
         stop.record(stream)
         barrier()
         torch.cuda.nvtx.range_pop()
+        # keep the GPU under the same load a little longer when the timed region was too short to sample
+        extra = 0
+        while len(clocks.samples) < 3 and extra < 200:
+            step()
+            extra += 1
+            if extra % 4 == 0:
+                torch.cuda.synchronize(device)
+        torch.cuda.synchronize(device)
+        clocks.end()
     elapsed_ms = start.elapsed_time(stop)
     launches = chain.statistics()["kernel_launches"] - launches_before
     # the dominant kernel alone, timed live with CUDA events on the launching stream (phq_last_kernel_milliseconds)
@@ -256,7 +291,7 @@ def main():
     clock_summary = clocks.summary()
     sm_mhz = clock_summary.get("sm_mhz") or 0
     sm_count = torch.cuda.get_device_properties(device).multi_processor_count
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, n),
                 "peak_source": peak_source, "kernel": "pamld_kernel" if chain.info[0].algorithm == 0 or args.workload != "c2" else "mdd_kernel",
                 "kernel_ms_per_launch_set": kernel_ms_mean, "algorithmic_bytes_per_read": bytes_per_read,
                 "pair_words_per_read": pairs, "pair_words_per_s": pairs * n / (kernel_ms_mean * 1e-3),

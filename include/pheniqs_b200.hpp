@@ -1,0 +1,161 @@
+/*  pheniqs_b200.hpp — header-only C++ host wrapper over the C ABI (pheniqs_b200.h).
+
+    Mirrors the shape of the reference's per-thread decoder object so the call site in
+    TranscodingThread::run (transcode.h:202-225) changes from "classify one Read" to
+    "classify one batch of Reads":
+
+        reference                                   here
+        ---------                                   ----
+        TranscodingDecoder(const Value& ontology)   phq::BatchDecoder(compiled_json, device)
+        classify(const Read&, Read&)                classify(batch)            (transcode.h:51-65)
+        collect(const TranscodingDecoder&)          accumulator_buffer() + one all-reduce (transcode.cpp:162-179)
+        finalize()                                  estimate_priors(k)         (classifier.h:94-124)
+        Error subclasses with ErrorCode             phq::Error subclasses with the same codes (error.h:32-136)
+
+    No CUDA or torch types appear; link with -lpheniqs_b200.
+*/
+#ifndef PHENIQS_B200_HPP
+#define PHENIQS_B200_HPP
+
+#include "pheniqs_b200.h"
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace phq {
+
+/* error.h:46-136: one exception class per ErrorCode the path can raise */
+class Error : public std::runtime_error {
+    public:
+        const int code;
+        Error(int code, const std::string& message) : std::runtime_error(message), code(code) {}
+};
+class InternalError : public Error { public: explicit InternalError(const std::string& m) : Error(PHQ_INTERNAL_ERROR, m) {} };
+class ConfigurationError : public Error { public: explicit ConfigurationError(const std::string& m) : Error(PHQ_CONFIGURATION_ERROR, m) {} };
+class OutOfMemoryError : public Error { public: explicit OutOfMemoryError(const std::string& m) : Error(PHQ_OUT_OF_MEMORY_ERROR, m) {} };
+class SequenceError : public Error { public: explicit SequenceError(const std::string& m) : Error(PHQ_SEQUENCE_ERROR, m) {} };
+class OverflowError : public Error { public: explicit OverflowError(const std::string& m) : Error(PHQ_OVERFLOW_ERROR, m) {} };
+
+inline void raise(int status, const char* message) {
+    const std::string text(message != NULL ? message : "");
+    switch(status) {
+        case PHQ_OK: return;
+        case PHQ_CONFIGURATION_ERROR: throw ConfigurationError(text);
+        case PHQ_OUT_OF_MEMORY_ERROR: throw OutOfMemoryError(text);
+        case PHQ_SEQUENCE_ERROR: throw SequenceError(text);
+        case PHQ_OVERFLOW_ERROR: throw OverflowError(text);
+        case PHQ_INTERNAL_ERROR: throw InternalError(text);
+        default: throw Error(status, text);
+    }
+}
+
+/* Transcode::compile for the decoder sections of a job */
+inline std::string compile_job(const std::string& job_json) {
+    char* out(NULL);
+    raise(phq_compile_job(job_json.c_str(), &out), phq_last_global_error());
+    std::string compiled(out);
+    phq_free(out);
+    return compiled;
+}
+
+/* host planes of one decoder for a batch, owned by the caller (pinned when `pinned`) */
+class TileBuffer {
+    public:
+        TileBuffer() : n_reads_(0), pinned_(false) { tile_.bases = NULL; tile_.nmask = NULL; tile_.quality = NULL; tile_.pitch = 0; }
+        TileBuffer(const TileBuffer&) = delete;
+        void operator=(const TileBuffer&) = delete;
+        ~TileBuffer() { release(); }
+        void allocate(const phq_decoder_info& info, int64_t n_reads, bool pinned) {
+            release();
+            n_reads_ = n_reads;
+            pinned_ = pinned;
+            const size_t pitch(static_cast< size_t >(n_reads > 0 ? n_reads : 1));
+            tile_.pitch = static_cast< int64_t >(pitch);
+            tile_.bases = static_cast< const uint32_t* >(get(pitch * info.word_cardinality * sizeof(uint32_t)));
+            tile_.nmask = static_cast< const uint16_t* >(get(pitch * info.word_cardinality * sizeof(uint16_t)));
+            tile_.quality = static_cast< const uint32_t* >(get(pitch * info.quality_word_cardinality * sizeof(uint32_t)));
+        }
+        const phq_tile& tile() const { return tile_; }
+    private:
+        phq_tile tile_;
+        int64_t n_reads_;
+        bool pinned_;
+        void* get(size_t bytes) {
+            void* p(NULL);
+            if(pinned_) { raise(phq_host_alloc(&p, bytes), phq_last_global_error()); }
+            else { p = ::operator new(bytes ? bytes : 1); }
+            return p;
+        }
+        void drop(const void* p) {
+            if(p == NULL) { return; }
+            if(pinned_) { phq_host_free(const_cast< void* >(p)); } else { ::operator delete(const_cast< void* >(p)); }
+        }
+        void release() {
+            drop(tile_.bases); drop(tile_.nmask); drop(tile_.quality);
+            tile_.bases = NULL; tile_.nmask = NULL; tile_.quality = NULL;
+        }
+};
+
+/* one GPU's decoder chain: what a TranscodingThread's TranscodingDecoder is in the reference */
+class BatchDecoder {
+    public:
+        BatchDecoder(const std::string& compiled_job_json, int device) : handle_(NULL) {
+            raise(phq_create(compiled_job_json.c_str(), device, &handle_), phq_last_global_error());
+            const int n(phq_decoder_count(handle_));
+            info_.resize(static_cast< size_t >(n));
+            for(int k(0); k < n; ++k) { check(phq_decoder_describe(handle_, k, &info_[k])); }
+        }
+        BatchDecoder(const BatchDecoder&) = delete;
+        void operator=(const BatchDecoder&) = delete;
+        ~BatchDecoder() { phq_destroy(handle_); }
+
+        size_t decoder_cardinality() const { return info_.size(); }
+        const phq_decoder_info& info(size_t k) const { return info_[k]; }
+
+        /* Rule::apply + packing (transform.h:142-169) for reads held one code byte and one Phred byte per base */
+        void pack(int64_t n_reads, int32_t n_input_segments, const uint8_t* const* code, const uint8_t* const* quality,
+                  const int64_t* const* offset, const std::vector< phq_tile >& tiles) {
+            check(phq_pack(handle_, n_reads, n_input_segments, code, quality, offset, tiles.data()));
+        }
+        /* TranscodingDecoder::classify (transcode.h:51-65) for a batch; host buffers */
+        void classify(int64_t n_reads, const std::vector< phq_tile >& tiles, const uint8_t* qcfail_in,
+                      const std::vector< phq_result* >& results, uint8_t* qcfail_out) {
+            check(phq_decode_batch(handle_, n_reads, tiles.data(), qcfail_in, results.data(), qcfail_out));
+        }
+        /* device pointers, asynchronous on `stream` */
+        void classify_device(int64_t n_reads, const std::vector< phq_tile >& tiles, uint8_t* qcfail, const std::vector< phq_result* >& results, void* stream) {
+            check(phq_decode_batch_device(handle_, n_reads, tiles.data(), qcfail, results.data(), stream));
+        }
+        /* AccumulatingOption tables of decoder k (selector.h:32-60) */
+        void accumulators(size_t k, std::vector< uint64_t >& u64_table, std::vector< double >& f64_table) {
+            const size_t rows(static_cast< size_t >(info_[k].barcode_cardinality) + 1);
+            u64_table.assign(rows * 6, 0);
+            f64_table.assign(rows * 2, 0);
+            check(phq_accumulators(handle_, static_cast< int >(k), u64_table.data(), f64_table.data()));
+        }
+        void totals(uint64_t& count, uint64_t& pf_count) { check(phq_totals(handle_, &count, &pf_count)); }
+        /* the buffer to all-reduce(sum) across GPUs in place of collect() (transcode.cpp:162-179) */
+        void accumulator_buffer(void*& device_pointer, int64_t& n_u64, int64_t& n_f64) { check(phq_accumulator_buffer(handle_, &device_pointer, &n_u64, &n_f64)); }
+        void reset() { check(phq_reset_accumulators(handle_)); }
+        /* Classifier::finalize (classifier.h:94-124) */
+        double estimate_priors(size_t k, std::vector< double >& concentration) {
+            double noise(0);
+            concentration.assign(static_cast< size_t >(info_[k].barcode_cardinality), 0);
+            check(phq_estimate_priors(handle_, static_cast< int >(k), &noise, concentration.data()));
+            return noise;
+        }
+        /* Classifier::adjust_prior (classifier.h:125-160) applied to the live tables */
+        void set_priors(size_t k, double noise, const std::vector< double >& concentration) {
+            check(phq_set_priors(handle_, static_cast< int >(k), noise, concentration.data()));
+        }
+        phq_handle* handle() { return handle_; }
+
+    private:
+        phq_handle* handle_;
+        std::vector< phq_decoder_info > info_;
+        void check(int status) { raise(status, phq_last_error(handle_)); }
+};
+
+}   /* namespace phq */
+#endif
