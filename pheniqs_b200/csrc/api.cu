@@ -74,6 +74,8 @@ struct phq_handle {
     std::vector< DecoderParams > params;
     std::vector< std::vector< ScratchSegment > > scratch;
     std::vector< BarcodeEntry* > device_barcodes;
+    std::vector< void* > device_grid;          /* combinatorial codec blobs (kernels.cuh), NULL where not applicable */
+    std::vector< int32_t > grid_shape;         /* per decoder: grid_a, grid_b, grid_entries, grid_split */
     double* device_phred;
     unsigned char* device_accumulators;
     std::vector< int64_t > offset_u64;
@@ -140,6 +142,84 @@ void upload_barcodes(phq_handle* h, size_t k) {
     PHQ_CUDA(cudaMemcpy(h->device_barcodes[k], table.data(), table.size() * sizeof(BarcodeEntry), cudaMemcpyHostToDevice));
 }
 
+/*  Combinatorial codecs (C1: 12 distinct i7 words x 8 distinct i5 words = 96 barcodes): group the barcodes
+    by the word of their first segment and index the distinct words of the remaining segments, so the scan
+    forms each word's probability once per read (pamld_grid_kernel). Built when it pays: at least two
+    segments, a supported shape, and far fewer distinct words than barcodes. */
+void upload_grid(phq_handle* h, size_t k) {
+    const DecoderSpec& d(h->chain[k]);
+    if(h->device_grid[k] != NULL) { cudaFree(h->device_grid[k]); h->device_grid[k] = NULL; }
+    for(int i(0); i < 4; ++i) { h->grid_shape[k * 4 + i] = 0; }
+    if(d.algorithm != PHQ_PAMLD || d.segment_cardinality < 2) { return; }
+    const int32_t split(d.segment_length[0]);
+    const int32_t L(d.nucleotide_cardinality);
+    if(!grid_shape_supported(split, L)) { return; }
+    auto planes = [&](int32_t b, int32_t from, int32_t to, uint32_t& lo, uint32_t& hi) {
+        lo = 0; hi = 0;
+        for(int32_t j(from); j < to; ++j) {
+            const uint8_t code(d.barcode[static_cast< size_t >(b) * L + j]);
+            const uint32_t two(code == 1 ? 0u : code == 2 ? 1u : code == 4 ? 2u : 3u);
+            lo |= (two & 1u) << (j - from);
+            hi |= (two >> 1) << (j - from);
+        }
+    };
+    std::map< std::pair< uint32_t, uint32_t >, std::vector< int32_t > > by_prefix;
+    std::map< std::pair< uint32_t, uint32_t >, int32_t > suffix_index;
+    std::vector< std::pair< uint32_t, uint32_t > > suffix_word;
+    std::vector< int32_t > suffix_of(static_cast< size_t >(d.barcode_cardinality));
+    for(int32_t b(0); b < d.barcode_cardinality; ++b) {
+        uint32_t lo, hi;
+        planes(b, 0, split, lo, hi);
+        by_prefix[std::make_pair(lo, hi)].push_back(b);
+        planes(b, split, L, lo, hi);
+        const auto key(std::make_pair(lo, hi));
+        auto found(suffix_index.find(key));
+        if(found == suffix_index.end()) {
+            found = suffix_index.emplace(key, static_cast< int32_t >(suffix_word.size())).first;
+            suffix_word.push_back(key);
+        }
+        suffix_of[b] = found->second;
+    }
+    const size_t KA(by_prefix.size()), KB(suffix_word.size());
+    if((KA + KB) * 2 > static_cast< size_t >(d.barcode_cardinality) || KB > 64) { return; }
+    struct Cell { uint32_t a, b, c, d; };
+    std::vector< Cell > blob(KA + KB);
+    std::vector< Cell > entries;
+    size_t at(0);
+    for(const auto& run : by_prefix) {
+        Cell header;
+        header.a = run.first.first; header.b = run.first.second;
+        header.c = static_cast< uint32_t >(entries.size());
+        for(int32_t b : run.second) {
+            Cell e;
+            e.a = static_cast< uint32_t >(suffix_of[b]) * 256u;
+            e.b = static_cast< uint32_t >(b);
+            memcpy(&e.c, &d.concentration[b], sizeof(double));
+            entries.push_back(e);
+        }
+        while(entries.size() % 4 != 0) {        /* pad the run with prior 0: the product is 0 and never wins */
+            Cell e;
+            e.a = 0; e.b = 0; e.c = 0; e.d = 0;
+            entries.push_back(e);
+        }
+        header.d = static_cast< uint32_t >(entries.size()) - header.c;
+        blob[at++] = header;
+    }
+    for(size_t i(0); i < KB; ++i) {
+        Cell w;
+        w.a = suffix_word[i].first; w.b = suffix_word[i].second; w.c = 0; w.d = 0;
+        blob[at++] = w;
+    }
+    blob.insert(blob.end(), entries.begin(), entries.end());
+    if(blob.size() * 16 > 64 * 1024) { return; }
+    PHQ_CUDA(cudaMalloc(&h->device_grid[k], blob.size() * 16));
+    PHQ_CUDA(cudaMemcpy(h->device_grid[k], blob.data(), blob.size() * 16, cudaMemcpyHostToDevice));
+    h->grid_shape[k * 4 + 0] = static_cast< int32_t >(KA);
+    h->grid_shape[k * 4 + 1] = static_cast< int32_t >(KB);
+    h->grid_shape[k * 4 + 2] = static_cast< int32_t >(entries.size());
+    h->grid_shape[k * 4 + 3] = split;
+}
+
 void refresh_params(phq_handle* h, size_t k) {
     const DecoderSpec& d(h->chain[k]);
     DecoderParams& p(h->params[k]);
@@ -181,6 +261,11 @@ void refresh_params(phq_handle* h, size_t k) {
     p.acc_f64 = h->f64_plane() + h->offset_f64[k];
     p.totals = NULL;
     p.diagnostics = h->diagnostics();
+    p.grid = h->device_grid[k];
+    p.grid_a = h->grid_shape[k * 4 + 0];
+    p.grid_b = h->grid_shape[k * 4 + 1];
+    p.grid_entries = h->grid_shape[k * 4 + 2];
+    p.grid_split = h->grid_shape[k * 4 + 3];
 }
 
 void destroy(phq_handle* h) {
@@ -188,6 +273,7 @@ void destroy(phq_handle* h) {
     if(h->device < 0) { delete h; return; }
     cudaSetDevice(h->device);
     for(auto* p : h->device_barcodes) { if(p != NULL) { cudaFree(p); } }
+    for(auto* p : h->device_grid) { if(p != NULL) { cudaFree(p); } }
     if(h->device_phred != NULL) { cudaFree(h->device_phred); }
     if(h->device_accumulators != NULL) { cudaFree(h->device_accumulators); }
     if(h->slots_ready) {
@@ -342,6 +428,8 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         const size_t n(chain.size());
         h->params.resize(n);
         h->device_barcodes.assign(n, NULL);
+        h->device_grid.assign(n, NULL);
+        h->grid_shape.assign(n * 4, 0);
         h->scratch.resize(n);
         h->offset_u64.resize(n);
         h->offset_f64.resize(n);
@@ -368,6 +456,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
             if(chain[k].tiled()) {
                 PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), static_cast< size_t >(chain[k].barcode_cardinality) * sizeof(BarcodeEntry)));
                 upload_barcodes(h, k);
+                upload_grid(h, k);
             }
             refresh_params(h, k);
         }
@@ -666,6 +755,7 @@ int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* 
         }
         PHQ_CUDA(cudaDeviceSynchronize());
         upload_barcodes(handle, static_cast< size_t >(decoder));
+        upload_grid(handle, static_cast< size_t >(decoder));
         refresh_params(handle, static_cast< size_t >(decoder));
     });
 }

@@ -48,10 +48,14 @@ struct SharedPlan {
     unsigned fixed_bytes;       /* everything except the per-warp tables */
 };
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
-__host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool phred_tables) {
+__host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool phred_tables, int blob_entries = 0) {
     SharedPlan p;
     p.stage_capacity = barcode_cardinality < STAGE_ENTRIES ? barcode_cardinality : STAGE_ENTRIES;
     p.stage_buffers = barcode_cardinality <= STAGE_ENTRIES ? 1 : 2;
+    if(blob_entries > 0) {      /* the combinatorial scan stages its grid blob instead of the barcode table */
+        p.stage_capacity = blob_entries;
+        p.stage_buffers = 1;
+    }
     p.accumulator_rows = (barcode_cardinality + 1 <= SHARED_ACCUMULATOR_ROWS) ? barcode_cardinality + 1 : 0;
     unsigned at = 0;
     p.off_stage = at;       at += align_up(unsigned(p.stage_capacity) * unsigned(p.stage_buffers) * 16u, 128u);
@@ -138,9 +142,9 @@ struct BlockState {
     Accumulator accumulator;
 };
 
-__device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const DecoderParams& P, bool phred_tables) {
+__device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const DecoderParams& P, bool phred_tables, int blob_entries = 0) {
     BlockState s;
-    s.plan = make_plan(P.barcode_cardinality, phred_tables);
+    s.plan = make_plan(P.barcode_cardinality, phred_tables, blob_entries);
     s.stage = reinterpret_cast< BarcodeEntry* >(smem + s.plan.off_stage);
     s.phred = reinterpret_cast< double* >(smem + s.plan.off_phred);
     s.misc = reinterpret_cast< uint32_t* >(smem + s.plan.off_misc);
@@ -538,6 +542,250 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     block_epilogue(S, P);
 }
 
+/* ------------------------------------------------------------------ PAMLD scan kernel for combinatorial codecs
+   Multi-segment codecs are usually combinatorial: C1's 96 dual-index barcodes are 12 distinct i7 words
+   x 8 distinct i5 words. P(r|b) factors over segments, so with A = the first segment and B = the rest
+
+       p_b = SA[word_A(b)] * SB[word_B(b)] * prior_b
+
+   The kernel computes SB for every distinct B word once per read into a per-lane column in shared memory,
+   then walks the barcodes grouped by A word: SA is formed once per A word (uniform loop) and each barcode
+   costs ONE conflict-free LDS.64 (its SB entry), two DMUL and the selection step, instead of four lookups,
+   a mismatch mask and address arithmetic. The scan order is (A word, index); exact ties are queued for
+   pamld_tie_kernel like in the generic kernel, so the first-maximum rule is not affected. */
+struct __align__(16) GridHeader { uint32_t lo, hi, first, count; };                 /* a distinct A word and its run of entries */
+struct __align__(16) GridWord { uint32_t lo, hi, pad0, pad1; };                     /* a distinct B word */
+struct __align__(16) GridEntry { uint32_t suffix_offset; uint32_t index; double prior; };   /* a barcode: SB row (bytes), original index */
+
+/*  Subset tables of the combinatorial scan use groups of W positions (2^W entries of 256 bytes per group and
+    warp). The scan itself does one SB lookup per barcode, so the tables are only read ~44 times per read:
+    W = 2 halves their footprint (8 KB per warp at 16 nucleotides) and doubles the resident warps. */
+template < int W, int table_group, int local >
+__device__ __forceinline__ double group_lookup(uint32_t base, uint32_t m) {
+    constexpr int shift = 8 - W * local;        /* bits W*local.. of m land on bits 8.. of the address */
+    const uint32_t moved = (shift >= 0) ? (m << (shift >= 0 ? shift : 0)) : (m >> (shift >= 0 ? 0 : -shift));
+    uint32_t address;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(address) : "r"(moved), "n"(((1 << W) - 1) << 8), "r"(base));
+    double value;
+    asm volatile("ld.shared.f64 %0, [%1 + %2];" : "=d"(value) : "r"(address), "n"(table_group * (256 << W)));
+    return value;
+}
+/* product over the GROUPS groups of a part whose first table group is `first`; m = the part's mismatch bits from bit 0 */
+template < int W, int first, int GROUPS, int k >
+struct PartProduct {
+    static __device__ __forceinline__ double of(uint32_t base, uint32_t m, double t) {
+        return PartProduct< W, first, GROUPS, k + 1 >::of(base, m, t * group_lookup< W, first + k, k >(base, m));
+    }
+};
+template < int W, int first, int GROUPS >
+struct PartProduct< W, first, GROUPS, GROUPS > {
+    static __device__ __forceinline__ double of(uint32_t, uint32_t, double t) { return t; }
+};
+template < int W, int first, int GROUPS >
+__device__ __forceinline__ double part_product(uint32_t base, uint32_t m) {
+    return PartProduct< W, first, GROUPS, 1 >::of(base, m, group_lookup< W, first, 0 >(base, m));
+}
+__device__ __forceinline__ double column_load(uint32_t address) {
+    double value;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(value) : "r"(address));
+    return value;
+}
+
+constexpr int GRID_MAX_WARPS = 20;
+constexpr int GRID_GROUP_WIDTH = 2;
+
+template < int LA, int LB, int W >
+__global__ void __launch_bounds__(GRID_MAX_WARPS * WARP_SIZE, 1)
+pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
+    constexpr int L = LA + LB;
+    constexpr int G = (L + 3) / 4;              /* quality words */
+    constexpr int GA = (LA + W - 1) / W;        /* table groups of W positions per part */
+    constexpr int GB = (LB + W - 1) / W;
+    constexpr int GROUP_BYTES = 256 << W;
+    constexpr uint32_t MASK_A = (1u << LA) - 1u;
+    constexpr uint32_t MASK_B = (1u << LB) - 1u;
+    extern __shared__ __align__(256) unsigned char smem[];
+    const BlockState S = block_prologue(smem, P, true, P.grid_a + P.grid_b + P.grid_entries);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int warp_cardinality = blockDim.x >> 5;
+    const int KA = P.grid_a;
+    const int KB = P.grid_b;
+
+    /* the grid blob (headers, B words, entries) is staged once per CTA by one TMA bulk copy */
+    const GridHeader* const header = reinterpret_cast< const GridHeader* >(smem + S.plan.off_stage);
+    const GridWord* const word = reinterpret_cast< const GridWord* >(header + KA);
+    const GridEntry* const entry = reinterpret_cast< const GridEntry* >(word + KB);
+    if(tid == 0) {
+        const uint32_t bytes = static_cast< uint32_t >(KA + KB + P.grid_entries) * 16u;
+        mbarrier_expect_tx(&S.mbarrier[0], bytes);
+        tma_bulk_load(smem + S.plan.off_stage, P.grid, bytes, &S.mbarrier[0]);
+    }
+    mbarrier_wait(&S.mbarrier[0], 0);
+
+    /* per warp: (GA + GB) table groups of 2^W entries x 256 bytes, then KB rows of 256 bytes for the B word products */
+    const uint32_t window = shared_address(smem);
+    const uint32_t aligned_tables = ((window + S.plan.off_tables + 4095u) & ~4095u) - window;
+    const size_t warp_bytes = static_cast< size_t >(GA + GB) * GROUP_BYTES;
+    double* const table = reinterpret_cast< double* >(smem + aligned_tables + warp * warp_bytes) + lane;
+    const uint32_t table_base = shared_address(table);
+    double* const suffix = reinterpret_cast< double* >(smem + aligned_tables + warp_cardinality * warp_bytes + static_cast< size_t >(warp) * KB * 256) + lane;
+    const uint32_t suffix_base = shared_address(suffix);
+    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+
+        uint32_t o_lo = 0, o_hi = 0, nmask = 0;
+        uint32_t quality[G];
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { quality[g] = 0; }
+        uint32_t qcfail = 0;
+        if(valid) {
+            const uint32_t w0 = load_stream(A.bases + r);
+            o_lo = w0 & 0xffffu;
+            o_hi = w0 >> 16;
+            nmask = load_stream(A.nmask + r);
+            if(G > 4) {
+                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
+                o_lo |= w1 << 16;
+                o_hi |= w1 & 0xffff0000u;
+                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
+            }
+            #pragma unroll
+            for(int g = 0; g < G; ++g) { quality[g] = load_stream(A.quality + g * A.pitch + r); }
+            qcfail = A.qcfail[r];
+        }
+
+        /* ---- per-position factors; P0 in position order; subset tables per part */
+        double base_probability = 1.0;
+        uint32_t high_quality_mask = 0;
+        int uniform_positions = 0;
+        double w[(GA + GB) * W];
+        #pragma unroll
+        for(int k = 0; k < (GA + GB) * W; ++k) { w[k] = 1.0; }
+        #pragma unroll
+        for(int j = 0; j < L; ++j) {
+            const uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            if(static_cast< int >(q) >= P.high_quality_threshold) { high_quality_mask |= 1u << j; }
+            const PositionFactor f = position_factor(S.phred, uniform_factor, q, (nmask >> j) & 1u);
+            uniform_positions += f.uniform ? 1 : 0;
+            base_probability *= f.factor;
+            w[j < LA ? j : GA * W + (j - LA)] = f.ratio;
+        }
+        #pragma unroll
+        for(int g = 0; g < GA + GB; ++g) {
+            const double* const v = w + g * W;
+            double* const t = table + g * (GROUP_BYTES / 8);
+            if(W == 2) {
+                t[0 * WARP_SIZE] = 1.0;
+                t[1 * WARP_SIZE] = v[0];
+                t[2 * WARP_SIZE] = v[1];
+                t[3 * WARP_SIZE] = v[0] * v[1];
+            } else {
+                const double w01 = v[0] * v[1];
+                const double w02 = v[0] * v[2];
+                const double w12 = v[1] * v[2];
+                const double w012 = w01 * v[2];
+                t[0 * WARP_SIZE] = 1.0;
+                t[1 * WARP_SIZE] = v[0];
+                t[2 * WARP_SIZE] = v[1];
+                t[3 * WARP_SIZE] = w01;
+                t[4 * WARP_SIZE] = v[2];
+                t[5 * WARP_SIZE] = w02;
+                t[6 * WARP_SIZE] = w12;
+                t[7 * WARP_SIZE] = w012;
+                t[8 * WARP_SIZE] = v[W - 1];
+                t[9 * WARP_SIZE] = v[0] * v[W - 1];
+                t[10 * WARP_SIZE] = v[1] * v[W - 1];
+                t[11 * WARP_SIZE] = w01 * v[W - 1];
+                t[12 * WARP_SIZE] = v[2] * v[W - 1];
+                t[13 * WARP_SIZE] = w02 * v[W - 1];
+                t[14 * WARP_SIZE] = w12 * v[W - 1];
+                t[15 * WARP_SIZE] = w012 * v[W - 1];
+            }
+        }
+        __syncwarp();
+
+        const uint32_t a_lo = o_lo & MASK_A, a_hi = o_hi & MASK_A, a_n = nmask & MASK_A;
+        const uint32_t b_lo = (o_lo >> LA) & MASK_B, b_hi = (o_hi >> LA) & MASK_B, b_n = (nmask >> LA) & MASK_B;
+
+        /* ---- SB: the product of every distinct B word, into this lane's column */
+        #pragma unroll 2
+        for(int k = 0; k < KB; ++k) {
+            const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+            const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+            suffix[k * WARP_SIZE] = part_product< W, GA, GB >(table_base, m);
+        }
+        __syncwarp();
+
+        /* ---- barcodes grouped by A word */
+        Selection selection;
+        selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
+        for(int a = 0; a < KA; ++a) {
+            const uint4 h = *reinterpret_cast< const uint4* >(header + a);
+            const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+            const double prefix = part_product< W, 0, GA >(table_base, m);
+            const int last = static_cast< int >(h.z + h.w);
+            #pragma unroll 2
+            for(int i = static_cast< int >(h.z); i < last; i += 4) {        /* runs are padded to a multiple of four with prior 0 */
+                double p[4];
+                #pragma unroll
+                for(int u = 0; u < 4; ++u) {
+                    const uint4 raw = *reinterpret_cast< const uint4* >(entry + i + u);
+                    p[u] = (prefix * column_load(suffix_base + raw.x)) * __hiloint2double(raw.w, raw.z);
+                }
+                select_four(selection, p[0], p[1], p[2], p[3], i);
+            }
+        }
+
+        /* ---- ties are queued; everything else is decided here */
+        const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
+        const unsigned queued = __ballot_sync(FULL_MASK, tied);
+        if(queued) {
+            unsigned slot = 0;
+            if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
+            slot = __shfl_sync(FULL_MASK, slot, 0);
+            if(tied) {
+                const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
+                P.tie_list[at] = static_cast< int >(r);
+                TieRecord record;
+                record.best = selection.best;
+                record.rest = selection.rest;
+                record.base_probability = base_probability;
+                record.high_quality_mask = high_quality_mask;
+                record.uniform = uniform_positions == L ? 1u : 0u;
+                P.tie_record[at] = record;
+            }
+        }
+        const bool decided = valid && !tied;
+        if(decided) {
+            const int winner = static_cast< int >(entry[selection.index].index);
+            const BarcodeEntry e = P.barcodes[winner];
+            const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, e.lo, e.hi);
+            const double t = part_product< W, 0, GA >(table_base, m & MASK_A) * part_product< W, GA, GB >(table_base, (m >> LA) & MASK_B);
+            const Verdict v = pamld_decide(P, S.accumulator, &S.misc[3], winner, m, t, e.prior, selection.rest, base_probability,
+                                           uniform_positions == L, high_quality_mask, qcfail);
+            qcfail = v.qcfail;
+            A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
+            if(A.results != nullptr) { store_result(A.results, r, v.decoded, v.distance, v.confidence); }
+        }
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, decided);
+            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
+            }
+        }
+        __syncwarp();
+    }
+    block_epilogue(S, P);
+}
+
 /* ------------------------------------------------------------------ PAMLD tie kernel
    Structural ties (equal multisets of mismatch qualities under equal priors) are common for noise reads
    (~2 % of the synthetic workloads). The reference resolves them by the rounding of its position ordered
@@ -903,10 +1151,46 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
     return cudaGetLastError();
 }
 
+/* the combinatorial scan: staging area = the grid blob instead of the barcode table */
+template < int LA, int LB >
+cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    constexpr int W = GRID_GROUP_WIDTH;
+    constexpr int G = (LA + LB + 3) / 4;
+    constexpr int GA = (LA + W - 1) / W;
+    constexpr int GB = (LB + W - 1) / W;
+    const int blob_entries = params.grid_a + params.grid_b + params.grid_entries;
+    const SharedPlan plan = make_plan(params.barcode_cardinality, true, blob_entries);
+    const size_t fixed = plan.fixed_bytes;
+    const size_t per_warp = static_cast< size_t >(GA + GB) * (256 << W) + static_cast< size_t >(params.grid_b) * 256;
+    if(fixed + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - fixed) / per_warp);
+    warps = warps > GRID_MAX_WARPS ? GRID_MAX_WARPS : warps;
+    const size_t bytes = fixed + per_warp * warps;
+    cudaError_t status = cudaFuncSetAttribute(pamld_grid_kernel< LA, LB, W >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    if(status != cudaSuccess) { return status; }
+    const int threads = warps * WARP_SIZE;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
+    status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
+    if(status != cudaSuccess) { return status; }
+    pamld_grid_kernel< LA, LB, W ><<< grid, threads, bytes, stream >>>(params, tile);
+    status = cudaGetLastError();
+    if(status != cudaSuccess) { return status; }
+    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
+    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, TIE_WARPS * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+    return cudaGetLastError();
+}
+
 }   /* namespace */
 
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     if(tile.n_reads <= 0) { return cudaSuccess; }
+    if(params.grid != nullptr) {
+        if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_grid< 6, 6 >(params, tile, geometry, stream); }
+        if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_grid< 8, 8 >(params, tile, geometry, stream); }
+        if(params.grid_split == 10 && params.nucleotide_cardinality == 20) { return launch_pamld_grid< 10, 10 >(params, tile, geometry, stream); }
+        if(params.grid_split == 12 && params.nucleotide_cardinality == 24) { return launch_pamld_grid< 12, 12 >(params, tile, geometry, stream); }
+    }
     switch(params.group_cardinality) {
         case 1: return launch_pamld_groups< 1 >(params, tile, geometry, stream);
         case 2: return launch_pamld_groups< 2 >(params, tile, geometry, stream);

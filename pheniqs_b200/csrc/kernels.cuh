@@ -71,6 +71,11 @@ struct DecoderParams {
     double* acc_f64;                            /* [(N+1)][2] device */
     unsigned long long* totals;                 /* [2] count, pf_count; NULL unless this is the last decoder of the chain */
     unsigned long long* diagnostics;            /* [DIAG_COLUMNS] */
+    const void* grid;                           /* combinatorial codec blob: grid_a headers, grid_b words, grid_entries entries (16 B each); NULL = generic scan */
+    int32_t grid_a;
+    int32_t grid_b;
+    int32_t grid_entries;
+    int32_t grid_split;                         /* nucleotides of the first segment */
     int* tie_list;                              /* [n_reads] reads whose winner needs the exact tie path (PAMLD) */
     TieRecord* tie_record;                      /* [n_reads] parallel to tie_list */
     unsigned* tie_count;                        /* length of tie_list, reset before every scan */
@@ -99,6 +104,8 @@ cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, c
 /* naive / passthrough bookkeeping: count and pf_count of the undetermined row (and the chain totals) */
 cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& geometry);
+/* (first segment length, total length) pairs the combinatorial scan is instantiated for */
+inline bool grid_shape_supported(int split, int total) { return (split == 6 && total == 12) || (split == 8 && total == 16) || (split == 10 && total == 20) || (split == 12 && total == 24); }
 
 }   /* namespace phq */
 #endif

@@ -126,6 +126,34 @@ def test_random_decoders(variant, short):
     check(*run_both(None, code, quality, offset, qcfail, compiled=compiled))
 
 
+@pytest.mark.parametrize("shape", [(6, 6, 5, 7), (8, 8, 6, 9), (10, 10, 14, 14), (12, 12, 3, 11)])
+def test_combinatorial_codecs(shape):
+    """Dual-index style codecs (distinct first-segment words x distinct second-segment words, not all
+    combinations present, runs not a multiple of four) take the combinatorial scan kernel."""
+    la, lb, ka, kb = shape
+    rng = np.random.default_rng(la * 100 + ka)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def words(count, length):
+        out = []
+        while len(out) < count:
+            w = rng.integers(0, 4, size=length)
+            if all((w != v).sum() >= 3 for v in out):
+                out.append(w)
+        return [letters[w].tobytes().decode() for w in out]
+    first, second = words(ka, la), words(kb, lb)
+    codec = {}
+    for i, a in enumerate(first):
+        for j, b in enumerate(second):
+            if rng.random() < 0.8:
+                codec["@%02d_%02d" % (j, i)] = {"barcode": [a, b], "concentration": float(rng.integers(1, 4))}
+    job = {"sample": {"algorithm": "pamld", "transform": {"token": ["0:0:%d" % la, "1:0:%d" % lb]}, "codec": codec, "noise": 0.04, "confidence threshold": 0.9,
+                      "high quality threshold": 20, "high quality distance threshold": 2}}
+    compiled = compile_job(job)
+    code, quality, offset, _ = workload.synthesize(compiled, [0], 30000, seed=8)
+    check(*run_both(None, code, quality, offset, compiled=compiled))
+
+
 def test_structural_ties_take_the_exact_path():
     """Uniform priors + all-N / low quality observations: many exactly tied barcodes; first maximum must match."""
     rng = np.random.default_rng(3)
