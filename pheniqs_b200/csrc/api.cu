@@ -299,16 +299,15 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
     const size_t n_decoders(h->chain.size());
     bool needs_queue(false);
     for(const auto& d : h->chain) { needs_queue = needs_queue || d.algorithm == PHQ_PAMLD; }
-    /* layout: [16 bytes: counter][n_reads TieRecord][n_reads int] */
-    const size_t record_bytes(static_cast< size_t >(n_reads) * sizeof(TieRecord));
-    if(needs_queue) { tie_list.reserve(16 + record_bytes + static_cast< size_t >(n_reads) * sizeof(int)); }
+    /* layout: [16 bytes: counter][up to PAMLD_LAUNCH_READS TieRecord] */
+    const long long queue_reads(n_reads < PAMLD_LAUNCH_READS ? n_reads : PAMLD_LAUNCH_READS);
+    if(needs_queue) { tie_list.reserve(16 + static_cast< size_t >(queue_reads) * sizeof(TieRecord)); }
     for(size_t k(0); k < n_decoders; ++k) {
         DecoderParams p(h->params[k]);
         p.totals = (k + 1 == n_decoders) ? h->totals() : NULL;
         if(tie_list.pointer != NULL) {
             p.tie_count = reinterpret_cast< unsigned* >(tie_list.pointer);
             p.tie_record = reinterpret_cast< TieRecord* >(tie_list.pointer + 16);
-            p.tie_list = reinterpret_cast< int* >(tie_list.pointer + 16 + record_bytes);
         }
         TileArguments a;
         memset(&a, 0, sizeof(a));
@@ -325,12 +324,28 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
             a.nmask = tiles[k].nmask;
             a.quality = tiles[k].quality;
             a.pitch = tiles[k].pitch;
-            status = h->chain[k].algorithm == PHQ_PAMLD ? launch_pamld(p, a, h->geometry, stream) : launch_mdd(p, a, h->geometry, stream);
+            if(h->chain[k].algorithm == PHQ_PAMLD) {
+                /* sub-launches over read ranges keep the tie queue bounded; planes are [word][read], so a range is a pointer offset */
+                for(long long begin(0); begin < n_reads && status == cudaSuccess; begin += PAMLD_LAUNCH_READS) {
+                    TileArguments part(a);
+                    part.n_reads = (n_reads - begin) < PAMLD_LAUNCH_READS ? (n_reads - begin) : PAMLD_LAUNCH_READS;
+                    part.bases = a.bases + begin;
+                    part.nmask = a.nmask + begin;
+                    part.quality = a.quality + begin;
+                    part.qcfail = a.qcfail + begin;
+                    part.results = a.results != NULL ? a.results + begin : NULL;
+                    status = launch_pamld(p, part, h->geometry, stream);
+                    h->kernel_launches += PAMLD_KERNEL_LAUNCHES;
+                }
+            } else {
+                status = launch_mdd(p, a, h->geometry, stream);
+                h->kernel_launches += MDD_KERNEL_LAUNCHES;
+            }
         } else {
             status = launch_count(p, a, h->geometry, stream);
+            h->kernel_launches += COUNT_KERNEL_LAUNCHES;
         }
         PHQ_CUDA(status);
-        h->kernel_launches += h->chain[k].algorithm == PHQ_PAMLD ? PAMLD_KERNEL_LAUNCHES : 1;
     }
 }
 

@@ -506,13 +506,18 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
             slot = __shfl_sync(FULL_MASK, slot, 0);
             if(tied) {
                 const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
-                P.tie_list[at] = static_cast< int >(r);
                 TieRecord record;
                 record.best = selection.best;
                 record.rest = selection.rest;
                 record.base_probability = base_probability;
                 record.high_quality_mask = high_quality_mask;
                 record.uniform = uniform_positions == L ? 1u : 0u;
+                record.o_lo = o_lo;
+                record.o_hi = o_hi;
+                record.nmask = nmask;
+                record.read = static_cast< uint32_t >(r);
+                #pragma unroll
+                for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
                 P.tie_record[at] = record;
             }
         }
@@ -751,13 +756,18 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
             slot = __shfl_sync(FULL_MASK, slot, 0);
             if(tied) {
                 const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
-                P.tie_list[at] = static_cast< int >(r);
                 TieRecord record;
                 record.best = selection.best;
                 record.rest = selection.rest;
                 record.base_probability = base_probability;
                 record.high_quality_mask = high_quality_mask;
                 record.uniform = uniform_positions == L ? 1u : 0u;
+                record.o_lo = o_lo;
+                record.o_hi = o_hi;
+                record.nmask = nmask;
+                record.read = static_cast< uint32_t >(r);
+                #pragma unroll
+                for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
                 P.tie_record[at] = record;
             }
         }
@@ -822,23 +832,41 @@ __device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, do
     return pa > pb || (pa == pb && a.index < b.index);
 }
 
-constexpr int TIE_WARPS = 8;
+/* warps per CTA of the tie kernel: its per-warp workspace is static shared memory (48 KB limit) */
+__host__ __device__ constexpr int tie_warps(int G) { return G <= 4 ? 8 : 4; }
 constexpr int TIE_STAGE_ENTRIES = 1024;
+constexpr int TIE_READS = 4;                    /* reads per warp: eight lanes each */
+constexpr int TIE_LANES = WARP_SIZE / TIE_READS;
+
+/* per warp scratch of the tie kernel */
+template < int G >
+struct TieWorkspace {
+    double table[TIE_READS][G * 16];            /* linear subset product tables */
+    double match_value[TIE_READS][G * 4];       /* per position substitution lookup when the base matches (phred.cpp:39-72) */
+    double mismatch_value[TIE_READS][G * 4];    /* ... when it does not */
+    double ratio[TIE_READS][G * 4];
+    double sigma[WARP_SIZE];                    /* evaluated candidates */
+    double prior[WARP_SIZE];
+    uint32_t list[WARP_SIZE];                   /* candidate = read slot << 28 | barcode */
+    uint32_t o_lo[TIE_READS], o_hi[TIE_READS], nmask[TIE_READS];
+};
 
 template < int G >
-__global__ void __launch_bounds__(TIE_WARPS * WARP_SIZE, 4)
+__global__ void __launch_bounds__(tie_warps(G) * WARP_SIZE, 3)
 pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     extern __shared__ __align__(16) unsigned char tie_smem[];   /* barcode table when it fits TIE_STAGE_ENTRIES */
     __shared__ double phred_shared[PHRED_TABLE_SIZE];
-    __shared__ double table_shared[TIE_WARPS][G * 16];
-    __shared__ double value_shared[TIE_WARPS][3][G * 4];         /* per position: match score, mismatch score (phred.cpp:39-72), mismatch ratio */
+    constexpr int TIE_WARPS = tie_warps(G);
+    __shared__ TieWorkspace< G > workspace[TIE_WARPS];
     __shared__ uint32_t block_counter[4];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int slot = lane / TIE_LANES;          /* which of the warp's reads this lane works on */
+    const int sub = lane % TIE_LANES;
     const int N = P.barcode_cardinality;
     const unsigned tie_cardinality = *P.tie_count;
-    if(blockIdx.x * TIE_WARPS >= tie_cardinality) { return; }
+    if(blockIdx.x * TIE_WARPS * TIE_READS >= tie_cardinality) { return; }
 
     const bool staged = N <= TIE_STAGE_ENTRIES;
     const BarcodeEntry* barcodes = P.barcodes;
@@ -859,101 +887,115 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     const int L = P.nucleotide_cardinality;
     const double uniform_quality = phred_shared[PHRED_UNIFORM_QUALITY];
     const double base = phred_shared[PHRED_BASE];
-    double* const table = table_shared[warp];
-    double* const match_value = value_shared[warp][0];
-    double* const mismatch_value = value_shared[warp][1];
-    double* const ratio_value = value_shared[warp][2];
-    const unsigned warp_cardinality = gridDim.x * TIE_WARPS;
+    TieWorkspace< G >& W = workspace[warp];
+    const unsigned stride = gridDim.x * TIE_WARPS * TIE_READS;
 
-    for(unsigned item = blockIdx.x * TIE_WARPS + warp; item < tie_cardinality; item += warp_cardinality) {
-        const long long r = P.tie_list[item];
-        const TieRecord record = P.tie_record[item];
-        /* ---- the observation (every lane reads the same words: broadcast) */
-        uint32_t o_lo, o_hi, nmask;
-        {
-            const uint32_t w0 = A.bases[r];
-            o_lo = w0 & 0xffffu;
-            o_hi = w0 >> 16;
-            nmask = A.nmask[r];
-            if(G > 4) {
-                const uint32_t w1 = A.bases[A.pitch + r];
-                o_lo |= w1 << 16;
-                o_hi |= w1 & 0xffff0000u;
-                nmask |= static_cast< uint32_t >(A.nmask[A.pitch + r]) << 16;
-            }
-        }
-        /* ---- per-position scores: lane j owns position j */
-        if(lane < G * 4) {
-            uint32_t q = (A.quality[(lane >> 2) * A.pitch + r] >> (8 * (lane & 3))) & 0xffu;
+    for(unsigned first_item = (blockIdx.x * TIE_WARPS + warp) * TIE_READS; first_item < tie_cardinality; first_item += stride) {
+        const unsigned item = first_item + slot;
+        const bool live = item < tie_cardinality;
+        /* everything the scan knew about the read travels in the record: one contiguous 80-byte read per item */
+        TieRecord record;
+        if(live) { record = P.tie_record[item]; }
+        else { record.best = 0; record.rest = 0; record.base_probability = 1; record.o_lo = 0; record.o_hi = 0; record.nmask = 0; record.read = 0; record.uniform = 0; record.high_quality_mask = 0; }
+        const uint32_t o_lo = record.o_lo, o_hi = record.o_hi, nmask = record.nmask;
+        if(sub == 0) { W.o_lo[slot] = o_lo; W.o_hi[slot] = o_hi; W.nmask[slot] = nmask; }
+
+        /* ---- per-position scores: the eight lanes of a read share its positions */
+        for(int j = sub; j < G * 4; j += TIE_LANES) {
+            uint32_t q = live ? (record.quality[j >> 2] >> (8 * (j & 3))) & 0xffu : 0u;
             q = q > 127u ? 127u : q;
-            const bool ambiguous = (nmask >> lane) & 1u;
-            match_value[lane] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : phred_shared[PHRED_TRUE_POSITIVE_QUALITY + q]);
-            mismatch_value[lane] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : static_cast< double >(q));
-            ratio_value[lane] = ambiguous ? 1.0 : phred_shared[PHRED_MISMATCH_RATIO + q];
+            const bool ambiguous = (nmask >> j) & 1u;
+            W.match_value[slot][j] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : phred_shared[PHRED_TRUE_POSITIVE_QUALITY + q]);
+            W.mismatch_value[slot][j] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : static_cast< double >(q));
+            W.ratio[slot][j] = ambiguous ? 1.0 : phred_shared[PHRED_MISMATCH_RATIO + q];
         }
         __syncwarp();
         /* subset product table (linear: any lane -> entry mapping is conflict free or a broadcast), same
            association as the scan kernel: ((w0 w1) w2) w3 */
-        #pragma unroll
-        for(int e = lane; e < G * 16; e += WARP_SIZE) {
+        for(int e = sub; e < G * 16; e += TIE_LANES) {
             const int g = e >> 4;
             double t = 1.0;
             #pragma unroll
             for(int k = 0; k < 4; ++k) {
-                if((e >> k) & 1) { t *= ratio_value[g * 4 + k]; }
+                if((e >> k) & 1) { t *= W.ratio[slot][g * 4 + k]; }
             }
-            table[e] = t;
+            W.table[slot][e] = t;
         }
         __syncwarp();
 
-        /* ---- candidates: barcodes within 2^-18 of the scan's maximum; each one's sigma_q exactly */
+        /* ---- candidates: barcodes within 2^-18 of the scan's maximum, compacted over the whole warp, then
+           each one's sigma_q evaluated exactly by one lane */
         const double threshold = __hiloint2double(__double2hiint(record.best), 0) * (1.0 - 3.814697265625e-06);
         Candidate best;
         best.prior = 0; best.sigma = 0; best.index = -1;
-        #pragma unroll 1
-        for(int first = 0; first < N; first += WARP_SIZE) {
-            const int b = first + lane;
-            bool candidate = false;
-            uint32_t m = 0;
-            double prior = 0.0;
-            if(b < N) {
+        int count = 0;
+        const double* const table = W.table[slot];
+
+        auto evaluate = [&](int pending) {
+            if(lane < pending) {
+                const uint32_t packed = W.list[lane];
+                const int owner = packed >> 28;
+                const int b = packed & 0x0fffffff;
                 const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
-                m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
-                prior = __hiloint2double(raw.w, raw.z);
+                const uint32_t m = ((W.o_lo[owner] ^ raw.x) | (W.o_hi[owner] ^ raw.y)) | W.nmask[owner];
+                /* Barcode::compensated_decoding_probability's accumulation, bit for bit (barcode.h:147-162) */
+                const double* const on_match = W.match_value[owner];
+                const double* const on_mismatch = W.mismatch_value[owner];
+                double sigma = 0.0, compensation = 0.0;
+                #pragma unroll 4
+                for(int j = 0; j < L; ++j) {
+                    const double value = ((m >> j) & 1u) ? on_mismatch[j] : on_match[j];
+                    const double y = __dsub_rn(value, compensation);
+                    const double t = __dadd_rn(sigma, y);
+                    compensation = __dsub_rn(__dsub_rn(t, sigma), y);
+                    sigma = t;
+                }
+                W.sigma[lane] = sigma;
+                W.prior[lane] = __hiloint2double(raw.w, raw.z);
+            }
+            __syncwarp();
+            /* the first lane of every read folds in the candidates that belong to it */
+            if(sub == 0) {
+                for(int c = 0; c < pending; ++c) {
+                    const uint32_t packed = W.list[c];
+                    if(static_cast< int >(packed >> 28) == slot) {
+                        Candidate other;
+                        other.prior = W.prior[c]; other.sigma = W.sigma[c]; other.index = static_cast< int >(packed & 0x0fffffff);
+                        if(beats(other, best, base)) { best = other; }
+                    }
+                }
+            }
+            __syncwarp();
+        };
+
+        #pragma unroll 1
+        for(int first = 0; first < N; first += TIE_LANES) {
+            const int b = first + sub;
+            bool candidate = false;
+            if(live && b < N) {
+                const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
+                const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
                 double p = table[m & 15u];
                 #pragma unroll
                 for(int g = 1; g < G; ++g) { p *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
-                candidate = p * prior >= threshold;
+                candidate = p * __hiloint2double(raw.w, raw.z) >= threshold;
             }
-            if(__any_sync(FULL_MASK, candidate)) {
-                if(candidate) {
-                    /* Barcode::compensated_decoding_probability's accumulation, bit for bit (barcode.h:147-162) */
-                    double sigma = 0.0, compensation = 0.0;
-                    #pragma unroll 4
-                    for(int j = 0; j < L; ++j) {
-                        const double value = ((m >> j) & 1u) ? mismatch_value[j] : match_value[j];
-                        const double y = __dsub_rn(value, compensation);
-                        const double t = __dadd_rn(sigma, y);
-                        compensation = __dsub_rn(__dsub_rn(t, sigma), y);
-                        sigma = t;
-                    }
-                    Candidate c;
-                    c.prior = prior; c.sigma = sigma; c.index = b;
-                    if(beats(c, best, base)) { best = c; }
+            const unsigned found = __ballot_sync(FULL_MASK, candidate);
+            if(found) {
+                const int fresh = __popc(found);
+                if(count + fresh > WARP_SIZE) {
+                    evaluate(count);
+                    count = 0;
                 }
+                if(candidate) { W.list[count + __popc(found & ((1u << lane) - 1u))] = (static_cast< uint32_t >(slot) << 28) | static_cast< uint32_t >(b); }
+                count += fresh;
                 __syncwarp();
             }
         }
-        #pragma unroll 1
-        for(int offset = 16; offset > 0; offset >>= 1) {
-            Candidate other;
-            other.prior = __shfl_xor_sync(FULL_MASK, best.prior, offset);
-            other.sigma = __shfl_xor_sync(FULL_MASK, best.sigma, offset);
-            other.index = __shfl_xor_sync(FULL_MASK, best.index, offset);
-            if(beats(other, best, base)) { best = other; }
-        }
+        if(count) { evaluate(count); }
 
-        if(lane == 0) {
+        if(sub == 0 && live) {
+            const long long r = record.read;
             const int winner = best.index >= 0 ? best.index : 0;
             const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + winner);
             const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
@@ -1147,7 +1189,7 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
     if(status != cudaSuccess) { return status; }
     /* the queue length is only known on the device: a fixed grid strides over it */
     const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
-    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, TIE_WARPS * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     return cudaGetLastError();
 }
 
@@ -1177,7 +1219,7 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
     const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
-    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, TIE_WARPS * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,9 @@ struct __align__(16) TieRecord {
     double base_probability;    /* P0 */
     uint32_t high_quality_mask;
     uint32_t uniform;
+    uint32_t o_lo, o_hi, nmask; /* the observation */
+    uint32_t read;              /* read index within the launch */
+    uint32_t quality[8];
 };
 
 struct DecoderParams {
@@ -76,9 +79,8 @@ struct DecoderParams {
     int32_t grid_b;
     int32_t grid_entries;
     int32_t grid_split;                         /* nucleotides of the first segment */
-    int* tie_list;                              /* [n_reads] reads whose winner needs the exact tie path (PAMLD) */
-    TieRecord* tie_record;                      /* [n_reads] parallel to tie_list */
-    unsigned* tie_count;                        /* length of tie_list, reset before every scan */
+    TieRecord* tie_record;                      /* [reads of the launch] queue of reads whose winner needs the exact tie path (PAMLD) */
+    unsigned* tie_count;                        /* queue length, reset before every scan */
 };
 
 struct TileArguments {
@@ -99,6 +101,8 @@ struct LaunchGeometry {
 /* each returns the CUDA error of the launch; all are asynchronous on `stream`.
    launch_pamld launches two kernels (scan, then the tie pass over the reads the scan queued). */
 enum { PAMLD_KERNEL_LAUNCHES = 2, MDD_KERNEL_LAUNCHES = 1, COUNT_KERNEL_LAUNCHES = 1 };
+/* PAMLD launches cover at most this many reads, so the tie queue (80 bytes per read, worst case every read) stays bounded */
+constexpr long long PAMLD_LAUNCH_READS = 1ll << 24;
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 /* naive / passthrough bookkeeping: count and pf_count of the undetermined row (and the chain totals) */
