@@ -254,6 +254,7 @@ def main():
         stop.record(stream)
         barrier()
         torch.cuda.nvtx.range_pop()
+        launches = chain.statistics()["kernel_launches"] - launches_before
         # keep the GPU under the same load a little longer when the timed region was too short to sample
         extra = 0
         while len(clocks.samples) < 3 and extra < 200:
@@ -264,7 +265,6 @@ def main():
         torch.cuda.synchronize(device)
         clocks.end()
     elapsed_ms = start.elapsed_time(stop)
-    launches = chain.statistics()["kernel_launches"] - launches_before
     # the dominant kernel alone, timed live with CUDA events on the launching stream (phq_last_kernel_milliseconds)
     for _ in range(min(args.steps, 5)):
         flags.zero_()
@@ -305,8 +305,15 @@ def main():
                        "l2": "inputs (%d MB per GPU) exceed L2; no flush needed" % (bytes_per_read * n >> 20), "parallelism": "reads sharded x%d, accumulators all-reduced" % world},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clock_summary}
 
-    # ---------------------------------------------------------------- end to end through the host-buffer C-ABI call
+    # ---------------------------------------------------------------- end to end through the host-buffer C-ABI calls
+    # Pinned host tiles in, per-read results out, every copy inside the timed region. Two forms of the same call:
+    #   e2e       phq_decode_batch_compact with the smallest quality form that fits the batch (here 2-bit codebook
+    #             indices: the synthetic reads, like current Illumina output, have 4 distinct qualities) and the 8-byte
+    #             records that carry what the reference's output carries (index, distance, qcfail, float(1 - confidence));
+    #             used when every topic has one decoder, where those records are lossless w.r.t. the reference's output
+    #   e2e_full  phq_decode_batch with Phred bytes in and 16-byte {index, distance, f64 confidence} + qcfail byte out
     if not args.no_e2e:
+        from pheniqs_b200 import COMPACT_DTYPE, RESULT_DTYPE
         m = args.e2e_reads or min(n, 1 << 26)
         host_tiles = chain.allocate_tiles(m, pinned=True)
         for k, t in enumerate(tiles):
@@ -315,36 +322,62 @@ def main():
             host_tiles[k].bases[:] = t[0][:, :m].cpu().numpy().view(np.uint32)
             host_tiles[k].nmask[:] = t[1][:, :m].cpu().numpy().view(np.uint16)
             host_tiles[k].quality[:] = t[2][:, :m].cpu().numpy().view(np.uint32)
-        from pheniqs_b200 import RESULT_DTYPE
-        host_results = []
+        e2e_steps = max(3, min(args.steps, 5))
+
+        def time_host(call):
+            for _ in range(2):
+                call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                call()
+            torch.cuda.synchronize(device)
+            seconds = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([seconds], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                seconds = float(t.item())
+            return m * world * e2e_steps / seconds
+
         keep = []
+        full_results = []
         for info in chain.info:
             if info.has_tile:
                 buffer = torch.zeros((m, 2), dtype=torch.float64).pin_memory()
                 keep.append(buffer)
-                host_results.append(buffer.numpy().view(RESULT_DTYPE).reshape(-1))
+                full_results.append(buffer.numpy().view(RESULT_DTYPE).reshape(-1))
             else:
-                host_results.append(None)
+                full_results.append(None)
         qc_buffer = torch.zeros(m, dtype=torch.uint8).pin_memory()
         qc_out = qc_buffer.numpy()
-        h2d = sum((info.word_cardinality * 6 + info.quality_word_cardinality * 4) * m for info in chain.info if info.has_tile)
-        d2h = sum(16 * m for info in chain.info if info.has_tile) + m
-        e2e_steps = max(3, min(args.steps, 5))
-        for _ in range(2):
-            chain.decode(host_tiles, m, None, results=host_results, qcfail_out=qc_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            chain.decode(host_tiles, m, None, results=host_results, qcfail_out=qc_out)
-        torch.cuda.synchronize(device)
-        seconds = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([seconds], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            seconds = float(t.item())
-        line["e2e"] = {"value": m * world * e2e_steps / seconds, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "reads_per_gpu_per_step": m, "steps": e2e_steps, "call": "phq_decode_batch (pinned host tiles in; results + qcfail out)"}
-        del host_tiles, host_results, keep
+        h2d_full = sum(t.bytes_per_read() * m for t in host_tiles if t is not None)
+        d2h_full = sum(16 * m for info in chain.info if info.has_tile) + m
+        full_value = time_host(lambda: chain.decode(host_tiles, m, None, results=full_results, qcfail_out=qc_out))
+        e2e_full = {"value": full_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_full), "d2h_bytes_per_step": int(d2h_full),
+                    "reads_per_gpu_per_step": m, "steps": e2e_steps, "call": "phq_decode_batch (Phred byte tiles in; 16-byte results + qcfail byte out)"}
+
+        topics = [info.topic for info in chain.info if info.has_tile]
+        lossless = len(topics) == len(set(topics))
+        if lossless:
+            forms = [t.compress_quality() for t in host_tiles if t is not None]
+            compact_results = []
+            for info in chain.info:
+                if info.has_tile:
+                    buffer = torch.zeros(m, dtype=torch.float64).pin_memory()
+                    keep.append(buffer)
+                    compact_results.append(buffer.numpy().view(COMPACT_DTYPE).reshape(-1))
+                else:
+                    compact_results.append(None)
+            h2d = sum(t.bytes_per_read() * m for t in host_tiles if t is not None)
+            d2h = sum(8 * m for info in chain.info if info.has_tile)
+            value = time_host(lambda: chain.decode_compact(host_tiles, m, None, results=compact_results))
+            line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                           "reads_per_gpu_per_step": m, "steps": e2e_steps, "quality_bits": forms,
+                           "call": "phq_decode_batch_compact (2-bit + mask + codebook-index tiles in; 8-byte records out: index, distance, qcfail, float(1 - confidence))"}
+            line["e2e_full"] = e2e_full
+        else:
+            line["e2e"] = e2e_full
+        del host_tiles, full_results, keep
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         baseline, _, _ = time_cpu(compiled, spec)

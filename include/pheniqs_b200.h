@@ -78,12 +78,21 @@ typedef struct {
       quality[w * pitch + r]  byte k      = Phred value (offset removed) of base 4w + k;
                               PHQ_ABSENT_QUALITY marks a base a short read does not have (MDD)
 
+    Binned qualities (current Illumina instruments emit 4 distinct values) can travel as indices
+    into a per-tile codebook: with quality_bits = 4 or 2, position j occupies quality_bits bits at
+    bit (j * quality_bits) % 32 of word (j * quality_bits) / 32 of the quality plane and
+    quality_codebook[index] is its Phred value. quality_bits = 0 or 8 means plain bytes. This only
+    changes how the bytes travel to the device (a 16-base observation shrinks from 22 to 10 bytes
+    with 2-bit indices); the kernels see the same Phred values.
+
     Replaces the byte-per-base Segment / Observation containers of sequence.h:264-300. */
 typedef struct {
     const uint32_t* bases;
     const uint16_t* nmask;
     const uint32_t* quality;
     int64_t pitch;                      /* elements between consecutive words of a plane (>= n_reads) */
+    int32_t quality_bits;               /* 0 or 8: Phred bytes; 4 or 2: indices into quality_codebook */
+    uint8_t quality_codebook[16];
 } phq_tile;
 
 /*  What one decoder decides for one read: decoded->index (0 = undetermined), edit_distance and
@@ -93,6 +102,19 @@ typedef struct {
     int32_t distance;
     double confidence;
 } phq_result;
+
+/*  The same decision in the 8 bytes the reference's OUTPUT carries for one decoder: the channel /
+    read group index, the distance, the running qcfail flag and the error probability exactly as
+    Read::flush forms it, float(1.0 - confidence) (read.h:187-199, the XB / XC / XM tags). Lossless
+    with respect to the reference's output when a topic has one decoder; with several decoders of one
+    topic the reference multiplies the f64 confidences first (read.h:279-285), which needs phq_result. */
+typedef struct {
+    uint32_t packed;                    /* bits 0-23 index, 24-29 distance, 30 qcfail after this decoder */
+    float error_probability;            /* float(1.0 - confidence); 1 for an undetermined read */
+} phq_compact_result;
+#define PHQ_COMPACT_INDEX(p) ((p) & 0xffffffu)
+#define PHQ_COMPACT_DISTANCE(p) (((p) >> 24) & 0x3fu)
+#define PHQ_COMPACT_QCFAIL(p) (((p) >> 30) & 1u)
 
 /* ------------------------------------------------------------------ configuration */
 
@@ -132,10 +154,14 @@ int phq_decoder_describe(const phq_handle* handle, int decoder, phq_decoder_info
     Short tokens: PAMLD tiles reproduce what a single reference thread sees (terminator, then
     the bytes left in its Observation by earlier reads, barcode.h:150 / sequence.h:296-300);
     MDD tiles mark missing positions PHQ_ABSENT_QUALITY (sequence.h:90-98 iterate the observed
-    length). The handle carries the Observation scratch from call to call. */
+    length). The handle carries the Observation scratch from call to call.
+    tiles[k].quality_bits selects how qualities are written: 0 / 8 = Phred bytes, 4 / 2 = codebook
+    indices (PHQ_CONFIGURATION_ERROR if the batch has more distinct values than fit), -1 = the
+    smallest that fits; on return quality_bits and quality_codebook describe what was written. The
+    quality plane must be allocated for the byte form (quality_word_cardinality words). */
 int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
              const uint8_t* const* code, const uint8_t* const* quality, const int64_t* const* offset,
-             const phq_tile* tiles);
+             phq_tile* tiles);
 
 /* ------------------------------------------------------------------ classification */
 
@@ -150,10 +176,18 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
 int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
                      const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out);
 
+/*  Same, returning phq_compact_result records (8 bytes per read and decoder instead of 16 + the
+    qcfail byte). compact_results[k] may be NULL. */
+int phq_decode_batch_compact(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
+                             const uint8_t* qcfail_in, phq_compact_result* const* compact_results);
+
 /*  Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t, NULL = default
     stream): `qcfail` is read and updated in place. Nothing is copied; the caller synchronises. */
 int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
                             uint8_t* device_qcfail, phq_result* const* device_results, void* stream);
+
+int phq_decode_batch_device_compact(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
+                                    uint8_t* device_qcfail, phq_compact_result* const* device_compact_results, void* stream);
 
 int phq_host_alloc(void** pointer, size_t bytes);       /* pinned host memory */
 void phq_host_free(void* pointer);

@@ -19,6 +19,7 @@
 
 #include "pheniqs_b200.h"
 
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -62,7 +63,7 @@ inline std::string compile_job(const std::string& job_json) {
 /* host planes of one decoder for a batch, owned by the caller (pinned when `pinned`) */
 class TileBuffer {
     public:
-        TileBuffer() : n_reads_(0), pinned_(false) { tile_.bases = NULL; tile_.nmask = NULL; tile_.quality = NULL; tile_.pitch = 0; }
+        TileBuffer() : n_reads_(0), pinned_(false) { memset(&tile_, 0, sizeof(tile_)); }
         TileBuffer(const TileBuffer&) = delete;
         void operator=(const TileBuffer&) = delete;
         ~TileBuffer() { release(); }
@@ -113,10 +114,16 @@ class BatchDecoder {
         size_t decoder_cardinality() const { return info_.size(); }
         const phq_decoder_info& info(size_t k) const { return info_[k]; }
 
-        /* Rule::apply + packing (transform.h:142-169) for reads held one code byte and one Phred byte per base */
+        /* Rule::apply + packing (transform.h:142-169) for reads held one code byte and one Phred byte per base;
+           tiles[k].quality_bits chooses the quality form on the way in and reports it on the way out */
         void pack(int64_t n_reads, int32_t n_input_segments, const uint8_t* const* code, const uint8_t* const* quality,
-                  const int64_t* const* offset, const std::vector< phq_tile >& tiles) {
+                  const int64_t* const* offset, std::vector< phq_tile >& tiles) {
             check(phq_pack(handle_, n_reads, n_input_segments, code, quality, offset, tiles.data()));
+        }
+        /* the 8-byte records of the reference's output (index, distance, qcfail, float error probability) */
+        void classify_compact(int64_t n_reads, const std::vector< phq_tile >& tiles, const uint8_t* qcfail_in,
+                              const std::vector< phq_compact_result* >& results) {
+            check(phq_decode_batch_compact(handle_, n_reads, tiles.data(), qcfail_in, results.data()));
         }
         /* TranscodingDecoder::classify (transcode.h:51-65) for a batch; host buffers */
         void classify(int64_t n_reads, const std::vector< phq_tile >& tiles, const uint8_t* qcfail_in,

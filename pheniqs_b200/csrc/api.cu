@@ -295,7 +295,8 @@ void destroy(phq_handle* h) {
 }
 
 /* launch the chain on device-resident planes (TranscodingDecoder::classify order, transcode.h:51-60) */
-void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t* qcfail, phq_result* const* results, DeviceBuffer< unsigned char >& tie_list, cudaStream_t stream) {
+void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t* qcfail, phq_result* const* results, phq_compact_result* const* compact,
+                  DeviceBuffer< unsigned char >& tie_list, cudaStream_t stream) {
     const size_t n_decoders(h->chain.size());
     bool needs_queue(false);
     for(const auto& d : h->chain) { needs_queue = needs_queue || d.algorithm == PHQ_PAMLD; }
@@ -314,6 +315,9 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
         a.n_reads = n_reads;
         a.qcfail = qcfail;
         a.results = results != NULL ? results[k] : NULL;
+        a.compact = compact != NULL ? compact[k] : NULL;
+        a.quality_bits = 8;
+        a.nucleotides = h->chain[k].nucleotide_cardinality;
         cudaError_t status(cudaSuccess);
         if(h->chain[k].tiled()) {
             if(tiles == NULL || tiles[k].bases == NULL || tiles[k].nmask == NULL || tiles[k].quality == NULL) {
@@ -324,6 +328,9 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
             a.nmask = tiles[k].nmask;
             a.quality = tiles[k].quality;
             a.pitch = tiles[k].pitch;
+            a.quality_bits = tiles[k].quality_bits == 0 ? 8 : tiles[k].quality_bits;
+            if(a.quality_bits != 8 && a.quality_bits != 4 && a.quality_bits != 2) { throw InternalError("quality_bits must be 8, 4 or 2"); }
+            memcpy(a.codebook, tiles[k].quality_codebook, 16);
             if(h->chain[k].algorithm == PHQ_PAMLD) {
                 /* sub-launches over read ranges keep the tie queue bounded; planes are [word][read], so a range is a pointer offset */
                 for(long long begin(0); begin < n_reads && status == cudaSuccess; begin += PAMLD_LAUNCH_READS) {
@@ -334,6 +341,7 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
                     part.quality = a.quality + begin;
                     part.qcfail = a.qcfail + begin;
                     part.results = a.results != NULL ? a.results + begin : NULL;
+                    part.compact = a.compact != NULL ? a.compact + begin : NULL;
                     status = launch_pamld(p, part, h->geometry, stream);
                     h->kernel_launches += PAMLD_KERNEL_LAUNCHES;
                 }
@@ -512,7 +520,7 @@ int phq_decoder_describe(const phq_handle* handle, int decoder, phq_decoder_info
 
 int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
              const uint8_t* const* code, const uint8_t* const* quality, const int64_t* const* offset,
-             const phq_tile* tiles) {
+             phq_tile* tiles) {
     phq_handle* h(handle);
     try {
         if(h == NULL) { throw InternalError("null handle"); }
@@ -520,7 +528,7 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
         for(size_t k(0); k < h->chain.size(); ++k) {
             const DecoderSpec& d(h->chain[k]);
             if(!d.tiled()) { continue; }
-            const phq_tile& tile(tiles[k]);
+            phq_tile& tile(tiles[k]);
             if(tile.bases == NULL || tile.nmask == NULL || tile.quality == NULL || tile.pitch < n_reads) { throw InternalError("decoder " + std::to_string(k) + " has no host tile to pack into"); }
             for(const auto& t : d.transform) {
                 if(t.input_segment_index >= n_input_segments) {
@@ -534,6 +542,8 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
             const int32_t words(d.word_cardinality());
             const int32_t quality_words(d.quality_word_cardinality());
             const bool stale_semantics(d.algorithm == PHQ_PAMLD);
+            bool seen[256];
+            memset(seen, 0, sizeof(seen));
 
             for(int64_t r(0); r < n_reads; ++r) {
                 /* Observation::clear + Rule::apply (sequence.h:296-300, transform.h:142-169) */
@@ -595,29 +605,67 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
                     out_quality[w * tile.pitch + r] = static_cast< uint32_t >(phred[4 * w]) | (static_cast< uint32_t >(phred[4 * w + 1]) << 8)
                         | (static_cast< uint32_t >(phred[4 * w + 2]) << 16) | (static_cast< uint32_t >(phred[4 * w + 3]) << 24);
                 }
+                for(int32_t j(0); j < d.nucleotide_cardinality; ++j) { seen[phred[j]] = true; }
             }
+            /* quality form: Phred bytes as written above, or indices into a codebook of the distinct values */
+            int32_t wanted(tile.quality_bits);
+            int32_t distinct(0);
+            uint8_t codebook[256];
+            uint8_t index_of[256];
+            memset(index_of, 0, sizeof(index_of));
+            for(int v(0); v < 256; ++v) { if(seen[v]) { index_of[v] = static_cast< uint8_t >(distinct); codebook[distinct++] = static_cast< uint8_t >(v); } }
+            if(wanted == -1) { wanted = distinct <= 4 ? 2 : (distinct <= 16 ? 4 : 8); }
+            if(wanted == 0) { wanted = 8; }
+            if(wanted != 8 && wanted != 4 && wanted != 2) { throw ConfigurationError("quality_bits must be -1, 0, 2, 4 or 8"); }
+            if(wanted != 8 && distinct > (1 << wanted)) {
+                throw ConfigurationError(std::to_string(distinct) + " distinct quality values do not fit " + std::to_string(wanted) + " bit indices");
+            }
+            memset(tile.quality_codebook, 0, sizeof(tile.quality_codebook));
+            if(wanted != 8) {
+                memcpy(tile.quality_codebook, codebook, static_cast< size_t >(distinct));
+                const int32_t per_word(32 / wanted);
+                const int32_t packed_words((d.nucleotide_cardinality * wanted + 31) / 32);
+                for(int64_t r(0); r < n_reads; ++r) {
+                    uint32_t packed[PHQ_MAX_NUCLEOTIDES / 4];
+                    memset(packed, 0, sizeof(packed));
+                    for(int32_t j(0); j < d.nucleotide_cardinality; ++j) {
+                        const uint8_t q(static_cast< uint8_t >((out_quality[(j >> 2) * tile.pitch + r] >> (8 * (j & 3))) & 0xffu));
+                        packed[j / per_word] |= static_cast< uint32_t >(index_of[q]) << (wanted * (j % per_word));
+                    }
+                    for(int32_t w(0); w < packed_words; ++w) { out_quality[w * tile.pitch + r] = packed[w]; }
+                }
+            }
+            tile.quality_bits = wanted;
         }
         return PHQ_OK;
     } catch(const phq::Error& e) { if(h != NULL) { h->error = e.what(); } else { global_error = e.what(); } return e.code; }
     catch(const std::exception& e) { if(h != NULL) { h->error = e.what(); } else { global_error = e.what(); } return PHQ_UNKNOWN_ERROR; }
 }
 
-int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
-                            uint8_t* device_qcfail, phq_result* const* device_results, void* stream) {
+static int decode_device(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles, uint8_t* device_qcfail,
+                         phq_result* const* device_results, phq_compact_result* const* device_compact, void* stream) {
     return guarded(handle, [&]() {
         if(n_reads < 0 || n_reads > 0x7fffffffll) { throw OverflowError("a batch holds at most 2^31 - 1 reads"); }
         if(device_qcfail == NULL) { throw InternalError("device_qcfail is required"); }
         cudaStream_t s(static_cast< cudaStream_t >(stream));
         PHQ_CUDA(cudaEventRecord(handle->timing_start, s));
-        launch_chain(handle, n_reads, device_tiles, device_qcfail, device_results, handle->tie_list, s);
+        launch_chain(handle, n_reads, device_tiles, device_qcfail, device_results, device_compact, handle->tie_list, s);
         PHQ_CUDA(cudaEventRecord(handle->timing_stop, s));
         handle->timing_stream = s;
         handle->timing_valid = true;
     });
 }
+int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
+                            uint8_t* device_qcfail, phq_result* const* device_results, void* stream) {
+    return decode_device(handle, n_reads, device_tiles, device_qcfail, device_results, NULL, stream);
+}
+int phq_decode_batch_device_compact(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
+                                    uint8_t* device_qcfail, phq_compact_result* const* device_compact, void* stream) {
+    return decode_device(handle, n_reads, device_tiles, device_qcfail, NULL, device_compact, stream);
+}
 
-int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
-                     const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out) {
+static int decode_host(phq_handle* handle, int64_t n_reads, const phq_tile* tiles, const uint8_t* qcfail_in,
+                       phq_result* const* results, phq_compact_result* const* compact, uint8_t* qcfail_out) {
     return guarded(handle, [&]() {
         phq_handle* h(handle);
         if(n_reads < 0) { throw InternalError("illegal read count"); }
@@ -631,6 +679,7 @@ int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
             if(turn >= STAGING_SLOTS) { PHQ_CUDA(cudaEventSynchronize(s.done)); }
             std::vector< phq_tile > device_tiles(n_decoders);
             std::vector< phq_result* > device_results(n_decoders, static_cast< phq_result* >(NULL));
+            std::vector< phq_compact_result* > device_compact(n_decoders, static_cast< phq_compact_result* >(NULL));
             s.qcfail.reserve(static_cast< size_t >(sub));
             if(qcfail_in != NULL) { PHQ_CUDA(cudaMemcpyAsync(s.qcfail.pointer, qcfail_in + begin, static_cast< size_t >(count), cudaMemcpyHostToDevice, s.stream)); }
             else { PHQ_CUDA(cudaMemsetAsync(s.qcfail.pointer, 0, static_cast< size_t >(count), s.stream)); }
@@ -640,30 +689,39 @@ int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
                 if(d.tiled()) {
                     if(tiles == NULL || tiles[k].bases == NULL) { throw InternalError("decoder " + std::to_string(k) + " needs a tile"); }
                     const int32_t words(d.word_cardinality());
-                    const int32_t quality_words(d.quality_word_cardinality());
+                    const int32_t bits(tiles[k].quality_bits == 0 ? 8 : tiles[k].quality_bits);
+                    /* only the rows the chosen quality form occupies travel */
+                    const int32_t quality_words((d.nucleotide_cardinality * bits + 31) / 32);
                     s.bases[k].reserve(static_cast< size_t >(sub) * words);
                     s.nmask[k].reserve(static_cast< size_t >(sub) * words);
-                    s.quality[k].reserve(static_cast< size_t >(sub) * quality_words);
+                    s.quality[k].reserve(static_cast< size_t >(sub) * d.quality_word_cardinality());
                     PHQ_CUDA(cudaMemcpy2DAsync(s.bases[k].pointer, static_cast< size_t >(sub) * 4, tiles[k].bases + begin, static_cast< size_t >(tiles[k].pitch) * 4,
                                                static_cast< size_t >(count) * 4, words, cudaMemcpyHostToDevice, s.stream));
                     PHQ_CUDA(cudaMemcpy2DAsync(s.nmask[k].pointer, static_cast< size_t >(sub) * 2, tiles[k].nmask + begin, static_cast< size_t >(tiles[k].pitch) * 2,
                                                static_cast< size_t >(count) * 2, words, cudaMemcpyHostToDevice, s.stream));
                     PHQ_CUDA(cudaMemcpy2DAsync(s.quality[k].pointer, static_cast< size_t >(sub) * 4, tiles[k].quality + begin, static_cast< size_t >(tiles[k].pitch) * 4,
                                                static_cast< size_t >(count) * 4, quality_words, cudaMemcpyHostToDevice, s.stream));
+                    device_tiles[k] = tiles[k];
                     device_tiles[k].bases = s.bases[k].pointer;
                     device_tiles[k].nmask = s.nmask[k].pointer;
                     device_tiles[k].quality = s.quality[k].pointer;
                     device_tiles[k].pitch = sub;
                 }
-                if(results != NULL && results[k] != NULL) {
+                const bool wanted((results != NULL && results[k] != NULL) || (compact != NULL && compact[k] != NULL));
+                if(wanted) {
+                    /* the staging buffer is sized for the 16-byte form and reused for the 8-byte one */
                     s.results[k].reserve(static_cast< size_t >(sub));
-                    device_results[k] = s.results[k].pointer;
+                    if(compact != NULL) { device_compact[k] = reinterpret_cast< phq_compact_result* >(s.results[k].pointer); }
+                    else { device_results[k] = s.results[k].pointer; }
                 }
             }
-            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, device_results.data(), s.tie_list, s.stream);
+            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, compact != NULL ? NULL : device_results.data(), compact != NULL ? device_compact.data() : NULL, s.tie_list, s.stream);
             for(size_t k(0); k < n_decoders; ++k) {
                 if(device_results[k] != NULL) {
                     PHQ_CUDA(cudaMemcpyAsync(results[k] + begin, device_results[k], static_cast< size_t >(count) * sizeof(phq_result), cudaMemcpyDeviceToHost, s.stream));
+                }
+                if(device_compact[k] != NULL) {
+                    PHQ_CUDA(cudaMemcpyAsync(compact[k] + begin, device_compact[k], static_cast< size_t >(count) * sizeof(phq_compact_result), cudaMemcpyDeviceToHost, s.stream));
                 }
             }
             if(qcfail_out != NULL) { PHQ_CUDA(cudaMemcpyAsync(qcfail_out + begin, s.qcfail.pointer, static_cast< size_t >(count), cudaMemcpyDeviceToHost, s.stream)); }
@@ -671,6 +729,14 @@ int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
         }
         for(int i(0); i < STAGING_SLOTS && i < turn; ++i) { PHQ_CUDA(cudaStreamSynchronize(h->slot[i].stream)); }
     });
+}
+int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
+                     const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out) {
+    return decode_host(handle, n_reads, tiles, qcfail_in, results, NULL, qcfail_out);
+}
+int phq_decode_batch_compact(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
+                             const uint8_t* qcfail_in, phq_compact_result* const* compact_results) {
+    return decode_host(handle, n_reads, tiles, qcfail_in, NULL, compact_results, NULL);
 }
 
 int phq_host_alloc(void** pointer, size_t bytes) {

@@ -106,13 +106,48 @@ __device__ __forceinline__ void tma_bulk_load(void* destination, const void* sou
 /* streaming loads / stores: tiles and results are touched once */
 __device__ __forceinline__ uint32_t load_stream(const uint32_t* p) { return __ldcs(p); }
 __device__ __forceinline__ uint32_t load_stream(const uint16_t* p) { return static_cast< uint32_t >(__ldcs(reinterpret_cast< const unsigned short* >(p))); }
-__device__ __forceinline__ void store_result(phq_result* results, long long r, int32_t index, int32_t distance, double confidence) {
-    int4 v;
-    v.x = index;
-    v.y = distance;
-    v.z = __double2loint(confidence);
-    v.w = __double2hiint(confidence);
-    __stcs(reinterpret_cast< int4* >(results) + r, v);
+__device__ __forceinline__ void store_result(const TileArguments& A, long long r, int32_t index, int32_t distance, double confidence, uint32_t qcfail) {
+    if(A.compact != nullptr) {
+        /* Read::flush: float(1.0 - confidence) (read.h:189) */
+        int2 v;
+        v.x = static_cast< int >(static_cast< uint32_t >(index) | (static_cast< uint32_t >(distance) << 24) | (qcfail << 30));
+        v.y = __float_as_int(static_cast< float >(1.0 - confidence));
+        __stcs(reinterpret_cast< int2* >(A.compact) + r, v);
+    } else if(A.results != nullptr) {
+        int4 v;
+        v.x = index;
+        v.y = distance;
+        v.z = __double2loint(confidence);
+        v.w = __double2hiint(confidence);
+        __stcs(reinterpret_cast< int4* >(A.results) + r, v);
+    }
+}
+
+/*  The four Phred bytes of quality word g (positions 4g .. 4g+3) of read r, whatever form they travelled
+    in. Codebook forms are decoded with byte permutes: a 2-bit index word selects among the 4 bytes of one
+    codebook register with a single PRMT, a 4-bit index word among 16 bytes with two and a byte-wise blend. */
+__device__ __forceinline__ uint32_t quality_word(const TileArguments& A, long long r, int g) {
+    if(A.quality_bits == 8) { return load_stream(A.quality + g * A.pitch + r); }
+    /* index 0 is a real quality in a codebook: positions past the observation must still read as Phred 0 */
+    const int valid = A.nucleotides - 4 * g;
+    const uint32_t keep = valid >= 4 ? 0xffffffffu : (valid <= 0 ? 0u : ((1u << (8 * valid)) - 1u));
+    if(A.quality_bits == 2) {
+        const uint32_t packed = load_stream(A.quality + (g >> 2) * A.pitch + r);
+        const uint32_t c = (packed >> (8 * (g & 3))) & 0xffu;
+        const uint32_t selector = (c & 0x3u) | ((c & 0xcu) << 2) | ((c & 0x30u) << 4) | ((c & 0xc0u) << 6);
+        return __byte_perm(A.codebook[0], 0u, selector) & keep;
+    }
+    if(A.quality_bits == 4) {
+        const uint32_t packed = load_stream(A.quality + (g >> 1) * A.pitch + r);
+        const uint32_t c = (packed >> (16 * (g & 1))) & 0xffffu;
+        const uint32_t low = __byte_perm(A.codebook[0], A.codebook[1], c & 0x7777u);
+        const uint32_t high = __byte_perm(A.codebook[2], A.codebook[3], c & 0x7777u);
+        /* bit 3 of every index chooses the upper half of the codebook: one flag bit per byte, widened to a byte mask */
+        const uint32_t flag = ((c & 0x8u) >> 3) | ((c & 0x80u) << 1) | ((c & 0x800u) << 5) | ((c & 0x8000u) << 9);
+        const uint32_t mask = flag * 0xffu;
+        return (low ^ ((low ^ high) & mask)) & keep;
+    }
+    return 0u;
 }
 
 /* ------------------------------------------------------------------ per-CTA accumulators
@@ -411,7 +446,7 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
                 nmask |= load_stream(A.nmask + A.pitch + r) << 16;
             }
             #pragma unroll
-            for(int g = 0; g < G; ++g) { quality[g] = load_stream(A.quality + g * A.pitch + r); }
+            for(int g = 0; g < G; ++g) { quality[g] = quality_word(A, r, g); }
             qcfail = A.qcfail[r];
         }
 
@@ -532,7 +567,7 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
                                            uniform_positions == L, high_quality_mask, qcfail);
             qcfail = v.qcfail;
             A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
-            if(A.results != nullptr) { store_result(A.results, r, v.decoded, v.distance, v.confidence); }
+            store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
         }
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, decided);
@@ -661,7 +696,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                 nmask |= load_stream(A.nmask + A.pitch + r) << 16;
             }
             #pragma unroll
-            for(int g = 0; g < G; ++g) { quality[g] = load_stream(A.quality + g * A.pitch + r); }
+            for(int g = 0; g < G; ++g) { quality[g] = quality_word(A, r, g); }
             qcfail = A.qcfail[r];
         }
 
@@ -781,7 +816,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                                            uniform_positions == L, high_quality_mask, qcfail);
             qcfail = v.qcfail;
             A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
-            if(A.results != nullptr) { store_result(A.results, r, v.decoded, v.distance, v.confidence); }
+            store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
         }
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, decided);
@@ -1010,7 +1045,7 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
             const Verdict v = pamld_decide(P, accumulator, &block_counter[3], winner, m, t, prior, others, record.base_probability,
                                            record.uniform != 0u, record.high_quality_mask, qcfail);
             A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
-            if(A.results != nullptr) { store_result(A.results, r, v.decoded, v.distance, v.confidence); }
+            store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
             atomicAdd(&block_counter[0], 1u);
             if(!v.qcfail) { atomicAdd(&block_counter[1], 1u); }
         }
@@ -1060,7 +1095,7 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
                 nmask |= load_stream(A.nmask + A.pitch + r) << 16;
             }
             for(int g = 0; g < P.quality_word_cardinality; ++g) {
-                const uint32_t qw = load_stream(A.quality + g * A.pitch + r);
+                const uint32_t qw = quality_word(A, r, g);
                 #pragma unroll
                 for(int k = 0; k < 4; ++k) {
                     const uint32_t q = (qw >> (8 * k)) & 0xffu;
@@ -1121,7 +1156,7 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
             S.accumulator.add(decoded, ACC_COUNT, 1u);
             if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
             A.qcfail[r] = static_cast< uint8_t >(qcfail);
-            if(A.results != nullptr) { store_result(A.results, r, decoded, distance, 0.0); }
+            store_result(A, r, decoded, distance, 0.0, qcfail);
         }
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, valid);
@@ -1145,7 +1180,7 @@ count_kernel(const DecoderParams P, const TileArguments A) {
     for(long long r = static_cast< long long >(blockIdx.x) * blockDim.x + threadIdx.x; r < A.n_reads; r += static_cast< long long >(gridDim.x) * blockDim.x) {
         ++live;
         if(!A.qcfail[r]) { ++pass; }
-        if(A.results != nullptr) { store_result(A.results, r, 0, 0, 0.0); }
+        store_result(A, r, 0, 0, 0.0, A.qcfail[r]);
     }
     #pragma unroll
     for(int offset = 16; offset > 0; offset >>= 1) {

@@ -91,6 +91,10 @@ struct TileArguments {
     long long n_reads;
     uint8_t* qcfail;                            /* in/out running flag, [n_reads] */
     phq_result* results;                        /* may be NULL */
+    phq_compact_result* compact;                /* may be NULL; written instead of `results` when set */
+    int quality_bits;                           /* 8, 4 or 2 (phq_tile) */
+    int nucleotides;                            /* nucleotide cardinality of the decoder */
+    uint32_t codebook[4];                       /* quality_codebook, little endian words */
 };
 
 struct LaunchGeometry {

@@ -20,6 +20,7 @@ from . import binding
 from .binding import DecoderInfo, Tile, check, library
 
 RESULT_DTYPE = np.dtype([("index", np.int32), ("distance", np.int32), ("confidence", np.float64)])
+COMPACT_DTYPE = np.dtype([("packed", np.uint32), ("error_probability", np.float32)])
 ACC_U64_COLUMNS = ("count", "pf count", "accumulated distance", "low conditional confidence count", "low confidence count", "accumulated pf distance")
 ACC_F64_COLUMNS = ("accumulated confidence", "accumulated pf confidence")
 
@@ -52,6 +53,9 @@ class HostTile:
         self.pitch = max(n_reads, 1)
         self.words = info.word_cardinality
         self.quality_words = info.quality_word_cardinality
+        self.nucleotides = info.nucleotide_cardinality
+        self.quality_bits = 8
+        self.quality_codebook = bytes(16)
         self._pinned = []
         self.bases = self._allocate((self.words, self.pitch), np.uint32, pinned)
         self.nmask = self._allocate((self.words, self.pitch), np.uint16, pinned)
@@ -66,7 +70,43 @@ class HostTile:
         return t.numpy().view(dtype)
 
     def as_struct(self) -> Tile:
-        return Tile(self.bases.ctypes.data, self.nmask.ctypes.data, self.quality.ctypes.data, self.pitch)
+        return Tile(self.bases.ctypes.data, self.nmask.ctypes.data, self.quality.ctypes.data, self.pitch,
+                    self.quality_bits, (C.c_uint8 * 16)(*self.quality_codebook))
+
+    @property
+    def packed_quality_words(self) -> int:
+        """rows of the quality plane the chosen form occupies"""
+        return (self.nucleotides * self.quality_bits + 31) // 32
+
+    def bytes_per_read(self) -> int:
+        return self.words * 6 + self.packed_quality_words * 4
+
+    def compress_quality(self) -> int:
+        """Re-encode a byte-form quality plane in place as indices into a codebook of its distinct values
+        (what phq_pack does with quality_bits = -1), when at most 16 distinct values occur. Returns the form."""
+        if self.quality_bits != 8:
+            return self.quality_bits
+        L = self.nucleotides
+        present = np.zeros(256, dtype=bool)
+        for w in range(self.quality_words):
+            for k in range(4):
+                if 4 * w + k < L:
+                    present[np.unique((self.quality[w] >> (8 * k)) & 0xff)] = True
+        values = np.nonzero(present)[0]
+        bits = 2 if values.size <= 4 else (4 if values.size <= 16 else 8)
+        if bits == 8:
+            return 8
+        index_of = np.zeros(256, dtype=np.uint32)
+        index_of[values] = np.arange(values.size, dtype=np.uint32)
+        per_word = 32 // bits
+        packed = np.zeros(((L * bits + 31) // 32, self.pitch), dtype=np.uint32)
+        for j in range(L):
+            q = (self.quality[j // 4] >> (8 * (j % 4))) & 0xff
+            packed[j // per_word] |= index_of[q] << np.uint32(bits * (j % per_word))
+        self.quality[:packed.shape[0]] = packed
+        self.quality_bits = bits
+        self.quality_codebook = bytes(values.astype(np.uint8).tolist() + [0] * (16 - values.size))
+        return bits
 
 
 class DecoderChain:
@@ -111,8 +151,9 @@ class DecoderChain:
                 array[k] = t if isinstance(t, Tile) else t.as_struct()
         return array
 
-    def pack(self, code, quality, offset, tiles=None, pinned: bool = False):
-        """Rule::apply + packing for a batch held as per-segment flat arrays (phq_pack)."""
+    def pack(self, code, quality, offset, tiles=None, pinned: bool = False, quality_bits: int = 8):
+        """Rule::apply + packing for a batch held as per-segment flat arrays (phq_pack).
+        quality_bits: 8 = Phred bytes, 4 / 2 = codebook indices, -1 = the smallest form that fits."""
         n_segments = len(code)
         n_reads = int(offset[0].shape[0] - 1)
         if tiles is None:
@@ -123,7 +164,15 @@ class DecoderChain:
         pc = (C.c_void_p * n_segments)(*[c.ctypes.data for c in code])
         pq = (C.c_void_p * n_segments)(*[q.ctypes.data for q in quality])
         po = (C.c_void_p * n_segments)(*[o.ctypes.data for o in offset])
-        check(self.lib.phq_pack(self.handle, n_reads, n_segments, pc, pq, po, self._tile_array(tiles)), self.handle)
+        for t in tiles:
+            if t is not None:
+                t.quality_bits = quality_bits
+        array = self._tile_array(tiles)
+        check(self.lib.phq_pack(self.handle, n_reads, n_segments, pc, pq, po, array), self.handle)
+        for k, t in enumerate(tiles):
+            if t is not None:
+                t.quality_bits = int(array[k].quality_bits)
+                t.quality_codebook = bytes(array[k].quality_codebook)
         return tiles
 
     # ------------------------------------------------------------------ classification
@@ -139,6 +188,15 @@ class DecoderChain:
                                         pointers, qcfail_out.ctypes.data), self.handle)
         return results, qcfail_out
 
+    def decode_compact(self, tiles, n_reads: int, qcfail_in=None, results=None):
+        """phq_decode_batch_compact: 8-byte records (index | distance | qcfail, float error probability)."""
+        if results is None:
+            results = [np.zeros(n_reads, dtype=COMPACT_DTYPE) if info.has_tile else None for info in self.info]
+        pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
+        qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
+        check(self.lib.phq_decode_batch_compact(self.handle, n_reads, self._tile_array(tiles), None if qin is None else qin.ctypes.data, pointers), self.handle)
+        return results
+
     def decode_device(self, device_tiles, n_reads: int, qcfail, results=None, stream=None):
         """Same over device-resident torch tensors; asynchronous on `stream` (phq_decode_batch_device).
 
@@ -146,8 +204,9 @@ class DecoderChain:
         array = (Tile * self.n_decoders)()
         for k, t in enumerate(device_tiles):
             if t is not None:
-                bases, nmask, quality = t
-                array[k] = Tile(bases.data_ptr(), nmask.data_ptr(), quality.data_ptr(), bases.shape[-1])
+                bases, nmask, quality = t[:3]
+                bits, codebook = (t[3], t[4]) if len(t) > 3 else (8, bytes(16))
+                array[k] = Tile(bases.data_ptr(), nmask.data_ptr(), quality.data_ptr(), bases.shape[-1], bits, (C.c_uint8 * 16)(*codebook))
         pointers = (C.c_void_p * self.n_decoders)(*[None if (results is None or r is None) else r.data_ptr() for r in (results or [None] * self.n_decoders)])
         handle = 0 if stream is None else stream.cuda_stream
         check(self.lib.phq_decode_batch_device(self.handle, n_reads, array, qcfail.data_ptr(), pointers, C.c_void_p(handle)), self.handle)
@@ -162,7 +221,7 @@ class DecoderChain:
                 out.append(None)
                 continue
             out.append((torch.from_numpy(t.bases.view(np.int32)).to(device), torch.from_numpy(t.nmask.view(np.int16)).to(device),
-                        torch.from_numpy(t.quality.view(np.int32)).to(device)))
+                        torch.from_numpy(t.quality.view(np.int32)).to(device), t.quality_bits, t.quality_codebook))
         return out
 
     def last_kernel_milliseconds(self) -> float:

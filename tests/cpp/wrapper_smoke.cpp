@@ -27,7 +27,12 @@ int main() {
         decoder.pack(2, 1, pc, pq, po, tiles);
         /* read 0 = ACGT: lo plane 0b1010 (C, T), hi plane 0b1100 (G, T); read 1 has an N at position 1 */
         if(tiles[0].bases[0] != (0xau | (0xcu << 16)) || tiles[0].nmask[0] != 0 || tiles[0].nmask[1] != 2) { return 3; }
-        if(tiles[0].quality[0] != 0x1e1e1e1eu) { return 4; }
+        if(tiles[0].quality[0] != 0x1e1e1e1eu || tiles[0].quality_bits != 8) { return 4; }
+        /* the same batch with the smallest quality form: three distinct values (30, 10, 2) -> 2-bit indices */
+        tiles[0].quality_bits = -1;
+        decoder.pack(2, 1, pc, pq, po, tiles);
+        if(tiles[0].quality_bits != 2 || tiles[0].quality_codebook[0] != 2 || tiles[0].quality_codebook[1] != 10 || tiles[0].quality_codebook[2] != 30) { return 7; }
+        if(tiles[0].quality[0] != 0xaau || tiles[0].quality[1] != 0x51u) { return 8; }
         bool refused(false);
         try {
             std::vector< phq_result > results(2);

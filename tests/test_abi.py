@@ -152,3 +152,17 @@ def test_pack_reproduces_rule_apply(short):
             assert np.all(got_code[ambiguous] == 15)
         saw_short = saw_short or bool((~present).any())
     assert saw_short == bool(short)
+    # the codebook forms carry the same Phred values in fewer bytes
+    smallest = DecoderChain(compiled, device=-1).pack(code, quality, offset, quality_bits=-1)
+    for k, info in enumerate(chain.info):
+        if not info.has_tile:
+            continue
+        L = info.nucleotide_cardinality
+        a = workload.unpack_tile(tiles[k].bases, tiles[k].nmask, tiles[k].quality, L)
+        b = workload.unpack_tile(smallest[k].bases, smallest[k].nmask, smallest[k].quality, L, smallest[k].quality_bits, smallest[k].quality_codebook)
+        assert smallest[k].quality_bits in (2, 4) and smallest[k].packed_quality_words < tiles[k].packed_quality_words
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        copy = chain.pack(code, quality, offset)[k] if False else None
+    with pytest.raises(ConfigurationError):
+        noisy = [rng.integers(0, 40, size=q.shape).astype(np.uint8) for q in quality]
+        DecoderChain(compiled, device=-1).pack(code, noisy, offset, quality_bits=2)

@@ -154,6 +154,53 @@ def test_combinatorial_codecs(shape):
     check(*run_both(None, code, quality, offset, compiled=compiled))
 
 
+@pytest.mark.parametrize("name", ["c1", "c2", "c4"])
+def test_codebook_qualities_and_compact_results(name):
+    """Qualities travelling as 2-bit codebook indices and results travelling as 8-byte records give exactly
+    what the byte / 16-byte forms give (the compact error probability is float(1 - confidence), read.h:189)."""
+    spec = workload.load(name)
+    compiled = compile_job(spec["job"])
+    n = 50000
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], n, seed=13)
+    chain = DecoderChain(compiled, device=0)
+    plain = chain.pack(code, quality, offset)
+    results, flags = chain.decode(plain, n)
+    u_plain = [chain.accumulators(k) for k in range(chain.n_decoders)]
+    chain.reset()
+    small = DecoderChain(compiled, device=-1).pack(code, quality, offset, quality_bits=-1)
+    assert all(t is None or t.quality_bits == 2 for t in small)
+    again, flags_again = chain.decode(small, n)
+    for k in range(chain.n_decoders):
+        assert np.array_equal(again[k], results[k])
+        u, f = chain.accumulators(k)
+        assert np.array_equal(u, u_plain[k][0])
+    assert np.array_equal(flags, flags_again)
+    chain.reset()
+    compact = chain.decode_compact(small, n)
+    running = np.zeros(n, dtype=np.uint8)
+    for k, info in enumerate(chain.info):
+        if not info.has_tile:
+            continue
+        packed = compact[k]["packed"]
+        assert np.array_equal(packed & 0xffffff, results[k]["index"].astype(np.uint32))
+        assert np.array_equal((packed >> 24) & 0x3f, results[k]["distance"].astype(np.uint32))
+        assert np.array_equal(compact[k]["error_probability"], (1.0 - results[k]["confidence"]).astype(np.float32))
+        last = k
+    assert np.array_equal((compact[last]["packed"] >> 30) & 1, flags.astype(np.uint32))
+    # a 4-bit codebook: more than four distinct qualities
+    rng = np.random.default_rng(2)
+    quality9 = [np.array([2, 7, 11, 14, 22, 25, 30, 33, 37], dtype=np.uint8)[rng.integers(0, 9, size=q.shape)] for q in quality]
+    chain.reset()
+    wide = chain.pack(code, quality9, offset)
+    want, want_flags = chain.decode(wide, n)
+    four = DecoderChain(compiled, device=-1).pack(code, quality9, offset, quality_bits=-1)
+    assert all(t is None or t.quality_bits == 4 for t in four)
+    got, got_flags = chain.decode(four, n)
+    for k in range(chain.n_decoders):
+        assert np.array_equal(got[k], want[k])
+    assert np.array_equal(got_flags, want_flags)
+
+
 def test_structural_ties_take_the_exact_path():
     """Uniform priors + all-N / low quality observations: many exactly tied barcodes; first maximum must match."""
     rng = np.random.default_rng(3)
