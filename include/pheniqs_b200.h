@@ -76,7 +76,8 @@ typedef struct {
                               (A=0, C=1, G=2, T=3) of the 16 bases of word w of read r
       nmask[w * pitch + r]    bit j set   = base j is not one of A, C, G, T (N, IUPAC, '=' ...)
       quality[w * pitch + r]  byte k      = Phred value (offset removed) of base 4w + k;
-                              PHQ_ABSENT_QUALITY marks a base a short read does not have (MDD)
+                              PHQ_ABSENT_QUALITY marks a base a short read does not have (MDD); such a
+                              position also has its nmask bit and both base bits set
 
     Binned qualities (current Illumina instruments emit 4 distinct values) can travel as indices
     into a per-tile codebook: with quality_bits = 4 or 2, position j occupies quality_bits bits at

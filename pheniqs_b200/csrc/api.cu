@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <functional>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,6 +75,8 @@ struct phq_handle {
     std::vector< DecoderParams > params;
     std::vector< std::vector< ScratchSegment > > scratch;
     std::vector< BarcodeEntry* > device_barcodes;
+    std::vector< MddSlot* > device_mdd;        /* MDD lookup tables (kernels.cuh), NULL where the scan kernel is used */
+    std::vector< std::vector< int32_t > > mdd_shape;    /* per decoder: first slot and mask of every table, total slots */
     std::vector< void* > device_grid;          /* combinatorial codec blobs (kernels.cuh), NULL where not applicable */
     std::vector< int32_t > grid_shape;         /* per decoder: grid_a, grid_b, grid_entries, grid_split */
     double* device_phred;
@@ -220,6 +223,123 @@ void upload_grid(phq_handle* h, size_t k) {
     h->grid_shape[k * 4 + 3] = split;
 }
 
+/*  MDD lookup tables (MddSlot, kernels.cuh). Built when the reference's scan is provably a lookup: every segment
+    is at most 16 nucleotides, at most four segments, and every tolerance is within the segment's Shannon bound
+    (metric.h:87-111), so the spheres of radius `tolerance` around the distinct words of a segment are disjoint. */
+void upload_mdd_tables(phq_handle* h, size_t k) {
+    const DecoderSpec& d(h->chain[k]);
+    if(h->device_mdd[k] != NULL) { cudaFree(h->device_mdd[k]); h->device_mdd[k] = NULL; }
+    h->mdd_shape[k].clear();
+    if(d.algorithm != PHQ_MDD || d.segment_cardinality > 4) { return; }
+    const int32_t S(d.segment_cardinality);
+    const int32_t L(d.nucleotide_cardinality);
+    std::vector< std::vector< std::vector< uint8_t > > > words(static_cast< size_t >(S));      /* distinct words per segment, 2-bit codes */
+    std::vector< std::vector< int32_t > > word_of(static_cast< size_t >(S), std::vector< int32_t >(static_cast< size_t >(d.barcode_cardinality)));
+    for(int32_t s(0); s < S; ++s) {
+        if(d.segment_length[s] > 16) { return; }
+        std::map< std::vector< uint8_t >, int32_t > index;
+        for(int32_t b(0); b < d.barcode_cardinality; ++b) {
+            std::vector< uint8_t > w;
+            for(int32_t j(d.segment_offset[s]); j < d.segment_offset[s + 1]; ++j) {
+                const uint8_t code(d.barcode[static_cast< size_t >(b) * L + j]);
+                w.push_back(code == 1 ? 0 : code == 2 ? 1 : code == 4 ? 2 : 3);
+            }
+            auto found(index.find(w));
+            if(found == index.end()) {
+                found = index.emplace(w, static_cast< int32_t >(words[s].size())).first;
+                words[s].push_back(w);
+            }
+            word_of[s][b] = found->second;
+        }
+        if(words[s].size() > 65534) { return; }
+        /* Shannon bound of the segment: (minimum pairwise distance - 1) / 2 */
+        int32_t minimum(d.segment_length[s]);
+        if(words[s].size() > 4096) { return; }          /* the pairwise scan is quadratic */
+        for(size_t i(0); i < words[s].size(); ++i) {
+            for(size_t j(i + 1); j < words[s].size(); ++j) {
+                int32_t distance(0);
+                for(size_t p(0); p < words[s][i].size(); ++p) { distance += words[s][i][p] != words[s][j][p]; }
+                minimum = std::min(minimum, distance);
+            }
+        }
+        const int32_t bound((minimum - 1) / 2);
+        if(words[s].size() > 1 && d.distance_tolerance[s] > bound) { return; }
+        if(d.distance_tolerance[s] >= d.segment_length[s] || d.distance_tolerance[s] < 0) { return; }
+    }
+    /* enumerate every variant within tolerance: a subset of positions, each replaced by another base or made ambiguous */
+    struct Entry { uint32_t key_lo, key_hi, value; };
+    std::vector< std::vector< Entry > > entries(static_cast< size_t >(S) + 1);
+    for(int32_t s(0); s < S; ++s) {
+        const int32_t n(d.segment_length[s]);
+        const int32_t tolerance(d.distance_tolerance[s]);
+        std::map< std::pair< uint32_t, uint32_t >, uint32_t > seen;
+        for(size_t w(0); w < words[s].size(); ++w) {
+            std::vector< int32_t > position;
+            std::function< bool(int32_t, uint32_t, uint32_t, uint32_t, int32_t) > visit;
+            bool clash(false);
+            visit = [&](int32_t from, uint32_t lo, uint32_t hi, uint32_t amb, int32_t changed) -> bool {
+                const uint32_t key_lo((lo & ~amb) | ((hi & ~amb) << 16));
+                const uint32_t value(static_cast< uint32_t >(w) | (static_cast< uint32_t >(changed) << 24));
+                auto inserted(seen.emplace(std::make_pair(key_lo, amb), value));
+                if(!inserted.second && (inserted.first->second & 0xffffffu) != static_cast< uint32_t >(w)) { clash = true; return false; }
+                if(inserted.second) {
+                    Entry e; e.key_lo = key_lo; e.key_hi = amb; e.value = value;
+                    entries[s].push_back(e);
+                    if(entries[s].size() > 200000) { clash = true; return false; }
+                }
+                if(changed == tolerance) { return true; }
+                for(int32_t p(from); p < n; ++p) {
+                    const uint32_t bit(1u << p);
+                    const uint32_t original(((lo >> p) & 1u) | (((hi >> p) & 1u) << 1));
+                    for(uint32_t alternative(0); alternative < 4; ++alternative) {
+                        if(alternative == original) { continue; }
+                        const uint32_t lo2((lo & ~bit) | ((alternative & 1u) << p));
+                        const uint32_t hi2((hi & ~bit) | ((alternative >> 1) << p));
+                        if(!visit(p + 1, lo2, hi2, amb, changed + 1)) { return false; }
+                    }
+                    if(!visit(p + 1, lo, hi, amb | bit, changed + 1)) { return false; }
+                }
+                return true;
+            };
+            uint32_t lo(0), hi(0);
+            for(int32_t p(0); p < n; ++p) { lo |= (words[s][w][p] & 1u) << p; hi |= (static_cast< uint32_t >(words[s][w][p]) >> 1) << p; }
+            visit(0, lo, hi, 0u, 0);
+            if(clash) { return; }
+        }
+    }
+    if(S > 1) {
+        for(int32_t b(0); b < d.barcode_cardinality; ++b) {
+            uint32_t id[4] = { 0u, 0u, 0u, 0u };
+            for(int32_t s(0); s < S; ++s) { id[s] = static_cast< uint32_t >(word_of[s][b]); }
+            Entry e; e.key_lo = id[0] | (id[1] << 16); e.key_hi = id[2] | (id[3] << 16); e.value = static_cast< uint32_t >(b);
+            entries[S].push_back(e);
+        }
+    }
+    /* open addressing tables, load factor <= 1/2 */
+    std::vector< int32_t > shape;
+    std::vector< MddSlot > blob;
+    for(int32_t t(0); t <= S; ++t) {
+        size_t slots(4);
+        while(slots < entries[t].size() * 2) { slots *= 2; }
+        if(t == S && S == 1) { slots = 4; }
+        const size_t first(blob.size());
+        MddSlot empty; empty.key_lo = 0; empty.key_hi = MDD_EMPTY; empty.value = 0; empty.pad = 0;
+        blob.resize(first + slots, empty);
+        for(const auto& e : entries[t]) {
+            size_t at(mdd_hash(e.key_lo, e.key_hi) & (slots - 1));
+            while(blob[first + at].key_hi != MDD_EMPTY) { at = (at + 1) & (slots - 1); }
+            blob[first + at].key_lo = e.key_lo; blob[first + at].key_hi = e.key_hi; blob[first + at].value = e.value;
+        }
+        shape.push_back(static_cast< int32_t >(first));
+        shape.push_back(static_cast< int32_t >(slots - 1));
+    }
+    if(blob.size() > (1u << 20)) { return; }
+    shape.push_back(static_cast< int32_t >(blob.size()));
+    PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_mdd[k]), blob.size() * sizeof(MddSlot)));
+    PHQ_CUDA(cudaMemcpy(h->device_mdd[k], blob.data(), blob.size() * sizeof(MddSlot), cudaMemcpyHostToDevice));
+    h->mdd_shape[k] = shape;
+}
+
 void refresh_params(phq_handle* h, size_t k) {
     const DecoderSpec& d(h->chain[k]);
     DecoderParams& p(h->params[k]);
@@ -261,6 +381,16 @@ void refresh_params(phq_handle* h, size_t k) {
     p.acc_f64 = h->f64_plane() + h->offset_f64[k];
     p.totals = NULL;
     p.diagnostics = h->diagnostics();
+    for(int32_t s(0); s < d.segment_cardinality && s < PHQ_MAX_SEGMENTS; ++s) {
+        p.segment_offset[s] = d.segment_offset[s];
+        p.segment_length[s] = d.segment_length[s];
+    }
+    p.mdd_tables = h->device_mdd[k];
+    if(p.mdd_tables != NULL) {
+        const std::vector< int32_t >& shape(h->mdd_shape[k]);
+        for(int32_t t(0); t <= d.segment_cardinality; ++t) { p.mdd_first[t] = shape[2 * t]; p.mdd_mask[t] = shape[2 * t + 1]; }
+        p.mdd_slots = shape.back();
+    }
     p.grid = h->device_grid[k];
     p.grid_a = h->grid_shape[k * 4 + 0];
     p.grid_b = h->grid_shape[k * 4 + 1];
@@ -274,6 +404,7 @@ void destroy(phq_handle* h) {
     cudaSetDevice(h->device);
     for(auto* p : h->device_barcodes) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_grid) { if(p != NULL) { cudaFree(p); } }
+    for(auto* p : h->device_mdd) { if(p != NULL) { cudaFree(p); } }
     if(h->device_phred != NULL) { cudaFree(h->device_phred); }
     if(h->device_accumulators != NULL) { cudaFree(h->device_accumulators); }
     if(h->slots_ready) {
@@ -298,9 +429,10 @@ void destroy(phq_handle* h) {
 void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t* qcfail, phq_result* const* results, phq_compact_result* const* compact,
                   DeviceBuffer< unsigned char >& tie_list, cudaStream_t stream) {
     const size_t n_decoders(h->chain.size());
+    /* the PAMLD tie queue (80-byte records) and the MDD short-read queue (read indices) share one buffer:
+       [16 bytes: counter][queue]; launches cover at most PAMLD_LAUNCH_READS reads so it stays bounded */
     bool needs_queue(false);
-    for(const auto& d : h->chain) { needs_queue = needs_queue || d.algorithm == PHQ_PAMLD; }
-    /* layout: [16 bytes: counter][up to PAMLD_LAUNCH_READS TieRecord] */
+    for(size_t k(0); k < n_decoders; ++k) { needs_queue = needs_queue || h->chain[k].algorithm == PHQ_PAMLD || h->params[k].mdd_tables != NULL; }
     const long long queue_reads(n_reads < PAMLD_LAUNCH_READS ? n_reads : PAMLD_LAUNCH_READS);
     if(needs_queue) { tie_list.reserve(16 + static_cast< size_t >(queue_reads) * sizeof(TieRecord)); }
     for(size_t k(0); k < n_decoders; ++k) {
@@ -331,23 +463,23 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
             a.quality_bits = tiles[k].quality_bits == 0 ? 8 : tiles[k].quality_bits;
             if(a.quality_bits != 8 && a.quality_bits != 4 && a.quality_bits != 2) { throw InternalError("quality_bits must be 8, 4 or 2"); }
             memcpy(a.codebook, tiles[k].quality_codebook, 16);
-            if(h->chain[k].algorithm == PHQ_PAMLD) {
-                /* sub-launches over read ranges keep the tie queue bounded; planes are [word][read], so a range is a pointer offset */
-                for(long long begin(0); begin < n_reads && status == cudaSuccess; begin += PAMLD_LAUNCH_READS) {
-                    TileArguments part(a);
-                    part.n_reads = (n_reads - begin) < PAMLD_LAUNCH_READS ? (n_reads - begin) : PAMLD_LAUNCH_READS;
-                    part.bases = a.bases + begin;
-                    part.nmask = a.nmask + begin;
-                    part.quality = a.quality + begin;
-                    part.qcfail = a.qcfail + begin;
-                    part.results = a.results != NULL ? a.results + begin : NULL;
-                    part.compact = a.compact != NULL ? a.compact + begin : NULL;
+            /* sub-launches over read ranges keep the queues bounded; planes are [word][read], so a range is a pointer offset */
+            for(long long begin(0); begin < n_reads && status == cudaSuccess; begin += PAMLD_LAUNCH_READS) {
+                TileArguments part(a);
+                part.n_reads = (n_reads - begin) < PAMLD_LAUNCH_READS ? (n_reads - begin) : PAMLD_LAUNCH_READS;
+                part.bases = a.bases + begin;
+                part.nmask = a.nmask + begin;
+                part.quality = a.quality + begin;
+                part.qcfail = a.qcfail + begin;
+                part.results = a.results != NULL ? a.results + begin : NULL;
+                part.compact = a.compact != NULL ? a.compact + begin : NULL;
+                if(h->chain[k].algorithm == PHQ_PAMLD) {
                     status = launch_pamld(p, part, h->geometry, stream);
                     h->kernel_launches += PAMLD_KERNEL_LAUNCHES;
+                } else {
+                    status = launch_mdd(p, part, h->geometry, stream);
+                    h->kernel_launches += p.mdd_tables != NULL ? 2 * MDD_KERNEL_LAUNCHES : MDD_KERNEL_LAUNCHES;
                 }
-            } else {
-                status = launch_mdd(p, a, h->geometry, stream);
-                h->kernel_launches += MDD_KERNEL_LAUNCHES;
             }
         } else {
             status = launch_count(p, a, h->geometry, stream);
@@ -452,6 +584,8 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         h->params.resize(n);
         h->device_barcodes.assign(n, NULL);
         h->device_grid.assign(n, NULL);
+        h->device_mdd.assign(n, NULL);
+        h->mdd_shape.assign(n, std::vector< int32_t >());
         h->grid_shape.assign(n * 4, 0);
         h->scratch.resize(n);
         h->offset_u64.resize(n);
@@ -480,6 +614,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
                 PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), static_cast< size_t >(chain[k].barcode_cardinality) * sizeof(BarcodeEntry)));
                 upload_barcodes(h, k);
                 upload_grid(h, k);
+                upload_mdd_tables(h, k);
             }
             refresh_params(h, k);
         }
@@ -582,7 +717,13 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
                     for(int32_t i(0); i < d.segment_length[s]; ++i) {
                         const int32_t j(d.segment_offset[s] + i);
                         if(!stale_semantics && i >= from.length) {
-                            phred[j] = PHQ_ABSENT_QUALITY;      /* Sequence::distance_from stops at the observed length */
+                            /* Sequence::distance_from stops at the observed length: the position is absent, marked by
+                               PHQ_ABSENT_QUALITY and, so that kernels that never read qualities see it too, by an
+                               ambiguous position whose base bits are both set (a real ambiguous base has them clear) */
+                            phred[j] = PHQ_ABSENT_QUALITY;
+                            lo |= 1u << j;
+                            hi |= 1u << j;
+                            ambiguous |= 1u << j;
                             continue;
                         }
                         /* PAMLD reads the expected length: terminator, then stale bytes (barcode.h:150) */

@@ -1070,7 +1070,9 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
     const int segment_cardinality = SEGMENTS > 0 ? SEGMENTS : P.segment_cardinality;
     const uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
 
-    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    /* either all reads of the launch or, after mdd_table_kernel, the few it queued */
+    const long long item_cardinality = A.index_list != nullptr ? static_cast< long long >(*A.index_count) : A.n_reads;
+    const long long tile_cardinality = (item_cardinality + blockDim.x - 1) / blockDim.x;
     const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * stream.chunk_cardinality;
     unsigned iteration = 0;
@@ -1080,8 +1082,9 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
     if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
 
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
-        const long long r = tile * blockDim.x + tid;
-        const bool valid = r < A.n_reads;
+        const long long item = tile * blockDim.x + tid;
+        const bool valid = item < item_cardinality;
+        const long long r = (valid && A.index_list != nullptr) ? A.index_list[item] : item;
         uint32_t o_lo = 0, o_hi = 0, nmask = 0, present = 0, masked = 0, qcfail = 0;
         if(valid) {
             const uint32_t w0 = load_stream(A.bases + r);
@@ -1161,6 +1164,144 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, valid);
             const unsigned pass = __ballot_sync(FULL_MASK, valid && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
+            }
+        }
+    }
+    block_epilogue(S, P);
+}
+
+/* ------------------------------------------------------------------ MDD by lookup
+   See MddSlot in kernels.cuh. Per read: one probe sequence per segment and one for the tuple of words, instead
+   of a scan over every barcode. The exact match of mdd.cpp:44-46 (tested before quality masking) is the same
+   lookup with distance 0 on the unmasked observation. Reads that miss positions (short tokens: the reference
+   counts only the observed length) are queued for mdd_kernel. Only the base and ambiguity planes are read
+   unless quality masking is on. */
+__device__ __forceinline__ bool mdd_probe(const MddSlot* __restrict__ table, uint32_t mask, uint32_t key_lo, uint32_t key_hi, uint32_t& value) {
+    uint32_t at = mdd_hash(key_lo, key_hi) & mask;
+    #pragma unroll 1
+    for(uint32_t step = 0; step <= mask; ++step) {
+        const uint4 slot = *reinterpret_cast< const uint4* >(table + at);
+        if(slot.y == MDD_EMPTY) { return false; }
+        if(slot.x == key_lo && slot.y == key_hi) { value = slot.z; return true; }
+        at = (at + 1u) & mask;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256, 4)
+mdd_table_kernel(const DecoderParams P, const TileArguments A, int* queue, unsigned* queue_count, int staged) {
+    extern __shared__ __align__(256) unsigned char smem[];
+    const BlockState S = block_prologue(smem, P, false, staged ? P.mdd_slots : 1);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const MddSlot* tables = P.mdd_tables;
+    if(staged) {
+        if(tid == 0) {
+            const uint32_t bytes = static_cast< uint32_t >(P.mdd_slots) * 16u;
+            mbarrier_expect_tx(&S.mbarrier[0], bytes);
+            tma_bulk_load(smem + S.plan.off_stage, P.mdd_tables, bytes, &S.mbarrier[0]);
+        }
+        mbarrier_wait(&S.mbarrier[0], 0);
+        tables = reinterpret_cast< const MddSlot* >(smem + S.plan.off_stage);
+    }
+    const int segment_cardinality = P.segment_cardinality;
+    const bool masking = P.quality_masking_threshold > 0;
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+        uint32_t o_lo = 0, o_hi = 0, nmask = 0, qcfail = 0;
+        if(valid) {
+            const uint32_t w0 = load_stream(A.bases + r);
+            o_lo = w0 & 0xffffu;
+            o_hi = w0 >> 16;
+            nmask = load_stream(A.nmask + r);
+            if(P.word_cardinality > 1) {
+                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
+                o_lo |= w1 << 16;
+                o_hi |= w1 & 0xffff0000u;
+                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
+            }
+            qcfail = A.qcfail[r];
+        }
+        /* a position the read does not have is packed as ambiguous with both base bits set */
+        const bool partial = valid && (nmask & o_lo & o_hi) != 0u;
+
+        int decoded = 0, distance = 0;
+        if(valid && !partial) {
+            uint32_t ambiguity = nmask;
+            #pragma unroll 1
+            for(int pass = 0; pass < 2; ++pass) {
+                bool found = true;
+                int total = 0;
+                uint32_t word[4] = { 0u, 0u, 0u, 0u };
+                #pragma unroll 1
+                for(int s = 0; s < segment_cardinality && found; ++s) {
+                    const uint32_t field = (1u << P.segment_length[s]) - 1u;
+                    const uint32_t lo = (o_lo >> P.segment_offset[s]) & field;
+                    const uint32_t hi = (o_hi >> P.segment_offset[s]) & field;
+                    const uint32_t n = (ambiguity >> P.segment_offset[s]) & field;
+                    uint32_t value = 0;
+                    /* bases under an ambiguous / masked position do not take part in the key */
+                    found = mdd_probe(tables + P.mdd_first[s], static_cast< uint32_t >(P.mdd_mask[s]), (lo & ~n) | ((hi & ~n) << 16), n, value);
+                    word[s & 3] = value & 0xffffffu;
+                    total += static_cast< int >(value >> 24);
+                }
+                int barcode = -1;
+                if(found) {
+                    if(segment_cardinality == 1) {
+                        barcode = static_cast< int >(word[0]);
+                    } else {
+                        uint32_t value = 0;
+                        if(mdd_probe(tables + P.mdd_first[segment_cardinality], static_cast< uint32_t >(P.mdd_mask[segment_cardinality]),
+                                     word[0] | (word[1] << 16), word[2] | (word[3] << 16), value)) { barcode = static_cast< int >(value); }
+                    }
+                }
+                /* pass 0 is the unmasked observation: final when masking is off, and the exact match otherwise */
+                if(barcode >= 0 && (!masking || total == 0)) { decoded = barcode + 1; distance = total; break; }
+                if(!masking || pass == 1) {
+                    if(barcode >= 0) { decoded = barcode + 1; distance = total; }
+                    break;
+                }
+                /* quality masking (sequence.h:321-332): positions below the threshold always count as errors */
+                uint32_t masked = 0;
+                for(int g = 0; g < P.quality_word_cardinality; ++g) {
+                    const uint32_t qw = quality_word(A, r, g);
+                    #pragma unroll
+                    for(int k = 0; k < 4; ++k) {
+                        if(static_cast< int >((qw >> (8 * k)) & 0xffu) < P.quality_masking_threshold) { masked |= 1u << (g * 4 + k); }
+                    }
+                }
+                ambiguity = nmask | (masked & ((P.nucleotide_cardinality >= 32) ? 0xffffffffu : ((1u << P.nucleotide_cardinality) - 1u)));
+            }
+        }
+
+        const unsigned queued = __ballot_sync(FULL_MASK, partial);
+        if(queued) {
+            unsigned slot = 0;
+            if(lane == 0) { slot = atomicAdd(queue_count, static_cast< unsigned >(__popc(queued))); }
+            slot = __shfl_sync(FULL_MASK, slot, 0);
+            if(partial) { queue[slot + __popc(queued & ((1u << lane) - 1u))] = static_cast< int >(r); }
+        }
+        const bool decided = valid && !partial;
+        if(decided) {
+            if(decoded == 0) { qcfail = 1; }
+            if(decoded > 0 && distance > 0) {
+                S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
+                if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
+            }
+            S.accumulator.add(decoded, ACC_COUNT, 1u);
+            if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
+            A.qcfail[r] = static_cast< uint8_t >(qcfail);
+            store_result(A, r, decoded, distance, 0.0, qcfail);
+        }
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, decided);
+            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
             if(lane == 0) {
                 atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
                 atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
@@ -1281,8 +1422,7 @@ cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile,
     }
 }
 
-cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
-    if(tile.n_reads <= 0) { return cudaSuccess; }
+static cudaError_t launch_mdd_scan(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     const SharedPlan plan = make_plan(params.barcode_cardinality, false);
     const size_t bytes = plan.fixed_bytes;
     const int threads = 256;
@@ -1308,6 +1448,32 @@ cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, c
             break;
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    if(tile.n_reads <= 0) { return cudaSuccess; }
+    if(params.mdd_tables == nullptr) { return launch_mdd_scan(params, tile, geometry, stream); }
+    /* lookup kernel, then the scan kernel over the reads it queued (short tokens) */
+    int* const queue = reinterpret_cast< int* >(reinterpret_cast< unsigned char* >(params.tie_record));
+    unsigned* const queue_count = params.tie_count;
+    cudaError_t status = cudaMemsetAsync(queue_count, 0, sizeof(unsigned), stream);
+    if(status != cudaSuccess) { return status; }
+    const SharedPlan staged_plan = make_plan(params.barcode_cardinality, false, params.mdd_slots);
+    const bool staged = staged_plan.fixed_bytes <= 100 * 1024;         /* keep two CTAs per SM */
+    const SharedPlan plan = staged ? staged_plan : make_plan(params.barcode_cardinality, false, 1);
+    status = cudaFuncSetAttribute(mdd_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(plan.fixed_bytes));
+    if(status != cudaSuccess) { return status; }
+    const int threads = 256;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const long long resident = static_cast< long long >(geometry.multiprocessor_count) * 4;
+    const int grid = static_cast< int >(tiles < resident ? tiles : resident);
+    mdd_table_kernel<<< grid, threads, plan.fixed_bytes, stream >>>(params, tile, queue, queue_count, staged ? 1 : 0);
+    status = cudaGetLastError();
+    if(status != cudaSuccess) { return status; }
+    TileArguments rest(tile);
+    rest.index_list = queue;
+    rest.index_count = queue_count;
+    return launch_mdd_scan(params, rest, geometry, stream);
 }
 
 cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {

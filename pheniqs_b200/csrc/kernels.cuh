@@ -39,6 +39,26 @@ enum { ACC_COUNT = 0, ACC_PF_COUNT = 1, ACC_DISTANCE = 2, ACC_LOW_CONDITIONAL = 
 enum { ACC_CONFIDENCE = 0, ACC_PF_CONFIDENCE = 1, ACC_F64_COLUMNS = 2 };
 enum { DIAG_EXACT_PATH = 0, DIAG_THRESHOLD_BAND = 1, DIAG_COLUMNS = 2 };
 
+/*  MDD lookup tables (mdd_table_kernel). When every segment's tolerance is within its Shannon bound, at most one
+    distinct word of a segment lies within tolerance of an observed segment, so the reference's scan
+    (mdd.cpp:50-80) is a lookup: every variant of every distinct word within tolerance (substitutions and N /
+    masked positions) is a key of an open addressing hash table whose value is the word and the distance, and the
+    tuple of words is looked up in a second table that holds the barcodes. */
+struct __align__(16) MddSlot {
+    uint32_t key_lo;            /* segment: low plane | high plane << 16; combination: word 0 | word 1 << 16 */
+    uint32_t key_hi;            /* segment: ambiguity plane; combination: word 2 | word 3 << 16; 0xffffffff = empty slot */
+    uint32_t value;             /* segment: word | distance << 24; combination: barcode index */
+    uint32_t pad;
+};
+constexpr uint32_t MDD_EMPTY = 0xffffffffu;
+__host__ __device__ inline uint32_t mdd_hash(uint32_t key_lo, uint32_t key_hi) {
+    uint32_t h = (key_lo * 0x9E3779B1u) ^ (key_hi * 0x85EBCA77u) ^ 0x27D4EB2Fu;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
+}
+
 /* what the scan kernel hands to the tie kernel for a queued read */
 struct __align__(16) TieRecord {
     double best;                /* the scan's maximum prior adjusted product (relative to P0) */
@@ -74,6 +94,12 @@ struct DecoderParams {
     double* acc_f64;                            /* [(N+1)][2] device */
     unsigned long long* totals;                 /* [2] count, pf_count; NULL unless this is the last decoder of the chain */
     unsigned long long* diagnostics;            /* [DIAG_COLUMNS] */
+    const MddSlot* mdd_tables;                  /* NULL = scan every barcode (mdd_kernel) */
+    int32_t mdd_first[PHQ_MAX_SEGMENTS + 1];   /* first slot of each segment table; [segment_cardinality] = the combination table */
+    int32_t mdd_mask[PHQ_MAX_SEGMENTS + 1];    /* slots - 1 of each table (powers of two) */
+    int32_t mdd_slots;                          /* total slots */
+    int32_t segment_offset[PHQ_MAX_SEGMENTS];
+    int32_t segment_length[PHQ_MAX_SEGMENTS];
     const void* grid;                           /* combinatorial codec blob: grid_a headers, grid_b words, grid_entries entries (16 B each); NULL = generic scan */
     int32_t grid_a;
     int32_t grid_b;
@@ -94,6 +120,8 @@ struct TileArguments {
     phq_compact_result* compact;                /* may be NULL; written instead of `results` when set */
     int quality_bits;                           /* 8, 4 or 2 (phq_tile) */
     int nucleotides;                            /* nucleotide cardinality of the decoder */
+    const int* index_list;                      /* when set, the kernel works on reads index_list[0 .. *index_count) instead of 0 .. n_reads */
+    const unsigned* index_count;
     uint32_t codebook[4];                       /* quality_codebook, little endian words */
 };
 
