@@ -230,7 +230,7 @@ void upload_mdd_tables(phq_handle* h, size_t k) {
     const DecoderSpec& d(h->chain[k]);
     if(h->device_mdd[k] != NULL) { cudaFree(h->device_mdd[k]); h->device_mdd[k] = NULL; }
     h->mdd_shape[k].clear();
-    if(d.algorithm != PHQ_MDD || d.segment_cardinality > 4) { return; }
+    if(d.algorithm != PHQ_MDD || d.segment_cardinality > 4 || d.barcode_cardinality > MDD_MAX_BARCODES) { return; }
     const int32_t S(d.segment_cardinality);
     const int32_t L(d.nucleotide_cardinality);
     std::vector< std::vector< std::vector< uint8_t > > > words(static_cast< size_t >(S));      /* distinct words per segment, 2-bit codes */
@@ -251,7 +251,7 @@ void upload_mdd_tables(phq_handle* h, size_t k) {
             }
             word_of[s][b] = found->second;
         }
-        if(words[s].size() > 65534) { return; }
+        if(words[s].size() > static_cast< size_t >(MDD_MAX_WORDS)) { return; }
         /* Shannon bound of the segment: (minimum pairwise distance - 1) / 2 */
         int32_t minimum(d.segment_length[s]);
         if(words[s].size() > 4096) { return; }          /* the pairwise scan is quadratic */
@@ -264,7 +264,7 @@ void upload_mdd_tables(phq_handle* h, size_t k) {
         }
         const int32_t bound((minimum - 1) / 2);
         if(words[s].size() > 1 && d.distance_tolerance[s] > bound) { return; }
-        if(d.distance_tolerance[s] >= d.segment_length[s] || d.distance_tolerance[s] < 0) { return; }
+        if(d.distance_tolerance[s] >= d.segment_length[s] || d.distance_tolerance[s] < 0 || d.distance_tolerance[s] > 3) { return; }
     }
     /* enumerate every variant within tolerance: a subset of positions, each replaced by another base or made ambiguous */
     struct Entry { uint32_t key_lo, key_hi, value; };
@@ -279,9 +279,9 @@ void upload_mdd_tables(phq_handle* h, size_t k) {
             bool clash(false);
             visit = [&](int32_t from, uint32_t lo, uint32_t hi, uint32_t amb, int32_t changed) -> bool {
                 const uint32_t key_lo((lo & ~amb) | ((hi & ~amb) << 16));
-                const uint32_t value(static_cast< uint32_t >(w) | (static_cast< uint32_t >(changed) << 24));
+                const uint32_t value(static_cast< uint32_t >(w) | (static_cast< uint32_t >(changed) << 12));
                 auto inserted(seen.emplace(std::make_pair(key_lo, amb), value));
-                if(!inserted.second && (inserted.first->second & 0xffffffu) != static_cast< uint32_t >(w)) { clash = true; return false; }
+                if(!inserted.second && (inserted.first->second & 0xfffu) != static_cast< uint32_t >(w)) { clash = true; return false; }
                 if(inserted.second) {
                     Entry e; e.key_lo = key_lo; e.key_hi = amb; e.value = value;
                     entries[s].push_back(e);
@@ -307,28 +307,29 @@ void upload_mdd_tables(phq_handle* h, size_t k) {
             if(clash) { return; }
         }
     }
-    if(S > 1) {
-        for(int32_t b(0); b < d.barcode_cardinality; ++b) {
-            uint32_t id[4] = { 0u, 0u, 0u, 0u };
-            for(int32_t s(0); s < S; ++s) { id[s] = static_cast< uint32_t >(word_of[s][b]); }
-            Entry e; e.key_lo = id[0] | (id[1] << 16); e.key_hi = id[2] | (id[3] << 16); e.value = static_cast< uint32_t >(b);
-            entries[S].push_back(e);
-        }
+    /* the tuple of words -> barcode (for one segment: word -> barcode, words are in first-occurrence order) */
+    for(int32_t b(0); b < d.barcode_cardinality; ++b) {
+        uint32_t id[4] = { 0u, 0u, 0u, 0u };
+        for(int32_t s(0); s < S; ++s) { id[s] = static_cast< uint32_t >(word_of[s][b]); }
+        Entry e;
+        e.key_lo = id[0] | (id[1] << 12) | (id[2] << 24);
+        e.key_hi = (id[2] >> 8) | (id[3] << 4);
+        e.value = static_cast< uint32_t >(b);
+        entries[S].push_back(e);
     }
-    /* open addressing tables, load factor <= 1/2 */
+    /* open addressing tables, load factor <= 1/4 (mdd_probe fetches the home slot and its neighbour up front) */
     std::vector< int32_t > shape;
     std::vector< MddSlot > blob;
     for(int32_t t(0); t <= S; ++t) {
         size_t slots(4);
-        while(slots < entries[t].size() * 2) { slots *= 2; }
-        if(t == S && S == 1) { slots = 4; }
+        while(slots < entries[t].size() * 4) { slots *= 2; }
         const size_t first(blob.size());
-        MddSlot empty; empty.key_lo = 0; empty.key_hi = MDD_EMPTY; empty.value = 0; empty.pad = 0;
+        MddSlot empty; empty.key_lo = 0; empty.key_hi = 0; empty.value = static_cast< uint16_t >(MDD_EMPTY);
         blob.resize(first + slots, empty);
         for(const auto& e : entries[t]) {
             size_t at(mdd_hash(e.key_lo, e.key_hi) & (slots - 1));
-            while(blob[first + at].key_hi != MDD_EMPTY) { at = (at + 1) & (slots - 1); }
-            blob[first + at].key_lo = e.key_lo; blob[first + at].key_hi = e.key_hi; blob[first + at].value = e.value;
+            while(blob[first + at].value != MDD_EMPTY) { at = (at + 1) & (slots - 1); }
+            blob[first + at].key_lo = e.key_lo; blob[first + at].key_hi = static_cast< uint16_t >(e.key_hi); blob[first + at].value = static_cast< uint16_t >(e.value);
         }
         shape.push_back(static_cast< int32_t >(first));
         shape.push_back(static_cast< int32_t >(slots - 1));

@@ -1179,94 +1179,117 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
    lookup with distance 0 on the unmasked observation. Reads that miss positions (short tokens: the reference
    counts only the observed length) are queued for mdd_kernel. Only the base and ambiguity planes are read
    unless quality masking is on. */
+/*  Open addressing probe. The tables are built at load factor <= 1/4, so the home slot or its neighbour answer
+    almost every lookup: both are fetched up front (two independent LDS.128) and the loop only runs for the
+    rare longer cluster, which keeps the lanes of a warp converged. STAGED = tables in shared memory. */
+template < bool STAGED >
+__device__ __forceinline__ uint2 mdd_slot(const MddSlot* __restrict__ table, uint32_t at) {
+    if(STAGED) {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(shared_address(table) + at * 8u));
+        return v;
+    }
+    return __ldg(reinterpret_cast< const uint2* >(table) + at);
+}
+/* slot words: x = key_lo, y = key_hi | value << 16 */
+template < bool STAGED >
 __device__ __forceinline__ bool mdd_probe(const MddSlot* __restrict__ table, uint32_t mask, uint32_t key_lo, uint32_t key_hi, uint32_t& value) {
     uint32_t at = mdd_hash(key_lo, key_hi) & mask;
+    const uint2 first = mdd_slot< STAGED >(table, at);
+    const uint2 second = mdd_slot< STAGED >(table, (at + 1u) & mask);
+    if(first.x == key_lo && (first.y & 0xffffu) == key_hi && (first.y >> 16) != MDD_EMPTY) { value = first.y >> 16; return true; }
+    if((first.y >> 16) == MDD_EMPTY) { return false; }
+    if(second.x == key_lo && (second.y & 0xffffu) == key_hi && (second.y >> 16) != MDD_EMPTY) { value = second.y >> 16; return true; }
+    if((second.y >> 16) == MDD_EMPTY) { return false; }
     #pragma unroll 1
-    for(uint32_t step = 0; step <= mask; ++step) {
-        const uint4 slot = *reinterpret_cast< const uint4* >(table + at);
-        if(slot.y == MDD_EMPTY) { return false; }
-        if(slot.x == key_lo && slot.y == key_hi) { value = slot.z; return true; }
-        at = (at + 1u) & mask;
+    for(uint32_t step = 2; step <= mask; ++step) {
+        const uint2 slot = mdd_slot< STAGED >(table, (at + step) & mask);
+        if((slot.y >> 16) == MDD_EMPTY) { return false; }
+        if(slot.x == key_lo && (slot.y & 0xffffu) == key_hi) { value = slot.y >> 16; return true; }
     }
     return false;
 }
 
+/* one lookup pass over the SEGMENTS segments with the given ambiguity plane: barcode index or -1, total distance */
+template < int SEGMENTS, bool STAGED >
+__device__ __forceinline__ int mdd_lookup(const DecoderParams& P, const MddSlot* __restrict__ tables, uint32_t o_lo, uint32_t o_hi, uint32_t ambiguity, int& total) {
+    uint32_t word[4] = { 0u, 0u, 0u, 0u };
+    total = 0;
+    #pragma unroll
+    for(int s = 0; s < SEGMENTS; ++s) {
+        const uint32_t field = (1u << P.segment_length[s]) - 1u;
+        const uint32_t n = (ambiguity >> P.segment_offset[s]) & field;
+        const uint32_t keep = field & ~n;           /* bases under an ambiguous / masked position do not take part in the key */
+        const uint32_t lo = (o_lo >> P.segment_offset[s]) & keep;
+        const uint32_t hi = (o_hi >> P.segment_offset[s]) & keep;
+        uint32_t value = 0;
+        if(!mdd_probe< STAGED >(tables + P.mdd_first[s], static_cast< uint32_t >(P.mdd_mask[s]), lo | (hi << 16), n, value)) { return -1; }
+        word[s] = value & 0xfffu;
+        total += static_cast< int >(value >> 12);
+    }
+    uint32_t value = 0;
+    if(!mdd_probe< STAGED >(tables + P.mdd_first[SEGMENTS], static_cast< uint32_t >(P.mdd_mask[SEGMENTS]),
+                            word[0] | (word[1] << 12) | (word[2] << 24), (word[2] >> 8) | (word[3] << 4), value)) { return -1; }
+    return static_cast< int >(value);
+}
+
+template < int SEGMENTS, bool MASKING, bool STAGED >
 __global__ void __launch_bounds__(256, 4)
-mdd_table_kernel(const DecoderParams P, const TileArguments A, int* queue, unsigned* queue_count, int staged) {
+mdd_table_kernel(const DecoderParams P, const TileArguments A, int* queue, unsigned* queue_count) {
+    constexpr bool staged = STAGED;
     extern __shared__ __align__(256) unsigned char smem[];
-    const BlockState S = block_prologue(smem, P, false, staged ? P.mdd_slots : 1);
+    const BlockState S = block_prologue(smem, P, false, staged ? (P.mdd_slots + 1) / 2 : 1);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const MddSlot* tables = P.mdd_tables;
     if(staged) {
         if(tid == 0) {
-            const uint32_t bytes = static_cast< uint32_t >(P.mdd_slots) * 16u;
+            const uint32_t bytes = static_cast< uint32_t >(P.mdd_slots) * 8u;        /* mdd_slots is kept even: 16-byte granules */
             mbarrier_expect_tx(&S.mbarrier[0], bytes);
             tma_bulk_load(smem + S.plan.off_stage, P.mdd_tables, bytes, &S.mbarrier[0]);
         }
         mbarrier_wait(&S.mbarrier[0], 0);
         tables = reinterpret_cast< const MddSlot* >(smem + S.plan.off_stage);
     }
-    const int segment_cardinality = P.segment_cardinality;
-    const bool masking = P.quality_masking_threshold > 0;
+    const bool two_words = P.word_cardinality > 1;
 
+    /* the planes of the next tile are requested before the current tile is worked on */
+    struct Planes { uint32_t w0, w1, n0, n1, qcfail; };
+    auto fetch = [&](long long r) {
+        Planes p;
+        p.w0 = 0; p.w1 = 0; p.n0 = 0; p.n1 = 0; p.qcfail = 0;
+        if(r < A.n_reads) {
+            p.w0 = load_stream(A.bases + r);
+            p.n0 = load_stream(A.nmask + r);
+            if(two_words) {
+                p.w1 = load_stream(A.bases + A.pitch + r);
+                p.n1 = load_stream(A.nmask + A.pitch + r);
+            }
+            p.qcfail = A.qcfail[r];
+        }
+        return p;
+    };
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    Planes next = fetch(static_cast< long long >(blockIdx.x) * blockDim.x + tid);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = tile * blockDim.x + tid;
         const bool valid = r < A.n_reads;
-        uint32_t o_lo = 0, o_hi = 0, nmask = 0, qcfail = 0;
-        if(valid) {
-            const uint32_t w0 = load_stream(A.bases + r);
-            o_lo = w0 & 0xffffu;
-            o_hi = w0 >> 16;
-            nmask = load_stream(A.nmask + r);
-            if(P.word_cardinality > 1) {
-                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
-                o_lo |= w1 << 16;
-                o_hi |= w1 & 0xffff0000u;
-                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
-            }
-            qcfail = A.qcfail[r];
-        }
+        const Planes now = next;
+        next = fetch((tile + gridDim.x) * blockDim.x + tid);
+        const uint32_t o_lo = (now.w0 & 0xffffu) | (now.w1 << 16);
+        const uint32_t o_hi = (now.w0 >> 16) | (now.w1 & 0xffff0000u);
+        const uint32_t nmask = now.n0 | (now.n1 << 16);
+        uint32_t qcfail = now.qcfail;
         /* a position the read does not have is packed as ambiguous with both base bits set */
         const bool partial = valid && (nmask & o_lo & o_hi) != 0u;
+        const bool decided = valid && !partial;
 
         int decoded = 0, distance = 0;
-        if(valid && !partial) {
-            uint32_t ambiguity = nmask;
-            #pragma unroll 1
-            for(int pass = 0; pass < 2; ++pass) {
-                bool found = true;
-                int total = 0;
-                uint32_t word[4] = { 0u, 0u, 0u, 0u };
-                #pragma unroll 1
-                for(int s = 0; s < segment_cardinality && found; ++s) {
-                    const uint32_t field = (1u << P.segment_length[s]) - 1u;
-                    const uint32_t lo = (o_lo >> P.segment_offset[s]) & field;
-                    const uint32_t hi = (o_hi >> P.segment_offset[s]) & field;
-                    const uint32_t n = (ambiguity >> P.segment_offset[s]) & field;
-                    uint32_t value = 0;
-                    /* bases under an ambiguous / masked position do not take part in the key */
-                    found = mdd_probe(tables + P.mdd_first[s], static_cast< uint32_t >(P.mdd_mask[s]), (lo & ~n) | ((hi & ~n) << 16), n, value);
-                    word[s & 3] = value & 0xffffffu;
-                    total += static_cast< int >(value >> 24);
-                }
-                int barcode = -1;
-                if(found) {
-                    if(segment_cardinality == 1) {
-                        barcode = static_cast< int >(word[0]);
-                    } else {
-                        uint32_t value = 0;
-                        if(mdd_probe(tables + P.mdd_first[segment_cardinality], static_cast< uint32_t >(P.mdd_mask[segment_cardinality]),
-                                     word[0] | (word[1] << 16), word[2] | (word[3] << 16), value)) { barcode = static_cast< int >(value); }
-                    }
-                }
-                /* pass 0 is the unmasked observation: final when masking is off, and the exact match otherwise */
-                if(barcode >= 0 && (!masking || total == 0)) { decoded = barcode + 1; distance = total; break; }
-                if(!masking || pass == 1) {
-                    if(barcode >= 0) { decoded = barcode + 1; distance = total; }
-                    break;
-                }
+        if(decided) {
+            /* the unmasked observation: final when masking is off, and the exact match (mdd.cpp:44-46) otherwise */
+            int total;
+            int barcode = mdd_lookup< SEGMENTS, STAGED >(P, tables, o_lo, o_hi, nmask, total);
+            if(MASKING && !(barcode >= 0 && total == 0)) {
                 /* quality masking (sequence.h:321-332): positions below the threshold always count as errors */
                 uint32_t masked = 0;
                 for(int g = 0; g < P.quality_word_cardinality; ++g) {
@@ -1276,8 +1299,10 @@ mdd_table_kernel(const DecoderParams P, const TileArguments A, int* queue, unsig
                         if(static_cast< int >((qw >> (8 * k)) & 0xffu) < P.quality_masking_threshold) { masked |= 1u << (g * 4 + k); }
                     }
                 }
-                ambiguity = nmask | (masked & ((P.nucleotide_cardinality >= 32) ? 0xffffffffu : ((1u << P.nucleotide_cardinality) - 1u)));
+                masked &= (P.nucleotide_cardinality >= 32) ? 0xffffffffu : ((1u << P.nucleotide_cardinality) - 1u);
+                barcode = mdd_lookup< SEGMENTS, STAGED >(P, tables, o_lo, o_hi, nmask | masked, total);
             }
+            if(barcode >= 0) { decoded = barcode + 1; distance = total; }
         }
 
         const unsigned queued = __ballot_sync(FULL_MASK, partial);
@@ -1287,10 +1312,9 @@ mdd_table_kernel(const DecoderParams P, const TileArguments A, int* queue, unsig
             slot = __shfl_sync(FULL_MASK, slot, 0);
             if(partial) { queue[slot + __popc(queued & ((1u << lane) - 1u))] = static_cast< int >(r); }
         }
-        const bool decided = valid && !partial;
         if(decided) {
             if(decoded == 0) { qcfail = 1; }
-            if(decoded > 0 && distance > 0) {
+            if(distance > 0) {
                 S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
                 if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
             }
@@ -1458,16 +1482,31 @@ cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, c
     unsigned* const queue_count = params.tie_count;
     cudaError_t status = cudaMemsetAsync(queue_count, 0, sizeof(unsigned), stream);
     if(status != cudaSuccess) { return status; }
-    const SharedPlan staged_plan = make_plan(params.barcode_cardinality, false, params.mdd_slots);
-    const bool staged = staged_plan.fixed_bytes <= 100 * 1024;         /* keep two CTAs per SM */
+    const SharedPlan staged_plan = make_plan(params.barcode_cardinality, false, (params.mdd_slots + 1) / 2);
+    const bool staged = staged_plan.fixed_bytes <= 54 * 1024;          /* keep four CTAs per SM */
     const SharedPlan plan = staged ? staged_plan : make_plan(params.barcode_cardinality, false, 1);
-    status = cudaFuncSetAttribute(mdd_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(plan.fixed_bytes));
-    if(status != cudaSuccess) { return status; }
     const int threads = 256;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const long long resident = static_cast< long long >(geometry.multiprocessor_count) * 4;
     const int grid = static_cast< int >(tiles < resident ? tiles : resident);
-    mdd_table_kernel<<< grid, threads, plan.fixed_bytes, stream >>>(params, tile, queue, queue_count, staged ? 1 : 0);
+    const bool masking = params.quality_masking_threshold > 0;
+    #define PHQ_LAUNCH_MDD_TABLE_AS(SEGMENTS, MASKING, STAGED) { \
+            status = cudaFuncSetAttribute(mdd_table_kernel< SEGMENTS, MASKING, STAGED >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(plan.fixed_bytes)); \
+            if(status != cudaSuccess) { return status; } \
+            mdd_table_kernel< SEGMENTS, MASKING, STAGED ><<< grid, threads, plan.fixed_bytes, stream >>>(params, tile, queue, queue_count); }
+    #define PHQ_LAUNCH_MDD_TABLE(SEGMENTS) \
+        if(masking && staged) PHQ_LAUNCH_MDD_TABLE_AS(SEGMENTS, true, true) \
+        else if(masking) PHQ_LAUNCH_MDD_TABLE_AS(SEGMENTS, true, false) \
+        else if(staged) PHQ_LAUNCH_MDD_TABLE_AS(SEGMENTS, false, true) \
+        else PHQ_LAUNCH_MDD_TABLE_AS(SEGMENTS, false, false)
+    switch(params.segment_cardinality) {
+        case 1: PHQ_LAUNCH_MDD_TABLE(1) break;
+        case 2: PHQ_LAUNCH_MDD_TABLE(2) break;
+        case 3: PHQ_LAUNCH_MDD_TABLE(3) break;
+        default: PHQ_LAUNCH_MDD_TABLE(4) break;
+    }
+    #undef PHQ_LAUNCH_MDD_TABLE_AS
+    #undef PHQ_LAUNCH_MDD_TABLE
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
     TileArguments rest(tile);

@@ -44,13 +44,14 @@ enum { DIAG_EXACT_PATH = 0, DIAG_THRESHOLD_BAND = 1, DIAG_COLUMNS = 2 };
     (mdd.cpp:50-80) is a lookup: every variant of every distinct word within tolerance (substitutions and N /
     masked positions) is a key of an open addressing hash table whose value is the word and the distance, and the
     tuple of words is looked up in a second table that holds the barcodes. */
-struct __align__(16) MddSlot {
-    uint32_t key_lo;            /* segment: low plane | high plane << 16; combination: word 0 | word 1 << 16 */
-    uint32_t key_hi;            /* segment: ambiguity plane; combination: word 2 | word 3 << 16; 0xffffffff = empty slot */
-    uint32_t value;             /* segment: word | distance << 24; combination: barcode index */
-    uint32_t pad;
+struct __align__(8) MddSlot {
+    uint32_t key_lo;            /* segment: low plane | high plane << 16; combination: word 0 | word 1 << 12 | word 2 << 24 (low 8 bits) */
+    uint16_t key_hi;            /* segment: ambiguity plane; combination: word 2 >> 8 | word 3 << 4 */
+    uint16_t value;             /* segment: word | distance << 12; combination: barcode index; 0xffff = empty slot */
 };
-constexpr uint32_t MDD_EMPTY = 0xffffffffu;
+constexpr uint32_t MDD_EMPTY = 0xffffu;
+constexpr int MDD_MAX_WORDS = 4095;             /* distinct words per segment (12 bits) */
+constexpr int MDD_MAX_BARCODES = 65535;         /* barcode index in 16 bits, 0xffff reserved */
 __host__ __device__ inline uint32_t mdd_hash(uint32_t key_lo, uint32_t key_hi) {
     uint32_t h = (key_lo * 0x9E3779B1u) ^ (key_hi * 0x85EBCA77u) ^ 0x27D4EB2Fu;
     h ^= h >> 15;
