@@ -78,7 +78,7 @@ struct phq_handle {
     std::vector< MddSlot* > device_mdd;        /* MDD lookup tables (kernels.cuh), NULL where the scan kernel is used */
     std::vector< std::vector< int32_t > > mdd_shape;    /* per decoder: first slot and mask of every table, total slots */
     std::vector< void* > device_grid;          /* combinatorial codec blobs (kernels.cuh), NULL where not applicable */
-    std::vector< int32_t > grid_shape;         /* per decoder: grid_a, grid_b, grid_entries, grid_split */
+    std::vector< int32_t > grid_shape;         /* per decoder: grid_a, grid_b, grid_entries, grid_split, grid_dense, grid_uniform */
     double* device_phred;
     unsigned char* device_accumulators;
     std::vector< int64_t > offset_u64;
@@ -152,7 +152,7 @@ void upload_barcodes(phq_handle* h, size_t k) {
 void upload_grid(phq_handle* h, size_t k) {
     const DecoderSpec& d(h->chain[k]);
     if(h->device_grid[k] != NULL) { cudaFree(h->device_grid[k]); h->device_grid[k] = NULL; }
-    for(int i(0); i < 4; ++i) { h->grid_shape[k * 4 + i] = 0; }
+    for(int i(0); i < 6; ++i) { h->grid_shape[k * 6 + i] = 0; }
     if(d.algorithm != PHQ_PAMLD || d.segment_cardinality < 2) { return; }
     const int32_t split(d.segment_length[0]);
     const int32_t L(d.nucleotide_cardinality);
@@ -186,41 +186,63 @@ void upload_grid(phq_handle* h, size_t k) {
     const size_t KA(by_prefix.size()), KB(suffix_word.size());
     if((KA + KB) * 2 > static_cast< size_t >(d.barcode_cardinality) || KB > 64) { return; }
     struct Cell { uint32_t a, b, c, d; };
-    std::vector< Cell > blob(KA + KB);
+    /* dense form when the codec fills most of the KA x KB grid: every A word gets KBP consecutive entries in B
+       word order, absent combinations carry prior 0 (pamld_grid_kernel, KBP > 0) */
+    const size_t KBP(KB <= 8 ? 8 : 16);
+    const bool shape_dense((split == 8 && L == 16) || (split == 10 && L == 20));
+    const bool dense(shape_dense && KB <= 16 && static_cast< size_t >(d.barcode_cardinality) * 10 >= KA * KBP * 6);
+    bool uniform(dense && static_cast< size_t >(d.barcode_cardinality) == KA * KBP);
+    for(int32_t b(1); b < d.barcode_cardinality && uniform; ++b) { uniform = d.concentration[b] == d.concentration[0]; }
+    std::vector< Cell > blob(KA + (dense ? KBP : KB));
     std::vector< Cell > entries;
     size_t at(0);
     for(const auto& run : by_prefix) {
         Cell header;
         header.a = run.first.first; header.b = run.first.second;
         header.c = static_cast< uint32_t >(entries.size());
-        for(int32_t b : run.second) {
-            Cell e;
-            e.a = static_cast< uint32_t >(suffix_of[b]) * 256u;
-            e.b = static_cast< uint32_t >(b);
-            memcpy(&e.c, &d.concentration[b], sizeof(double));
-            entries.push_back(e);
-        }
-        while(entries.size() % 4 != 0) {        /* pad the run with prior 0: the product is 0 and never wins */
-            Cell e;
-            e.a = 0; e.b = 0; e.c = 0; e.d = 0;
-            entries.push_back(e);
+        if(dense) {
+            Cell none;
+            none.a = 0; none.b = 0; none.c = 0; none.d = 0;
+            const size_t first(entries.size());
+            entries.resize(first + KBP, none);
+            for(int32_t b : run.second) {
+                Cell& e(entries[first + static_cast< size_t >(suffix_of[b])]);
+                e.a = static_cast< uint32_t >(suffix_of[b]) * 256u;
+                e.b = static_cast< uint32_t >(b);
+                memcpy(&e.c, &d.concentration[b], sizeof(double));
+            }
+        } else {
+            for(int32_t b : run.second) {
+                Cell e;
+                e.a = static_cast< uint32_t >(suffix_of[b]) * 256u;
+                e.b = static_cast< uint32_t >(b);
+                memcpy(&e.c, &d.concentration[b], sizeof(double));
+                entries.push_back(e);
+            }
+            while(entries.size() % 4 != 0) {        /* pad the run with prior 0: the product is 0 and never wins */
+                Cell e;
+                e.a = 0; e.b = 0; e.c = 0; e.d = 0;
+                entries.push_back(e);
+            }
         }
         header.d = static_cast< uint32_t >(entries.size()) - header.c;
         blob[at++] = header;
     }
-    for(size_t i(0); i < KB; ++i) {
+    for(size_t i(0); i < (dense ? KBP : KB); ++i) {
         Cell w;
-        w.a = suffix_word[i].first; w.b = suffix_word[i].second; w.c = 0; w.d = 0;
+        w.a = i < KB ? suffix_word[i].first : 0u; w.b = i < KB ? suffix_word[i].second : 0u; w.c = 0; w.d = 0;
         blob[at++] = w;
     }
     blob.insert(blob.end(), entries.begin(), entries.end());
     if(blob.size() * 16 > 64 * 1024) { return; }
     PHQ_CUDA(cudaMalloc(&h->device_grid[k], blob.size() * 16));
     PHQ_CUDA(cudaMemcpy(h->device_grid[k], blob.data(), blob.size() * 16, cudaMemcpyHostToDevice));
-    h->grid_shape[k * 4 + 0] = static_cast< int32_t >(KA);
-    h->grid_shape[k * 4 + 1] = static_cast< int32_t >(KB);
-    h->grid_shape[k * 4 + 2] = static_cast< int32_t >(entries.size());
-    h->grid_shape[k * 4 + 3] = split;
+    h->grid_shape[k * 6 + 0] = static_cast< int32_t >(KA);
+    h->grid_shape[k * 6 + 1] = static_cast< int32_t >(dense ? KBP : KB);
+    h->grid_shape[k * 6 + 2] = static_cast< int32_t >(entries.size());
+    h->grid_shape[k * 6 + 3] = split;
+    h->grid_shape[k * 6 + 4] = dense ? static_cast< int32_t >(KBP) : 0;
+    h->grid_shape[k * 6 + 5] = uniform ? 1 : 0;
 }
 
 /*  MDD lookup tables (MddSlot, kernels.cuh). Built when the reference's scan is provably a lookup: every segment
@@ -393,10 +415,12 @@ void refresh_params(phq_handle* h, size_t k) {
         p.mdd_slots = shape.back();
     }
     p.grid = h->device_grid[k];
-    p.grid_a = h->grid_shape[k * 4 + 0];
-    p.grid_b = h->grid_shape[k * 4 + 1];
-    p.grid_entries = h->grid_shape[k * 4 + 2];
-    p.grid_split = h->grid_shape[k * 4 + 3];
+    p.grid_a = h->grid_shape[k * 6 + 0];
+    p.grid_b = h->grid_shape[k * 6 + 1];
+    p.grid_entries = h->grid_shape[k * 6 + 2];
+    p.grid_split = h->grid_shape[k * 6 + 3];
+    p.grid_dense = h->grid_shape[k * 6 + 4];
+    p.grid_uniform = h->grid_shape[k * 6 + 5];
 }
 
 void destroy(phq_handle* h) {
@@ -587,7 +611,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         h->device_grid.assign(n, NULL);
         h->device_mdd.assign(n, NULL);
         h->mdd_shape.assign(n, std::vector< int32_t >());
-        h->grid_shape.assign(n * 4, 0);
+        h->grid_shape.assign(n * 6, 0);
         h->scratch.resize(n);
         h->offset_u64.resize(n);
         h->offset_f64.resize(n);

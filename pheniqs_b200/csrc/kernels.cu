@@ -323,6 +323,57 @@ __device__ __forceinline__ void select_four(Selection& s, double p0, double p1, 
     s.second = max(max(s.second, second), __double2hiint(low));
 }
 
+/* ------------------------------------------------------------------ the observation of one read
+   Everything a PAMLD scan needs from the tile planes. The scan kernels request the next tile's observation
+   before they start on the current one, so the DRAM latency of the planes is hidden behind a whole tile of
+   work even at the low occupancy the shared memory tables allow. */
+template < int G >
+struct ObservedRead {
+    uint32_t o_lo, o_hi, nmask, qcfail;
+    uint32_t raw[G];            /* quality plane words as they travelled (Phred bytes or codebook indices) */
+};
+template < int G >
+__device__ __forceinline__ ObservedRead< G > fetch_read(const TileArguments& A, long long r) {
+    ObservedRead< G > o;
+    o.o_lo = 0; o.o_hi = 0; o.nmask = 0; o.qcfail = 0;
+    #pragma unroll
+    for(int g = 0; g < G; ++g) { o.raw[g] = 0; }
+    if(r < A.n_reads) {
+        const uint32_t w0 = load_stream(A.bases + r);
+        o.o_lo = w0 & 0xffffu;
+        o.o_hi = w0 >> 16;
+        o.nmask = load_stream(A.nmask + r);
+        if(G > 4) {
+            const uint32_t w1 = load_stream(A.bases + A.pitch + r);
+            o.o_lo |= w1 << 16;
+            o.o_hi |= w1 & 0xffff0000u;
+            o.nmask |= load_stream(A.nmask + A.pitch + r) << 16;
+        }
+        const int rows = (A.nucleotides * A.quality_bits + 31) >> 5;
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { if(g < rows) { o.raw[g] = load_stream(A.quality + g * A.pitch + r); } }
+        o.qcfail = A.qcfail[r];
+    }
+    return o;
+}
+/* the four Phred bytes of quality word g from the raw words (see quality_word) */
+template < int G >
+__device__ __forceinline__ uint32_t decode_quality(const TileArguments& A, const uint32_t (&raw)[G], int g) {
+    if(A.quality_bits == 8) { return raw[g]; }
+    const int valid = A.nucleotides - 4 * g;
+    const uint32_t keep = valid >= 4 ? 0xffffffffu : (valid <= 0 ? 0u : ((1u << (8 * valid)) - 1u));
+    if(A.quality_bits == 2) {
+        const uint32_t c = (raw[g >> 2] >> (8 * (g & 3))) & 0xffu;
+        const uint32_t selector = (c & 0x3u) | ((c & 0xcu) << 2) | ((c & 0x30u) << 4) | ((c & 0xc0u) << 6);
+        return __byte_perm(A.codebook[0], 0u, selector) & keep;
+    }
+    const uint32_t c = (raw[g >> 1] >> (16 * (g & 1))) & 0xffffu;
+    const uint32_t low = __byte_perm(A.codebook[0], A.codebook[1], c & 0x7777u);
+    const uint32_t high = __byte_perm(A.codebook[2], A.codebook[3], c & 0x7777u);
+    const uint32_t flag = ((c & 0x8u) >> 3) | ((c & 0x80u) << 1) | ((c & 0x800u) << 5) | ((c & 0x8000u) << 9);
+    return (low ^ ((low ^ high) & (flag * 0xffu))) & keep;
+}
+
 /* ------------------------------------------------------------------ PAMLD decision
    pamld.cpp:87-122 followed by Decoder::classify (decoder.h:68-76) and Classifier::classify
    (classifier.h:78-86) for one read whose winner is known. `t` is the winner's subset product and
@@ -424,31 +475,19 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     const BarcodeEntry* resident_stage = nullptr;
     if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
 
+    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = tile * blockDim.x + tid;
         const bool valid = r < A.n_reads;
 
-        /* ---- load the observation of this lane's read */
-        uint32_t o_lo = 0, o_hi = 0, nmask = 0;
+        /* ---- this lane's read (requested one tile ago); request the next one */
+        const ObservedRead< G > observed = upcoming;
+        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
+        uint32_t qcfail = observed.qcfail;
         uint32_t quality[G];
         #pragma unroll
-        for(int g = 0; g < G; ++g) { quality[g] = 0; }
-        uint32_t qcfail = 0;
-        if(valid) {
-            const uint32_t w0 = load_stream(A.bases + r);
-            o_lo = w0 & 0xffffu;
-            o_hi = w0 >> 16;
-            nmask = load_stream(A.nmask + r);
-            if(G > 4) {
-                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
-                o_lo |= w1 << 16;
-                o_hi |= w1 & 0xffff0000u;
-                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
-            }
-            #pragma unroll
-            for(int g = 0; g < G; ++g) { quality[g] = quality_word(A, r, g); }
-            qcfail = A.qcfail[r];
-        }
+        for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
 
         /* ---- per-read constant P0, subset product tables, high quality mask */
         double base_probability = 1.0;
@@ -634,7 +673,11 @@ __device__ __forceinline__ double column_load(uint32_t address) {
 constexpr int GRID_MAX_WARPS = 20;
 constexpr int GRID_GROUP_WIDTH = 2;
 
-template < int LA, int LB, int W >
+/*  KBP > 0 selects the dense form: the codec fills (most of) the grid of A words x B words, the B word
+    probabilities stay in KBP registers and the barcodes of an A word are its KBP consecutive entries (absent
+    combinations have prior 0), so the scan loop has no per-lane shared memory traffic at all. UNIFORM
+    additionally drops the prior from the loop when every combination is present with the same prior. */
+template < int LA, int LB, int W, int KBP, bool UNIFORM >
 __global__ void __launch_bounds__(GRID_MAX_WARPS * WARP_SIZE, 1)
 pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
     constexpr int L = LA + LB;
@@ -675,30 +718,19 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
     const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
 
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = tile * blockDim.x + tid;
         const bool valid = r < A.n_reads;
 
-        uint32_t o_lo = 0, o_hi = 0, nmask = 0;
+        /* this lane's read (requested one tile ago); request the next one */
+        const ObservedRead< G > observed = upcoming;
+        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
+        uint32_t qcfail = observed.qcfail;
         uint32_t quality[G];
         #pragma unroll
-        for(int g = 0; g < G; ++g) { quality[g] = 0; }
-        uint32_t qcfail = 0;
-        if(valid) {
-            const uint32_t w0 = load_stream(A.bases + r);
-            o_lo = w0 & 0xffffu;
-            o_hi = w0 >> 16;
-            nmask = load_stream(A.nmask + r);
-            if(G > 4) {
-                const uint32_t w1 = load_stream(A.bases + A.pitch + r);
-                o_lo |= w1 << 16;
-                o_hi |= w1 & 0xffff0000u;
-                nmask |= load_stream(A.nmask + A.pitch + r) << 16;
-            }
-            #pragma unroll
-            for(int g = 0; g < G; ++g) { quality[g] = quality_word(A, r, g); }
-            qcfail = A.qcfail[r];
-        }
+        for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
 
         /* ---- per-position factors; P0 in position order; subset tables per part */
         double base_probability = 1.0;
@@ -753,32 +785,65 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
         const uint32_t a_lo = o_lo & MASK_A, a_hi = o_hi & MASK_A, a_n = nmask & MASK_A;
         const uint32_t b_lo = (o_lo >> LA) & MASK_B, b_hi = (o_hi >> LA) & MASK_B, b_n = (nmask >> LA) & MASK_B;
 
-        /* ---- SB: the product of every distinct B word, into this lane's column */
-        #pragma unroll 2
-        for(int k = 0; k < KB; ++k) {
-            const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
-            const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
-            suffix[k * WARP_SIZE] = part_product< W, GA, GB >(table_base, m);
-        }
-        __syncwarp();
-
-        /* ---- barcodes grouped by A word */
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
-        for(int a = 0; a < KA; ++a) {
-            const uint4 h = *reinterpret_cast< const uint4* >(header + a);
-            const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
-            const double prefix = part_product< W, 0, GA >(table_base, m);
-            const int last = static_cast< int >(h.z + h.w);
-            #pragma unroll 2
-            for(int i = static_cast< int >(h.z); i < last; i += 4) {        /* runs are padded to a multiple of four with prior 0 */
-                double p[4];
+        if constexpr(KBP > 0) {
+            /* ---- dense grid: B word probabilities in registers */
+            double sb[KBP];
+            #pragma unroll
+            for(int k = 0; k < KBP; ++k) {
+                const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+                const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+                sb[k] = part_product< W, GA, GB >(table_base, m);
+            }
+            for(int a = 0; a < KA; ++a) {
+                const uint2 h = *reinterpret_cast< const uint2* >(header + a);
+                const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+                const double prefix = part_product< W, 0, GA >(table_base, m);
+                const GridEntry* const run = entry + a * KBP;
                 #pragma unroll
-                for(int u = 0; u < 4; ++u) {
-                    const uint4 raw = *reinterpret_cast< const uint4* >(entry + i + u);
-                    p[u] = (prefix * column_load(suffix_base + raw.x)) * __hiloint2double(raw.w, raw.z);
+                for(int k = 0; k < KBP; k += 4) {
+                    double p[4];
+                    #pragma unroll
+                    for(int u = 0; u < 4; ++u) {
+                        p[u] = prefix * sb[k + u];
+                        if(!UNIFORM) { p[u] *= run[k + u].prior; }
+                    }
+                    select_four(selection, p[0], p[1], p[2], p[3], a * KBP + k);
                 }
-                select_four(selection, p[0], p[1], p[2], p[3], i);
+            }
+            if(UNIFORM) {
+                /* the common prior was left out of the loop: put it back */
+                const double prior = entry[0].prior;
+                selection.best *= prior;
+                selection.rest *= prior;
+            }
+        } else {
+            /* ---- SB: the product of every distinct B word, into this lane's column */
+            #pragma unroll 2
+            for(int k = 0; k < KB; ++k) {
+                const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+                const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+                suffix[k * WARP_SIZE] = part_product< W, GA, GB >(table_base, m);
+            }
+            __syncwarp();
+
+            /* ---- barcodes grouped by A word */
+            for(int a = 0; a < KA; ++a) {
+                const uint4 h = *reinterpret_cast< const uint4* >(header + a);
+                const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+                const double prefix = part_product< W, 0, GA >(table_base, m);
+                const int last = static_cast< int >(h.z + h.w);
+                #pragma unroll 2
+                for(int i = static_cast< int >(h.z); i < last; i += 4) {        /* runs are padded to a multiple of four with prior 0 */
+                    double p[4];
+                    #pragma unroll
+                    for(int u = 0; u < 4; ++u) {
+                        const uint4 raw = *reinterpret_cast< const uint4* >(entry + i + u);
+                        p[u] = (prefix * column_load(suffix_base + raw.x)) * __hiloint2double(raw.w, raw.z);
+                    }
+                    select_four(selection, p[0], p[1], p[2], p[3], i);
+                }
             }
         }
 
@@ -1394,8 +1459,8 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
 }
 
 /* the combinatorial scan: staging area = the grid blob instead of the barcode table */
-template < int LA, int LB >
-cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+template < int LA, int LB, int KBP, bool UNIFORM >
+cudaError_t launch_pamld_grid_as(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     constexpr int W = GRID_GROUP_WIDTH;
     constexpr int G = (LA + LB + 3) / 4;
     constexpr int GA = (LA + W - 1) / W;
@@ -1403,24 +1468,34 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
     const int blob_entries = params.grid_a + params.grid_b + params.grid_entries;
     const SharedPlan plan = make_plan(params.barcode_cardinality, true, blob_entries);
     const size_t fixed = plan.fixed_bytes;
-    const size_t per_warp = static_cast< size_t >(GA + GB) * (256 << W) + static_cast< size_t >(params.grid_b) * 256;
+    const size_t per_warp = static_cast< size_t >(GA + GB) * (256 << W) + (KBP > 0 ? 0 : static_cast< size_t >(params.grid_b) * 256);
     if(fixed + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
     int warps = static_cast< int >((geometry.shared_memory_per_block_optin - fixed) / per_warp);
     warps = warps > GRID_MAX_WARPS ? GRID_MAX_WARPS : warps;
     const size_t bytes = fixed + per_warp * warps;
-    cudaError_t status = cudaFuncSetAttribute(pamld_grid_kernel< LA, LB, W >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    cudaError_t status = cudaFuncSetAttribute(pamld_grid_kernel< LA, LB, W, KBP, UNIFORM >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
     if(status != cudaSuccess) { return status; }
     const int threads = warps * WARP_SIZE;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
     status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
     if(status != cudaSuccess) { return status; }
-    pamld_grid_kernel< LA, LB, W ><<< grid, threads, bytes, stream >>>(params, tile);
+    pamld_grid_kernel< LA, LB, W, KBP, UNIFORM ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
     const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
     pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     return cudaGetLastError();
+}
+template < int LA, int LB, bool DENSE >
+cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    if(DENSE && params.grid_dense == 8) {
+        return params.grid_uniform ? launch_pamld_grid_as< LA, LB, 8, true >(params, tile, geometry, stream) : launch_pamld_grid_as< LA, LB, 8, false >(params, tile, geometry, stream);
+    }
+    if(DENSE && params.grid_dense == 16) {
+        return params.grid_uniform ? launch_pamld_grid_as< LA, LB, 16, true >(params, tile, geometry, stream) : launch_pamld_grid_as< LA, LB, 16, false >(params, tile, geometry, stream);
+    }
+    return launch_pamld_grid_as< LA, LB, 0, false >(params, tile, geometry, stream);
 }
 
 }   /* namespace */
@@ -1428,10 +1503,10 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     if(tile.n_reads <= 0) { return cudaSuccess; }
     if(params.grid != nullptr) {
-        if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_grid< 6, 6 >(params, tile, geometry, stream); }
-        if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_grid< 8, 8 >(params, tile, geometry, stream); }
-        if(params.grid_split == 10 && params.nucleotide_cardinality == 20) { return launch_pamld_grid< 10, 10 >(params, tile, geometry, stream); }
-        if(params.grid_split == 12 && params.nucleotide_cardinality == 24) { return launch_pamld_grid< 12, 12 >(params, tile, geometry, stream); }
+        if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_grid< 6, 6, false >(params, tile, geometry, stream); }
+        if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_grid< 8, 8, true >(params, tile, geometry, stream); }
+        if(params.grid_split == 10 && params.nucleotide_cardinality == 20) { return launch_pamld_grid< 10, 10, true >(params, tile, geometry, stream); }
+        if(params.grid_split == 12 && params.nucleotide_cardinality == 24) { return launch_pamld_grid< 12, 12, false >(params, tile, geometry, stream); }
     }
     switch(params.group_cardinality) {
         case 1: return launch_pamld_groups< 1 >(params, tile, geometry, stream);

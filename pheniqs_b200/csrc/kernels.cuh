@@ -106,6 +106,8 @@ struct DecoderParams {
     int32_t grid_b;
     int32_t grid_entries;
     int32_t grid_split;                         /* nucleotides of the first segment */
+    int32_t grid_dense;                         /* 0, or the padded B word count (8 / 16) of the dense form: entries = grid_a x grid_dense */
+    int32_t grid_uniform;                       /* dense form with every combination present under one prior */
     TieRecord* tie_record;                      /* [reads of the launch] queue of reads whose winner needs the exact tie path (PAMLD) */
     unsigned* tie_count;                        /* queue length, reset before every scan */
 };

@@ -126,11 +126,13 @@ def test_random_decoders(variant, short):
     check(*run_both(None, code, quality, offset, qcfail, compiled=compiled))
 
 
-@pytest.mark.parametrize("shape", [(6, 6, 5, 7), (8, 8, 6, 9), (10, 10, 14, 14), (12, 12, 3, 11)])
+@pytest.mark.parametrize("shape", [(6, 6, 5, 7, 0.8, False), (8, 8, 6, 9, 0.8, False), (10, 10, 14, 14, 0.8, False), (12, 12, 3, 11, 0.8, False),
+                                   (8, 8, 5, 8, 1.0, True), (8, 8, 7, 6, 1.0, False), (10, 10, 4, 16, 1.0, True), (8, 8, 9, 7, 0.9, True)])
 def test_combinatorial_codecs(shape):
-    """Dual-index style codecs (distinct first-segment words x distinct second-segment words, not all
-    combinations present, runs not a multiple of four) take the combinatorial scan kernel."""
-    la, lb, ka, kb = shape
+    """Dual-index style codecs (distinct first-segment words x distinct second-segment words) take the
+    combinatorial scan kernel: sparse grids (runs not a multiple of four), dense grids with absent
+    combinations, and full grids with equal priors (the form that keeps the prior out of the loop)."""
+    la, lb, ka, kb, fill, equal = shape
     rng = np.random.default_rng(la * 100 + ka)
     letters = np.frombuffer(b"ACGT", dtype=np.uint8)
 
@@ -145,8 +147,8 @@ def test_combinatorial_codecs(shape):
     codec = {}
     for i, a in enumerate(first):
         for j, b in enumerate(second):
-            if rng.random() < 0.8:
-                codec["@%02d_%02d" % (j, i)] = {"barcode": [a, b], "concentration": float(rng.integers(1, 4))}
+            if rng.random() < fill:
+                codec["@%02d_%02d" % (j, i)] = {"barcode": [a, b], "concentration": 1.0 if equal else float(rng.integers(1, 4))}
     job = {"sample": {"algorithm": "pamld", "transform": {"token": ["0:0:%d" % la, "1:0:%d" % lb]}, "codec": codec, "noise": 0.04, "confidence threshold": 0.9,
                       "high quality threshold": 20, "high quality distance threshold": 2}}
     compiled = compile_job(job)
