@@ -292,7 +292,7 @@ def main():
     sm_mhz = clock_summary.get("sm_mhz") or 0
     sm_count = torch.cuda.get_device_properties(device).multi_processor_count
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, n),
-                "peak_source": peak_source, "kernel": "pamld_kernel" if chain.info[0].algorithm == 0 or args.workload != "c2" else "mdd_kernel",
+                "peak_source": peak_source, "kernel": "; ".join(chain.kernel_description(k) for k in range(chain.n_decoders)),
                 "kernel_ms_per_launch_set": kernel_ms_mean, "algorithmic_bytes_per_read": bytes_per_read,
                 "pair_words_per_read": pairs, "pair_words_per_s": pairs * n / (kernel_ms_mean * 1e-3),
                 "pair_words_per_clk_per_sm": (pairs * n / (kernel_ms_mean * 1e-3)) / (sm_mhz * 1e6 * sm_count) if sm_mhz else None,

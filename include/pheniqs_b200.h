@@ -221,6 +221,9 @@ int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* 
 /* kernels launched by this handle so far, and reads whose PAMLD decision fell within 1e-12
    (relative) of a threshold or needed the exact tie path (diagnostic "band" counters) */
 int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exact_path_reads, uint64_t* threshold_band_reads);
+/* names of the kernels decoder `decoder` launches with its current tables ("pamld_grid_kernel<8, 8, 2, 8, 1> +
+   pamld_tie_kernel<4>"), NUL terminated into buffer[capacity]; for reports and profiles. No reference counterpart. */
+int phq_kernel_description(phq_handle* handle, int decoder, char* buffer, size_t capacity);
 /* device time (ms) of the kernels of the last phq_decode_batch_device call, measured with CUDA
    events on the launching stream; synchronises that stream */
 int phq_last_kernel_milliseconds(phq_handle* handle, float* milliseconds);

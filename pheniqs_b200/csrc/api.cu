@@ -1018,6 +1018,14 @@ int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exac
     });
 }
 
+int phq_kernel_description(phq_handle* handle, int decoder, char* buffer, size_t capacity) {
+    return guarded(handle, [&]() {
+        if(decoder < 0 || static_cast< size_t >(decoder) >= handle->chain.size()) { throw InternalError("decoder index out of range"); }
+        if(handle->device < 0) { throw InternalError("handle was created without a device"); }
+        describe_kernels(handle->params[static_cast< size_t >(decoder)], static_cast< int >(handle->chain[static_cast< size_t >(decoder)].algorithm), buffer, capacity);
+    });
+}
+
 int phq_last_kernel_milliseconds(phq_handle* handle, float* milliseconds) {
     return guarded(handle, [&]() {
         if(!handle->timing_valid) { throw InternalError("no device batch has been decoded yet"); }

@@ -28,6 +28,7 @@
     re-evaluates that read cooperatively with the reference's exact operation order.
 */
 #include "kernels.cuh"
+#include <cstdio>
 
 namespace phq {
 
@@ -1001,8 +1002,13 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
         if(sub == 0) { W.o_lo[slot] = o_lo; W.o_hi[slot] = o_hi; W.nmask[slot] = nmask; }
 
         /* ---- per-position scores: the eight lanes of a read share its positions */
-        for(int j = sub; j < G * 4; j += TIE_LANES) {
-            uint32_t q = live ? (record.quality[j >> 2] >> (8 * (j & 3))) & 0xffu : 0u;
+        #pragma unroll
+        for(int step = 0; step < (G * 4 + TIE_LANES - 1) / TIE_LANES; ++step) {
+            const int j = sub + step * TIE_LANES;
+            if(j >= G * 4) { break; }
+            /* word j >> 2 = 2 * step + (sub >> 2): picked with a select so the record stays in registers */
+            const uint32_t word = (sub & 4) ? record.quality[(2 * step + 1) < 8 ? (2 * step + 1) : 7] : record.quality[2 * step < 8 ? 2 * step : 7];
+            uint32_t q = live ? (word >> (8 * (j & 3))) & 0xffu : 0u;
             q = q > 127u ? 127u : q;
             const bool ambiguous = (nmask >> j) & 1u;
             W.match_value[slot][j] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : phred_shared[PHRED_TRUE_POSITIVE_QUALITY + q]);
@@ -1598,6 +1604,31 @@ cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile,
     const int grid = static_cast< int >(blocks < resident ? blocks : resident);
     count_kernel<<< grid, threads, 0, stream >>>(params, tile);
     return cudaGetLastError();
+}
+
+/* the kernels launch_pamld / launch_mdd / launch_count pick for these parameters, for reports and profiles */
+void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, size_t capacity) {
+    if(buffer == nullptr || capacity == 0) { return; }
+    const int L = params.nucleotide_cardinality;
+    if(algorithm == 0) {
+        const bool grid = params.grid != nullptr && grid_shape_supported(params.grid_split, L);
+        if(grid) {
+            const bool dense = params.grid_dense != 0 && (params.grid_split == 8 || params.grid_split == 10);
+            snprintf(buffer, capacity, "pamld_grid_kernel<%d, %d, %d, %d, %d> + pamld_tie_kernel<%d>", params.grid_split, L - params.grid_split,
+                     GRID_GROUP_WIDTH, dense ? params.grid_dense : 0, dense && params.grid_uniform ? 1 : 0, (L + 3) / 4);
+        } else {
+            snprintf(buffer, capacity, "pamld_kernel<%d> + pamld_tie_kernel<%d>", params.group_cardinality, params.group_cardinality);
+        }
+    } else if(algorithm == 1) {
+        const int scan = params.segment_cardinality <= 2 ? params.segment_cardinality : 0;
+        if(params.mdd_tables != nullptr) {
+            snprintf(buffer, capacity, "mdd_table_kernel<%d> + mdd_kernel<%d> (short reads)", params.segment_cardinality < 4 ? params.segment_cardinality : 4, scan);
+        } else {
+            snprintf(buffer, capacity, "mdd_kernel<%d>", scan);
+        }
+    } else {
+        snprintf(buffer, capacity, "count_kernel");
+    }
 }
 
 cudaError_t prepare_kernels(const LaunchGeometry&) {

@@ -141,6 +141,7 @@ constexpr long long PAMLD_LAUNCH_READS = 1ll << 24;
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 /* naive / passthrough bookkeeping: count and pf_count of the undetermined row (and the chain totals) */
+void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, size_t capacity);
 cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& geometry);
 /* (first segment length, total length) pairs the combinatorial scan is instantiated for */

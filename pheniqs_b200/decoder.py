@@ -224,6 +224,12 @@ class DecoderChain:
                         torch.from_numpy(t.quality.view(np.int32)).to(device), t.quality_bits, t.quality_codebook))
         return out
 
+    def kernel_description(self, k: int) -> str:
+        """Names of the kernels decoder k launches with its current tables."""
+        buffer = C.create_string_buffer(256)
+        check(self.lib.phq_kernel_description(self.handle, k, buffer, len(buffer)), self.handle)
+        return buffer.value.decode()
+
     def last_kernel_milliseconds(self) -> float:
         ms = C.c_float()
         check(self.lib.phq_last_kernel_milliseconds(self.handle, C.byref(ms)), self.handle)
