@@ -45,13 +45,19 @@ WORKLOAD_LABEL = {
 }
 
 
-def algorithmic_bytes_per_read(chain) -> int:
-    """per tiled decoder ceil(L/4) + ceil(L/8) + L bytes in and 16 bytes out; + 1 byte qcfail per read."""
-    total = 1
+def algorithmic_bytes_per_read(chain, compiled) -> int:
+    """per tiled decoder ceil(L/4) + ceil(L/8) bytes of bases and no-call mask, L quality bytes and
+    16 bytes out; + 1 byte qcfail in and out per read. An MDD decoder without quality masking never needs the quality
+    plane (absent positions travel in the base words), so its L quality bytes are not counted."""
+    total = 2
     for info in chain.info:
         if info.has_tile:
+            topic = compiled[{0: "sample", 1: "molecular", 2: "cellular"}[info.topic]]
+            spec = topic[info.index] if isinstance(topic, list) else topic
             L = info.nucleotide_cardinality
-            total += (L + 3) // 4 + (L + 7) // 8 + L + 16
+            total += (L + 3) // 4 + (L + 7) // 8 + 16
+            if not (info.algorithm == 1 and int(spec.get("quality masking threshold", 0)) <= 0):
+                total += L
     return total
 
 
@@ -284,7 +290,7 @@ def main():
         u, _ = chain.accumulators(next(k for k, info in enumerate(chain.info) if info.has_tile))
         assert int(u[:, 0].sum()) == n, "accumulators do not cover the batch"
 
-    bytes_per_read = algorithmic_bytes_per_read(chain)
+    bytes_per_read = algorithmic_bytes_per_read(chain, compiled)
     peak, peak_source = measured_peaks()
     achieved = bytes_per_read * n / (kernel_ms_mean * 1e-3) / 1e9
     pairs = pair_words_per_read(chain)

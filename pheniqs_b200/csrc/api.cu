@@ -188,11 +188,13 @@ void upload_grid(phq_handle* h, size_t k) {
     struct Cell { uint32_t a, b, c, d; };
     /* dense form when the codec fills most of the KA x KB grid: every A word gets KBP consecutive entries in B
        word order, absent combinations carry prior 0 (pamld_grid_kernel, KBP > 0) */
-    const size_t KBP(KB <= 8 ? 8 : 16);
-    const bool shape_dense((split == 8 && L == 16) || (split == 10 && L == 20));
-    const bool dense(shape_dense && KB <= 16 && static_cast< size_t >(d.barcode_cardinality) * 10 >= KA * KBP * 6);
-    bool uniform(dense && static_cast< size_t >(d.barcode_cardinality) == KA * KBP);
+    /* separable form: the full KA x KB grid under one prior (the default of a multiplexed run before prior
+       estimation); entries are the KA x KB matrix and the kernel evaluates KA + KB words per read */
+    bool uniform(static_cast< size_t >(d.barcode_cardinality) == KA * KB);
     for(int32_t b(1); b < d.barcode_cardinality && uniform; ++b) { uniform = d.concentration[b] == d.concentration[0]; }
+    const size_t KBP(uniform ? KB : (KB <= 8 ? 8 : 16));
+    const bool shape_dense((split == 8 && L == 16) || (split == 10 && L == 20));
+    const bool dense(uniform || (shape_dense && KB <= 16 && static_cast< size_t >(d.barcode_cardinality) * 10 >= KA * KBP * 6));
     std::vector< Cell > blob(KA + (dense ? KBP : KB));
     std::vector< Cell > entries;
     size_t at(0);

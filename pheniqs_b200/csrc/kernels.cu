@@ -324,6 +324,23 @@ __device__ __forceinline__ void select_four(Selection& s, double p0, double p1, 
     s.second = max(max(s.second, second), __double2hiint(low));
 }
 
+/*  Selection over the word probabilities of one part of a separable codec: the maximum (first on equality),
+    the largest of the others and the sum of the others. */
+struct PartSelection {
+    double best;
+    double second;
+    double rest;
+    int index;
+};
+__device__ __forceinline__ void select_part(PartSelection& s, double value, int i) {
+    const bool higher = value > s.best;
+    const double low = higher ? s.best : value;
+    s.index = higher ? i : s.index;
+    s.best = higher ? value : s.best;
+    s.second = fmax(s.second, low);
+    s.rest += low;
+}
+
 /* ------------------------------------------------------------------ the observation of one read
    Everything a PAMLD scan needs from the tile planes. The scan kernels request the next tile's observation
    before they start on the current one, so the DRAM latency of the planes is hidden behind a whole tile of
@@ -788,7 +805,36 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
-        if constexpr(KBP > 0) {
+        if constexpr(UNIFORM) {
+            /* ---- full grid under one prior: p(a, k) = SA[a] * SB[k] * prior is separable, so the maximum is
+               (argmax SA, argmax SB), the runner-up is one of (best A, second B) / (second A, best B), and the
+               sum of everything else follows from the two parts' sums. KA + KB word products per read instead
+               of KA * KB pair products; the values are the same single roundings the pair loop would form. */
+            PartSelection part_b;
+            part_b.best = 0.0; part_b.second = 0.0; part_b.rest = 0.0; part_b.index = 0;
+            #pragma unroll 4
+            for(int k = 0; k < KB; ++k) {
+                const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+                const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+                select_part(part_b, part_product< W, GA, GB >(table_base, m), k);
+            }
+            PartSelection part_a;
+            part_a.best = 0.0; part_a.second = 0.0; part_a.rest = 0.0; part_a.index = 0;
+            #pragma unroll 4
+            for(int a = 0; a < KA; ++a) {
+                const uint2 h = *reinterpret_cast< const uint2* >(header + a);
+                const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+                select_part(part_a, part_product< W, 0, GA >(table_base, m), a);
+            }
+            const double prior = entry[0].prior;
+            const double best = part_a.best * part_b.best;
+            const double runner_up = fmax(part_a.best * part_b.second, part_a.second * part_b.best);
+            /* tie detection on the products before the common prior, like the pair loops */
+            selection.second = (__double2hiint(runner_up) + 1 >= __double2hiint(best)) ? 0x7ff00000 : 0;
+            selection.index = part_a.index * KB + part_b.index;
+            selection.rest = (part_a.best * part_b.rest + part_a.rest * (part_b.best + part_b.rest)) * prior;
+            selection.best = best * prior;
+        } else if constexpr(KBP > 0) {
             /* ---- dense grid: B word probabilities in registers */
             double sb[KBP];
             #pragma unroll
@@ -807,17 +853,10 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                     double p[4];
                     #pragma unroll
                     for(int u = 0; u < 4; ++u) {
-                        p[u] = prefix * sb[k + u];
-                        if(!UNIFORM) { p[u] *= run[k + u].prior; }
+                        p[u] = (prefix * sb[k + u]) * run[k + u].prior;
                     }
                     select_four(selection, p[0], p[1], p[2], p[3], a * KBP + k);
                 }
-            }
-            if(UNIFORM) {
-                /* the common prior was left out of the loop: put it back */
-                const double prior = entry[0].prior;
-                selection.best *= prior;
-                selection.rest *= prior;
             }
         } else {
             /* ---- SB: the product of every distinct B word, into this lane's column */
@@ -1495,12 +1534,9 @@ cudaError_t launch_pamld_grid_as(const DecoderParams& params, const TileArgument
 }
 template < int LA, int LB, bool DENSE >
 cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
-    if(DENSE && params.grid_dense == 8) {
-        return params.grid_uniform ? launch_pamld_grid_as< LA, LB, 8, true >(params, tile, geometry, stream) : launch_pamld_grid_as< LA, LB, 8, false >(params, tile, geometry, stream);
-    }
-    if(DENSE && params.grid_dense == 16) {
-        return params.grid_uniform ? launch_pamld_grid_as< LA, LB, 16, true >(params, tile, geometry, stream) : launch_pamld_grid_as< LA, LB, 16, false >(params, tile, geometry, stream);
-    }
+    if(params.grid_uniform) { return launch_pamld_grid_as< LA, LB, 1, true >(params, tile, geometry, stream); }
+    if(DENSE && params.grid_dense == 8) { return launch_pamld_grid_as< LA, LB, 8, false >(params, tile, geometry, stream); }
+    if(DENSE && params.grid_dense == 16) { return launch_pamld_grid_as< LA, LB, 16, false >(params, tile, geometry, stream); }
     return launch_pamld_grid_as< LA, LB, 0, false >(params, tile, geometry, stream);
 }
 
@@ -1615,7 +1651,7 @@ void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, 
         if(grid) {
             const bool dense = params.grid_dense != 0 && (params.grid_split == 8 || params.grid_split == 10);
             snprintf(buffer, capacity, "pamld_grid_kernel<%d, %d, %d, %d, %d> + pamld_tie_kernel<%d>", params.grid_split, L - params.grid_split,
-                     GRID_GROUP_WIDTH, dense ? params.grid_dense : 0, dense && params.grid_uniform ? 1 : 0, (L + 3) / 4);
+                     GRID_GROUP_WIDTH, params.grid_uniform ? 1 : (dense ? params.grid_dense : 0), params.grid_uniform ? 1 : 0, (L + 3) / 4);
         } else {
             snprintf(buffer, capacity, "pamld_kernel<%d> + pamld_tie_kernel<%d>", params.group_cardinality, params.group_cardinality);
         }

@@ -127,11 +127,12 @@ def test_random_decoders(variant, short):
 
 
 @pytest.mark.parametrize("shape", [(6, 6, 5, 7, 0.8, False), (8, 8, 6, 9, 0.8, False), (10, 10, 14, 14, 0.8, False), (12, 12, 3, 11, 0.8, False),
-                                   (8, 8, 5, 8, 1.0, True), (8, 8, 7, 6, 1.0, False), (10, 10, 4, 16, 1.0, True), (8, 8, 9, 7, 0.9, True)])
+                                   (8, 8, 5, 8, 1.0, True), (8, 8, 7, 6, 1.0, False), (10, 10, 4, 16, 1.0, True), (8, 8, 9, 7, 0.9, True),
+                                   (6, 6, 4, 5, 1.0, True), (12, 12, 3, 20, 1.0, True), (8, 8, 12, 3, 1.0, True)])
 def test_combinatorial_codecs(shape):
     """Dual-index style codecs (distinct first-segment words x distinct second-segment words) take the
     combinatorial scan kernel: sparse grids (runs not a multiple of four), dense grids with absent
-    combinations, and full grids with equal priors (the form that keeps the prior out of the loop)."""
+    combinations, and full grids with equal priors (the separable form: KA + KB word products per read)."""
     la, lb, ka, kb, fill, equal = shape
     rng = np.random.default_rng(la * 100 + ka)
     letters = np.frombuffer(b"ACGT", dtype=np.uint8)
