@@ -154,6 +154,9 @@ __device__ __forceinline__ uint32_t quality_word(const TileArguments& A, long lo
 /* ------------------------------------------------------------------ per-CTA accumulators
    AccumulatingOption (selector.h:32-60). Staged in shared memory (u32 counters, f64 sums) when the
    table is small, flushed with one global atomic per non-zero cell; straight to global otherwise. */
+/*  The per-CTA tables in shared memory hold every (total, pass-filter) column pair SPLIT: a read that passes
+    the filter is added to the pass-filter column only, one that fails to the total column only, and the
+    epilogue flushes total = failed + passed. One shared atomic per read and pair instead of two. */
 struct Accumulator {
     uint32_t* shared_u32;
     double* shared_f64;
@@ -163,9 +166,20 @@ struct Accumulator {
         if(shared_u32 != nullptr) { atomicAdd(&shared_u32[row * ACC_U64_COLUMNS + column], value); }
         else { atomicAdd(&global_u64[static_cast< long long >(row) * ACC_U64_COLUMNS + column], static_cast< unsigned long long >(value)); }
     }
-    __device__ __forceinline__ void add(int row, int column, double value) const {
-        if(shared_f64 != nullptr) { atomicAdd(&shared_f64[row * ACC_F64_COLUMNS + column], value); }
-        else { atomicAdd(&global_f64[static_cast< long long >(row) * ACC_F64_COLUMNS + column], value); }
+    /* total += value, and pass_filter += value when the read passes */
+    __device__ __forceinline__ void add_pair(int row, int total, int pass_filter, uint32_t value, bool passes) const {
+        if(shared_u32 != nullptr) { atomicAdd(&shared_u32[row * ACC_U64_COLUMNS + (passes ? pass_filter : total)], value); }
+        else {
+            atomicAdd(&global_u64[static_cast< long long >(row) * ACC_U64_COLUMNS + total], static_cast< unsigned long long >(value));
+            if(passes) { atomicAdd(&global_u64[static_cast< long long >(row) * ACC_U64_COLUMNS + pass_filter], static_cast< unsigned long long >(value)); }
+        }
+    }
+    __device__ __forceinline__ void add_pair(int row, int total, int pass_filter, double value, bool passes) const {
+        if(shared_f64 != nullptr) { atomicAdd(&shared_f64[row * ACC_F64_COLUMNS + (passes ? pass_filter : total)], value); }
+        else {
+            atomicAdd(&global_f64[static_cast< long long >(row) * ACC_F64_COLUMNS + total], value);
+            if(passes) { atomicAdd(&global_f64[static_cast< long long >(row) * ACC_F64_COLUMNS + pass_filter], value); }
+        }
     }
 };
 
@@ -210,11 +224,16 @@ __device__ __forceinline__ void block_epilogue(const BlockState& s, const Decode
     __syncthreads();
     const int tid = threadIdx.x;
     for(int i = tid; i < s.plan.accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) {
-        const uint32_t v = s.accumulator.shared_u32[i];
-        if(v) { atomicAdd(&P.acc_u64[i], static_cast< unsigned long long >(v)); }
+        const int column = i % ACC_U64_COLUMNS;
+        unsigned long long v = s.accumulator.shared_u32[i];
+        /* split pairs (Accumulator): the total column also receives what went to its pass-filter column */
+        if(column == ACC_COUNT) { v += s.accumulator.shared_u32[i - ACC_COUNT + ACC_PF_COUNT]; }
+        if(column == ACC_DISTANCE) { v += s.accumulator.shared_u32[i - ACC_DISTANCE + ACC_PF_DISTANCE]; }
+        if(v) { atomicAdd(&P.acc_u64[i], v); }
     }
     for(int i = tid; i < s.plan.accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) {
-        const double v = s.accumulator.shared_f64[i];
+        double v = s.accumulator.shared_f64[i];
+        if(i % ACC_F64_COLUMNS == ACC_CONFIDENCE) { v += s.accumulator.shared_f64[i - ACC_CONFIDENCE + ACC_PF_CONFIDENCE]; }
         if(v != 0.0) { atomicAdd(&P.acc_f64[i], v); }
     }
     if(tid < 2 && P.totals != nullptr && s.misc[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(s.misc[tid])); }
@@ -426,9 +445,8 @@ __device__ __forceinline__ Verdict pamld_decide(const DecoderParams& P, const Ac
 
     if(conditional_probability > P.random_barcode_probability) {
         if(v.confidence > P.confidence_threshold) {
-            accumulator.add(best_row, ACC_CONFIDENCE, v.confidence);
             if(P.high_quality_distance_threshold > 0 && high_quality_distance >= P.high_quality_distance_threshold) { v.qcfail = 1; }
-            if(!v.qcfail) { accumulator.add(best_row, ACC_PF_CONFIDENCE, v.confidence); }
+            accumulator.add_pair(best_row, ACC_CONFIDENCE, ACC_PF_CONFIDENCE, v.confidence, !v.qcfail);
         } else {
             accumulator.add(best_row, ACC_LOW_CONFIDENCE, 1u);
             v.qcfail = 1;
@@ -441,11 +459,9 @@ __device__ __forceinline__ Verdict pamld_decide(const DecoderParams& P, const Ac
         v.confidence = 0.0;
     }
     if(v.decoded > 0 && v.distance > 0) {
-        accumulator.add(v.decoded, ACC_DISTANCE, static_cast< uint32_t >(v.distance));
-        if(!v.qcfail) { accumulator.add(v.decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(v.distance)); }
+        accumulator.add_pair(v.decoded, ACC_DISTANCE, ACC_PF_DISTANCE, static_cast< uint32_t >(v.distance), !v.qcfail);
     }
-    accumulator.add(v.decoded, ACC_COUNT, 1u);
-    if(!v.qcfail) { accumulator.add(v.decoded, ACC_PF_COUNT, 1u); }
+    accumulator.add_pair(v.decoded, ACC_COUNT, ACC_PF_COUNT, 1u, !v.qcfail);
     return v;
 }
 
@@ -1263,11 +1279,9 @@ mdd_kernel(const DecoderParams P, const TileArguments A) {
             else if(found_index >= 0) { decoded = found_index + 1; distance = found_distance; }
             if(decoded == 0) { qcfail = 1; }
             if(decoded > 0 && distance > 0) {
-                S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
-                if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
+                S.accumulator.add_pair(decoded, ACC_DISTANCE, ACC_PF_DISTANCE, static_cast< uint32_t >(distance), !qcfail);
             }
-            S.accumulator.add(decoded, ACC_COUNT, 1u);
-            if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
+            S.accumulator.add_pair(decoded, ACC_COUNT, ACC_PF_COUNT, 1u, !qcfail);
             A.qcfail[r] = static_cast< uint8_t >(qcfail);
             store_result(A, r, decoded, distance, 0.0, qcfail);
         }
@@ -1425,11 +1439,9 @@ mdd_table_kernel(const DecoderParams P, const TileArguments A, int* queue, unsig
         if(decided) {
             if(decoded == 0) { qcfail = 1; }
             if(distance > 0) {
-                S.accumulator.add(decoded, ACC_DISTANCE, static_cast< uint32_t >(distance));
-                if(!qcfail) { S.accumulator.add(decoded, ACC_PF_DISTANCE, static_cast< uint32_t >(distance)); }
+                S.accumulator.add_pair(decoded, ACC_DISTANCE, ACC_PF_DISTANCE, static_cast< uint32_t >(distance), !qcfail);
             }
-            S.accumulator.add(decoded, ACC_COUNT, 1u);
-            if(!qcfail) { S.accumulator.add(decoded, ACC_PF_COUNT, 1u); }
+            S.accumulator.add_pair(decoded, ACC_COUNT, ACC_PF_COUNT, 1u, !qcfail);
             A.qcfail[r] = static_cast< uint8_t >(qcfail);
             store_result(A, r, decoded, distance, 0.0, qcfail);
         }
