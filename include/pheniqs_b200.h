@@ -216,6 +216,28 @@ int phq_estimate_priors(phq_handle* handle, int decoder, double* estimated_noise
     as Classifier::adjust_prior writes them, classifier.h:125-160) for the next pass. */
 int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* concentration /* [N] */);
 
+/* ------------------------------------------------------------------ report and prior adjusted job */
+
+/* The decoder sections of the job report Transcode::finalize assembles (transcode.cpp:1811-1863): "outgoing",
+   "sample", "molecular", "cellular" with every AccumulatingSelector / AccumulatingOption key the reference
+   encodes (selector.cpp:102-135, 215-247; classifier.h:161-177; barcode.cpp:53-67), the estimated priors
+   (classifier.h:94-124), read group tags on the sample elements, cleaned and key sorted (json.cpp:834-893),
+   written with at most `precision` decimal places (the reference's float precision, 15 by default).
+   "incoming" (feed statistics, not part of this path) is encoded when incoming_count > 0.
+   Reads the device accumulators of this handle; after an all-reduce of phq_accumulator_buffer it is the report
+   of the whole job. *report_json is malloc'd; release with phq_free. */
+int phq_report(phq_handle* handle, uint64_t incoming_count, uint64_t incoming_pf_count, int precision, char** report_json);
+/* the same from caller-held tables (u64_tables[k]: [(N_k + 1)][6], f64_tables[k]: [(N_k + 1)][2], chain order) and
+   chain totals; pure host work, also available on a host-only handle */
+int phq_encode_report(phq_handle* handle, const uint64_t* const* u64_tables, const double* const* f64_tables,
+                      uint64_t count, uint64_t pf_count, uint64_t incoming_count, uint64_t incoming_pf_count,
+                      int precision, char** report_json);
+/* The prior adjusted job: `noise` and every codec `concentration` of the sample / molecular / cellular decoders of
+   job_json replaced by the report's "estimated noise" / "estimated concentration" (barcodes matched by their
+   segments; 0 where the report has no estimate), as tool/pheniqs-prior-api.py:39-56, 186-215 and
+   Classifier::adjust_prior (classifier.h:125-160) do; key sorted. Host only. */
+int phq_adjust_job(const char* job_json, const char* report_json, int precision, char** adjusted_json);
+
 /* ------------------------------------------------------------------ instrumentation */
 
 /* kernels launched by this handle so far, and reads whose PAMLD decision fell within 1e-12

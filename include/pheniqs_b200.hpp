@@ -10,6 +10,7 @@
         classify(const Read&, Read&)                classify(batch)            (transcode.h:51-65)
         collect(const TranscodingDecoder&)          accumulator_buffer() + one all-reduce (transcode.cpp:162-179)
         finalize()                                  estimate_priors(k)         (classifier.h:94-124)
+        Transcode::finalize report                  report()                   (transcode.cpp:1811-1863)
         Error subclasses with ErrorCode             phq::Error subclasses with the same codes (error.h:32-136)
 
     No CUDA or torch types appear; link with -lpheniqs_b200.
@@ -58,6 +59,15 @@ inline std::string compile_job(const std::string& job_json) {
     std::string compiled(out);
     phq_free(out);
     return compiled;
+}
+
+/* the prior adjusted job (tool/pheniqs-prior-api.py:39-56, classifier.h:125-160) */
+inline std::string adjust_job(const std::string& job_json, const std::string& report_json, int precision = 15) {
+    char* out(NULL);
+    raise(phq_adjust_job(job_json.c_str(), report_json.c_str(), precision, &out), phq_last_global_error());
+    std::string adjusted(out);
+    phq_free(out);
+    return adjusted;
 }
 
 /* host planes of one decoder for a batch, owned by the caller (pinned when `pinned`) */
@@ -155,6 +165,14 @@ class BatchDecoder {
         /* Classifier::adjust_prior (classifier.h:125-160) applied to the live tables */
         void set_priors(size_t k, double noise, const std::vector< double >& concentration) {
             check(phq_set_priors(handle_, static_cast< int >(k), noise, concentration.data()));
+        }
+        /* the decoder sections of Transcode::finalize's report (transcode.cpp:1811-1863) from the device accumulators */
+        std::string report(uint64_t incoming_count = 0, uint64_t incoming_pf_count = 0, int precision = 15) {
+            char* out(NULL);
+            check(phq_report(handle_, incoming_count, incoming_pf_count, precision, &out));
+            std::string text(out);
+            phq_free(out);
+            return text;
         }
         phq_handle* handle() { return handle_; }
 

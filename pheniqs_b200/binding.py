@@ -66,7 +66,8 @@ EXPORTS = (
     "phq_decoder_count", "phq_decoder_describe", "phq_pack", "phq_decode_batch", "phq_decode_batch_compact",
     "phq_decode_batch_device", "phq_decode_batch_device_compact",
     "phq_host_alloc", "phq_host_free", "phq_accumulators", "phq_totals", "phq_accumulator_buffer",
-    "phq_reset_accumulators", "phq_estimate_priors", "phq_set_priors", "phq_statistics", "phq_kernel_description",
+    "phq_reset_accumulators", "phq_estimate_priors", "phq_set_priors", "phq_report", "phq_encode_report", "phq_adjust_job",
+    "phq_statistics", "phq_kernel_description",
     "phq_last_kernel_milliseconds",
 )
 
@@ -109,6 +110,9 @@ def library() -> C.CDLL:
     lib.phq_estimate_priors.argtypes = [C.c_void_p, C.c_int, P(C.c_double), C.c_void_p]
     lib.phq_set_priors.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
     lib.phq_statistics.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
+    lib.phq_report.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, P(C.c_void_p)]
+    lib.phq_encode_report.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_void_p), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, P(C.c_void_p)]
+    lib.phq_adjust_job.argtypes = [C.c_char_p, C.c_char_p, C.c_int, P(C.c_void_p)]
     lib.phq_kernel_description.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.phq_last_kernel_milliseconds.argtypes = [C.c_void_p, P(C.c_float)]
     _library = lib

@@ -6,6 +6,7 @@
 */
 #include "kernels.cuh"
 #include "spec.hpp"
+#include "report.hpp"
 
 #include <cuda_runtime.h>
 
@@ -71,6 +72,7 @@ constexpr long long SUB_BATCH_READS = 1ll << 22;
 
 struct phq_handle {
     int device;
+    Json job;                                   /* the compiled job as given (codec records for the report) */
     std::vector< DecoderSpec > chain;
     std::vector< DecoderParams > params;
     std::vector< std::vector< ScratchSegment > > scratch;
@@ -550,6 +552,20 @@ template < class F > int guarded(phq_handle* h, F body) {
     }
 }
 
+/* for entry points that are pure host work and therefore also serve host-only handles */
+template < class F > int guarded_host(phq_handle* h, F body) {
+    try {
+        if(h == NULL) { throw InternalError("null handle"); }
+        body();
+        return PHQ_OK;
+    } catch(const phq::Error& e) { h != NULL ? h->error = e.what() : global_error = e.what(); return e.code; }
+    catch(const JsonError& e) {
+        std::string m(std::string("Configuration error : ") + e.what());
+        h != NULL ? h->error = m : global_error = m;
+        return PHQ_CONFIGURATION_ERROR;
+    } catch(const std::exception& e) { h != NULL ? h->error = e.what() : global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
+}
+
 }   /* namespace */
 
 extern "C" {
@@ -578,13 +594,15 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
     try {
         if(compiled_job_json == NULL || handle == NULL) { throw InternalError("null argument"); }
         *handle = NULL;
-        std::vector< DecoderSpec > chain(parse_compiled_job(Json::parse(compiled_job_json)));
+        const Json job(Json::parse(compiled_job_json));
+        std::vector< DecoderSpec > chain(parse_compiled_job(job));
 
         if(device < 0) {
             /* host-only handle: configuration, phq_pack and phq_decoder_describe work; anything that
                needs the GPU fails with an internal error. For feed threads and CPU-only tests. */
             h = new phq_handle();
             h->device = -1;
+            h->job = job;
             h->chain = chain;
             h->scratch.resize(chain.size());
             for(size_t k(0); k < chain.size(); ++k) { h->scratch[k].resize(static_cast< size_t >(chain[k].segment_cardinality)); }
@@ -604,6 +622,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
 
         h = new phq_handle();
         h->device = device;
+        h->job = job;
         h->chain = chain;
         h->geometry.multiprocessor_count = prop.multiProcessorCount;
         h->geometry.shared_memory_per_block_optin = prop.sharedMemPerBlockOptin;
@@ -1018,6 +1037,63 @@ int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exac
         if(exact_path_reads != NULL) { *exact_path_reads = d[DIAG_EXACT_PATH]; }
         if(threshold_band_reads != NULL) { *threshold_band_reads = d[DIAG_THRESHOLD_BAND]; }
     });
+}
+
+/* ------------------------------------------------------------------ report and prior adjusted job (report.hpp) */
+namespace {
+char* duplicate(const std::string& text) {
+    char* out(static_cast< char* >(malloc(text.size() + 1)));
+    if(out == NULL) { throw phq::Error(PHQ_OUT_OF_MEMORY_ERROR, "Out of memory error"); }
+    memcpy(out, text.c_str(), text.size() + 1);
+    return out;
+}
+}
+
+int phq_encode_report(phq_handle* handle, const uint64_t* const* u64_tables, const double* const* f64_tables, uint64_t count, uint64_t pf_count,
+                      uint64_t incoming_count, uint64_t incoming_pf_count, int precision, char** report_json) {
+    return guarded_host(handle, [&]() {
+        if(u64_tables == NULL || f64_tables == NULL || report_json == NULL) { throw InternalError("null argument"); }
+        std::vector< AccumulatorTables > tables(handle->chain.size());
+        for(size_t k(0); k < handle->chain.size(); ++k) {
+            if(u64_tables[k] == NULL || f64_tables[k] == NULL) { throw InternalError("null accumulator table"); }
+            tables[k].u64 = u64_tables[k];
+            tables[k].f64 = f64_tables[k];
+        }
+        const Json report(encode_job_report(handle->job, handle->chain, tables, count, pf_count, incoming_count, incoming_pf_count));
+        *report_json = duplicate(report.dump(precision, 4));
+    });
+}
+
+int phq_report(phq_handle* handle, uint64_t incoming_count, uint64_t incoming_pf_count, int precision, char** report_json) {
+    return guarded(handle, [&]() {
+        if(report_json == NULL) { throw InternalError("null argument"); }
+        if(handle->device < 0) { throw InternalError("handle was created without a device"); }
+        std::vector< uint64_t > u(static_cast< size_t >(handle->n_u64));
+        std::vector< double > f(static_cast< size_t >(handle->n_f64));
+        PHQ_CUDA(cudaDeviceSynchronize());
+        PHQ_CUDA(cudaMemcpy(u.data(), handle->u64_plane(), u.size() * 8, cudaMemcpyDeviceToHost));
+        PHQ_CUDA(cudaMemcpy(f.data(), handle->f64_plane(), f.size() * 8, cudaMemcpyDeviceToHost));
+        std::vector< AccumulatorTables > tables(handle->chain.size());
+        for(size_t k(0); k < handle->chain.size(); ++k) {
+            tables[k].u64 = u.data() + handle->offset_u64[k];
+            tables[k].f64 = f.data() + handle->offset_f64[k];
+        }
+        const uint64_t count(u[u.size() - 4]), pf_count(u[u.size() - 3]);
+        const Json report(encode_job_report(handle->job, handle->chain, tables, count, pf_count, incoming_count, incoming_pf_count));
+        *report_json = duplicate(report.dump(precision, 4));
+    });
+}
+
+int phq_adjust_job(const char* job_json, const char* report_json, int precision, char** adjusted_json) {
+    try {
+        if(job_json == NULL || report_json == NULL || adjusted_json == NULL) { throw InternalError("null argument"); }
+        Json adjusted(adjust_job(Json::parse(job_json), Json::parse(report_json)));
+        adjusted.sort_keys();
+        *adjusted_json = duplicate(adjusted.dump(precision, 4));
+        return PHQ_OK;
+    } catch(const phq::Error& e) { global_error = e.what(); return e.code; }
+    catch(const JsonError& e) { global_error = std::string("Configuration error : ") + e.what(); return PHQ_CONFIGURATION_ERROR; }
+    catch(const std::exception& e) { global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
 }
 
 int phq_kernel_description(phq_handle* handle, int decoder, char* buffer, size_t capacity) {

@@ -39,6 +39,20 @@ def compile_job(job) -> dict:
         lib.phq_free(out)
 
 
+def adjust_job(job, report, precision: int = 15, text: bool = False):
+    """The prior adjusted job (phq_adjust_job): tool/pheniqs-prior-api.py:39-56 / classifier.h:125-160. Host only."""
+    lib = library()
+    as_bytes = lambda v: (v if isinstance(v, (str, bytes)) else json.dumps(v))
+    a, b = as_bytes(job), as_bytes(report)
+    out = C.c_void_p()
+    check(lib.phq_adjust_job(a.encode() if isinstance(a, str) else a, b.encode() if isinstance(b, str) else b, precision, C.byref(out)))
+    try:
+        raw = C.string_at(out).decode()
+        return raw if text else json.loads(raw)
+    finally:
+        lib.phq_free(out)
+
+
 def shard_range(n_reads: int, rank: int, world_size: int):
     """Contiguous read range of one rank, as the reference slices nothing but threads pull in turn
     (transcode.cpp:287-316); reads are independent, any partition is valid."""
@@ -274,6 +288,32 @@ class DecoderChain:
         u, f = self.accumulator_tensors()
         torch.cuda.current_stream(u.device).synchronize()
         all_reduce_accumulators(u, f, group)
+
+    def report(self, incoming=(0, 0), precision: int = 15, text: bool = False):
+        """The decoder sections of the job report (phq_report) from this handle's device accumulators."""
+        out = C.c_void_p()
+        check(self.lib.phq_report(self.handle, int(incoming[0]), int(incoming[1]), precision, C.byref(out)), self.handle)
+        try:
+            raw = C.string_at(out).decode()
+            return raw if text else json.loads(raw)
+        finally:
+            self.lib.phq_free(out)
+
+    def encode_report(self, tables, totals, incoming=(0, 0), precision: int = 15, text: bool = False):
+        """phq_encode_report: the same report from caller-held tables [(u64 [(N+1), 6], f64 [(N+1), 2]) per decoder]
+        and chain totals (count, pf_count). Pure host work: also valid on a host-only handle."""
+        u = [np.ascontiguousarray(t[0], dtype=np.uint64) for t in tables]
+        f = [np.ascontiguousarray(t[1], dtype=np.float64) for t in tables]
+        pu = (C.c_void_p * len(u))(*[a.ctypes.data for a in u])
+        pf = (C.c_void_p * len(f))(*[a.ctypes.data for a in f])
+        out = C.c_void_p()
+        check(self.lib.phq_encode_report(self.handle, pu, pf, int(totals[0]), int(totals[1]), int(incoming[0]), int(incoming[1]),
+                                         precision, C.byref(out)), self.handle)
+        try:
+            raw = C.string_at(out).decode()
+            return raw if text else json.loads(raw)
+        finally:
+            self.lib.phq_free(out)
 
     def estimate_priors(self, k: int):
         noise = C.c_double()
