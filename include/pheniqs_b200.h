@@ -190,6 +190,27 @@ int phq_decode_batch_device(phq_handle* handle, int64_t n_reads, const phq_tile*
 int phq_decode_batch_device_compact(phq_handle* handle, int64_t n_reads, const phq_tile* device_tiles,
                                     uint8_t* device_qcfail, phq_compact_result* const* device_compact_results, void* stream);
 
+/* ------------------------------------------------------------------ feed bytes in
+
+   The same classification from the bytes of the FASTQ records themselves: the device does what the feed and
+   Rule::apply do on the host in the reference — AsciiToAmbiguousBam and `quality - phred offset` (fastq.h:55-78,
+   iupac.h:153-171), token slicing and reverse complement (transform.h:65-80, 142-169) — and packs the tiles, so the
+   host only hands over the barcode-bearing input segments as they sit in its feed buffers (feed.h:281-456). */
+typedef struct phq_raw_segment {
+    const uint8_t* sequence;    /* ASCII nucleotides (IUPAC) of every read of the batch, concatenated */
+    const uint8_t* quality;     /* ASCII qualities (Phred + phred offset), same layout */
+    const int64_t* offset;      /* [n_reads + 1] first byte of every read; NULL when every read has `length` bytes */
+    int64_t length;             /* bytes per read when offset is NULL */
+} phq_raw_segment;
+
+/* phq_decode_batch / phq_decode_batch_compact with `segments[n_input_segments]` (host pointers; input segments no
+   token refers to may be left NULL) in place of packed tiles. Results, accumulators and the state short tokens
+   leave behind (see phq_pack) are identical to phq_pack of the decoded reads followed by phq_decode_batch. */
+int phq_decode_batch_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                         int32_t phred_offset, const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out);
+int phq_decode_batch_raw_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                                 int32_t phred_offset, const uint8_t* qcfail_in, phq_compact_result* const* compact_results);
+
 int phq_host_alloc(void** pointer, size_t bytes);       /* pinned host memory */
 void phq_host_free(void* pointer);
 

@@ -6,8 +6,8 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ("api.cu", "kernels.cu")
-HEADERS = ("kernels.cuh", "spec.hpp", "json.hpp", os.path.join("..", "..", "include", "pheniqs_b200.h"))
+SOURCES = ("api.cu", "kernels.cu", "pack.cu")
+HEADERS = ("kernels.cuh", "pack.cuh", "spec.hpp", "json.hpp", "report.hpp", os.path.join("..", "..", "include", "pheniqs_b200.h"))
 OUTPUT = os.path.join(HERE, "libpheniqs_b200.so")
 
 

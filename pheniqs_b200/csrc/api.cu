@@ -5,6 +5,7 @@
     File:line citations are relative to the reference tree.
 */
 #include "kernels.cuh"
+#include "pack.cuh"
 #include "spec.hpp"
 #include "report.hpp"
 
@@ -63,6 +64,9 @@ struct StagingSlot {
     std::vector< DeviceBuffer< phq_result > > results;
     DeviceBuffer< uint8_t > qcfail;
     DeviceBuffer< unsigned char > tie_list;  /* queue of the PAMLD tie pass: counter, read indices, records */
+    std::vector< DeviceBuffer< uint8_t > > raw_sequence;    /* feed bytes of phq_decode_batch_raw, per input segment */
+    std::vector< DeviceBuffer< uint8_t > > raw_quality;
+    std::vector< DeviceBuffer< long long > > raw_offset;
 };
 
 constexpr int STAGING_SLOTS = 3;
@@ -96,10 +100,15 @@ struct phq_handle {
     cudaStream_t timing_stream;
     bool timing_valid;
     uint64_t kernel_launches;
+    long long sub_batch_reads;              /* reads per in-flight sub-batch of the host-buffer calls */
     std::string error;
 
     phq_handle() : device(0), device_phred(NULL), device_accumulators(NULL), n_u64(0), n_f64(0), slots_ready(false),
-        timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0) {}
+        timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0), sub_batch_reads(SUB_BATCH_READS) {
+        /* PHQ_SUB_BATCH_READS: smaller sub-batches (tests exercise the boundaries with small inputs) */
+        const char* const value(getenv("PHQ_SUB_BATCH_READS"));
+        if(value != NULL && atoll(value) > 0) { sub_batch_reads = atoll(value); }
+    }
 
     unsigned long long* u64_plane() const { return reinterpret_cast< unsigned long long* >(device_accumulators); }
     double* f64_plane() const { return reinterpret_cast< double* >(device_accumulators + n_u64 * 8); }
@@ -858,7 +867,7 @@ static int decode_host(phq_handle* handle, int64_t n_reads, const phq_tile* tile
         if(n_reads < 0) { throw InternalError("illegal read count"); }
         ensure_slots(h);
         const size_t n_decoders(h->chain.size());
-        const long long sub(n_reads < SUB_BATCH_READS ? (n_reads > 0 ? n_reads : 1) : SUB_BATCH_READS);
+        const long long sub(n_reads < h->sub_batch_reads ? (n_reads > 0 ? n_reads : 1) : h->sub_batch_reads);
         int turn(0);
         for(long long begin(0); begin < n_reads; begin += sub, ++turn) {
             const long long count((n_reads - begin) < sub ? (n_reads - begin) : sub);
@@ -924,6 +933,214 @@ int phq_decode_batch(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
 int phq_decode_batch_compact(phq_handle* handle, int64_t n_reads, const phq_tile* tiles,
                              const uint8_t* qcfail_in, phq_compact_result* const* compact_results) {
     return decode_host(handle, n_reads, tiles, qcfail_in, NULL, compact_results, NULL);
+}
+
+/* ------------------------------------------------------------------ feed bytes in: pack on the device (pack.cuh) */
+namespace {
+
+/* host mirror of the kernel's view of one read of one output segment, for the state the Observation is left in */
+struct RawReader {
+    const DecoderSpec& d;
+    const phq_raw_segment* segments;
+    int32_t phred_offset;
+    int64_t begin(int32_t i, int64_t r) const { return segments[i].offset != NULL ? segments[i].offset[r] : r * segments[i].length; }
+    int32_t length(int32_t i, int64_t r) const { return segments[i].offset != NULL ? static_cast< int32_t >(segments[i].offset[r + 1] - segments[i].offset[r]) : static_cast< int32_t >(segments[i].length); }
+    int32_t observed_length(int64_t r, int32_t s) const {
+        int32_t total(0);
+        for(const auto& t : d.transform) {
+            if(t.output_segment_index != s) { continue; }
+            const int32_t n(length(t.input_segment_index, r));
+            const int32_t size(t.absolute_end(n) - t.absolute_start(n));
+            total += size > 0 ? size : 0;
+        }
+        return total;
+    }
+    void fetch(int64_t r, int32_t s, int32_t i, uint8_t& code, uint8_t& quality) const {
+        int32_t at(0);
+        for(const auto& t : d.transform) {
+            if(t.output_segment_index != s) { continue; }
+            const int32_t n(length(t.input_segment_index, r));
+            const int32_t start(t.absolute_start(n)), end(t.absolute_end(n));
+            const int32_t size(end - start);
+            if(size <= 0) { continue; }
+            if(i < at + size) {
+                const int64_t source(begin(t.input_segment_index, r) + (t.reverse_complement ? (end - (i - at) - 1) : (start + (i - at))));
+                code = ascii_to_bam(segments[t.input_segment_index].sequence[source]);
+                if(t.reverse_complement) { code = BAM_REVERSE_COMPLEMENT[code & 0xf]; }
+                quality = static_cast< uint8_t >(segments[t.input_segment_index].quality[source] - phred_offset);
+                return;
+            }
+            at += size;
+        }
+    }
+    /* the Observation after reads [0, r_last] on top of `scratch` (the state before read 0); r_last = -1 keeps scratch */
+    void state_after(int64_t r_last, const std::vector< ScratchSegment >& scratch, uint8_t* code, uint8_t* quality) const {
+        for(int32_t s(0); s < d.segment_cardinality; ++s) {
+            for(int32_t i(0); i < d.segment_length[s]; ++i) {
+                const int32_t j(d.segment_offset[s] + i);
+                code[j] = scratch[s].code[i];
+                quality[j] = scratch[s].quality[i];
+                for(int64_t r(r_last); r >= 0; --r) {
+                    const int32_t reach(observed_length(r, s));
+                    if(reach == i) { code[j] = 0; quality[j] = 0; break; }
+                    if(reach > i) { fetch(r, s, i, code[j], quality[j]); break; }
+                }
+            }
+        }
+    }
+};
+
+int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
+               const uint8_t* qcfail_in, phq_result* const* results, phq_compact_result* const* compact, uint8_t* qcfail_out) {
+    return guarded(handle, [&]() {
+        phq_handle* h(handle);
+        if(n_reads < 0 || n_input_segments < 0 || (n_input_segments > 0 && segments == NULL)) { throw InternalError("illegal argument"); }
+        if(n_input_segments > PACK_MAX_INPUT_SEGMENTS) { throw ConfigurationError("more than " + std::to_string(PACK_MAX_INPUT_SEGMENTS) + " input segments are not supported on this path"); }
+        ensure_slots(h);
+        const size_t n_decoders(h->chain.size());
+        std::vector< bool > used(static_cast< size_t >(n_input_segments), false);
+        for(size_t k(0); k < n_decoders; ++k) {
+            const DecoderSpec& d(h->chain[k]);
+            if(!d.tiled()) { continue; }
+            if(d.transform.size() > static_cast< size_t >(PACK_MAX_TOKENS)) { throw ConfigurationError("more than " + std::to_string(PACK_MAX_TOKENS) + " tokens per decoder are not supported on this path"); }
+            for(const auto& t : d.transform) {
+                if(t.input_segment_index >= n_input_segments) {
+                    throw ConfigurationError("invalid input feed reference " + std::to_string(t.input_segment_index) + " in token " + std::to_string(t.token_index));
+                }
+                used[static_cast< size_t >(t.input_segment_index)] = true;
+            }
+        }
+        for(int32_t i(0); i < n_input_segments; ++i) {
+            if(used[i] && (segments[i].sequence == NULL || segments[i].quality == NULL || (segments[i].offset == NULL && segments[i].length < 0))) {
+                throw InternalError("input segment " + std::to_string(i) + " has no bytes");
+            }
+        }
+        const long long sub(n_reads < h->sub_batch_reads ? (n_reads > 0 ? n_reads : 1) : h->sub_batch_reads);
+        int turn(0);
+        for(long long begin(0); begin < n_reads; begin += sub, ++turn) {
+            const long long count((n_reads - begin) < sub ? (n_reads - begin) : sub);
+            StagingSlot& s(h->slot[turn % STAGING_SLOTS]);
+            if(turn >= STAGING_SLOTS) { PHQ_CUDA(cudaEventSynchronize(s.done)); }
+            s.raw_sequence.resize(static_cast< size_t >(n_input_segments));
+            s.raw_quality.resize(static_cast< size_t >(n_input_segments));
+            s.raw_offset.resize(static_cast< size_t >(n_input_segments));
+            s.qcfail.reserve(static_cast< size_t >(sub));
+            if(qcfail_in != NULL) { PHQ_CUDA(cudaMemcpyAsync(s.qcfail.pointer, qcfail_in + begin, static_cast< size_t >(count), cudaMemcpyHostToDevice, s.stream)); }
+            else { PHQ_CUDA(cudaMemsetAsync(s.qcfail.pointer, 0, static_cast< size_t >(count), s.stream)); }
+
+            /* the bytes of this sub-batch's reads, as they sit in the feed buffers */
+            RawSegmentView view[PACK_MAX_INPUT_SEGMENTS];
+            memset(view, 0, sizeof(view));
+            for(int32_t i(0); i < n_input_segments; ++i) {
+                if(!used[i]) { continue; }
+                const phq_raw_segment& g(segments[i]);
+                const int64_t first_byte(g.offset != NULL ? g.offset[begin] : begin * g.length);
+                const int64_t last_byte(g.offset != NULL ? g.offset[begin + count] : (begin + count) * g.length);
+                const size_t bytes(static_cast< size_t >(last_byte - first_byte));
+                s.raw_sequence[i].reserve(bytes ? bytes : 1);
+                s.raw_quality[i].reserve(bytes ? bytes : 1);
+                if(bytes) {
+                    PHQ_CUDA(cudaMemcpyAsync(s.raw_sequence[i].pointer, g.sequence + first_byte, bytes, cudaMemcpyHostToDevice, s.stream));
+                    PHQ_CUDA(cudaMemcpyAsync(s.raw_quality[i].pointer, g.quality + first_byte, bytes, cudaMemcpyHostToDevice, s.stream));
+                }
+                view[i].sequence = s.raw_sequence[i].pointer - first_byte;
+                view[i].quality = s.raw_quality[i].pointer - first_byte;
+                view[i].length = g.length;
+                view[i].first = 0;
+                if(g.offset != NULL) {
+                    s.raw_offset[i].reserve(static_cast< size_t >(sub) + 1);
+                    PHQ_CUDA(cudaMemcpyAsync(s.raw_offset[i].pointer, g.offset + begin, static_cast< size_t >(count + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+                    view[i].offset = s.raw_offset[i].pointer;
+                } else {
+                    view[i].first = begin;      /* r * length is absolute like the offsets */
+                }
+            }
+
+            std::vector< phq_tile > device_tiles(n_decoders);
+            std::vector< phq_result* > device_results(n_decoders, static_cast< phq_result* >(NULL));
+            std::vector< phq_compact_result* > device_compact(n_decoders, static_cast< phq_compact_result* >(NULL));
+            for(size_t k(0); k < n_decoders; ++k) {
+                const DecoderSpec& d(h->chain[k]);
+                memset(&device_tiles[k], 0, sizeof(phq_tile));
+                if(d.tiled()) {
+                    s.bases[k].reserve(static_cast< size_t >(sub) * d.word_cardinality());
+                    s.nmask[k].reserve(static_cast< size_t >(sub) * d.word_cardinality());
+                    s.quality[k].reserve(static_cast< size_t >(sub) * d.quality_word_cardinality());
+                    PackPlan plan;
+                    memset(&plan, 0, sizeof(plan));
+                    plan.token_cardinality = static_cast< int32_t >(d.transform.size());
+                    plan.segment_cardinality = d.segment_cardinality;
+                    plan.nucleotide_cardinality = d.nucleotide_cardinality;
+                    plan.stale_semantics = d.algorithm == PHQ_PAMLD ? 1 : 0;
+                    plan.phred_offset = phred_offset;
+                    for(int32_t i(0); i <= d.segment_cardinality; ++i) { plan.segment_offset[i] = d.segment_offset[i]; }
+                    for(size_t i(0); i < d.transform.size(); ++i) {
+                        const TransformSpec& t(d.transform[i]);
+                        PackToken& to(plan.token[i]);
+                        to.input_segment = t.input_segment_index; to.start = t.start; to.end = t.end; to.end_terminated = t.end_terminated ? 1 : 0;
+                        to.output_segment = t.output_segment_index; to.reverse_complement = t.reverse_complement ? 1 : 0;
+                    }
+                    memcpy(plan.input, view, sizeof(view));
+                    /* the kernel indexes reads from 0: move the views to this sub-batch */
+                    for(int32_t i(0); i < n_input_segments; ++i) { if(plan.input[i].offset == NULL) { plan.input[i].first = begin; } }
+                    if(plan.stale_semantics) {
+                        const RawReader reader{ d, segments, phred_offset };
+                        reader.state_after(begin - 1, h->scratch[k], plan.carry_code, plan.carry_quality);
+                    }
+                    PHQ_CUDA(launch_pack(plan, count, s.bases[k].pointer, s.nmask[k].pointer, s.quality[k].pointer, sub, h->geometry.multiprocessor_count, s.stream));
+                    h->kernel_launches += 1;
+                    device_tiles[k].bases = s.bases[k].pointer;
+                    device_tiles[k].nmask = s.nmask[k].pointer;
+                    device_tiles[k].quality = s.quality[k].pointer;
+                    device_tiles[k].pitch = sub;
+                    device_tiles[k].quality_bits = 8;
+                }
+                const bool wanted((results != NULL && results[k] != NULL) || (compact != NULL && compact[k] != NULL));
+                if(wanted) {
+                    s.results[k].reserve(static_cast< size_t >(sub));
+                    if(compact != NULL) { device_compact[k] = reinterpret_cast< phq_compact_result* >(s.results[k].pointer); }
+                    else { device_results[k] = s.results[k].pointer; }
+                }
+            }
+            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, compact != NULL ? NULL : device_results.data(), compact != NULL ? device_compact.data() : NULL, s.tie_list, s.stream);
+            for(size_t k(0); k < n_decoders; ++k) {
+                if(device_results[k] != NULL) {
+                    PHQ_CUDA(cudaMemcpyAsync(results[k] + begin, device_results[k], static_cast< size_t >(count) * sizeof(phq_result), cudaMemcpyDeviceToHost, s.stream));
+                }
+                if(device_compact[k] != NULL) {
+                    PHQ_CUDA(cudaMemcpyAsync(compact[k] + begin, device_compact[k], static_cast< size_t >(count) * sizeof(phq_compact_result), cudaMemcpyDeviceToHost, s.stream));
+                }
+            }
+            if(qcfail_out != NULL) { PHQ_CUDA(cudaMemcpyAsync(qcfail_out + begin, s.qcfail.pointer, static_cast< size_t >(count), cudaMemcpyDeviceToHost, s.stream)); }
+            PHQ_CUDA(cudaEventRecord(s.done, s.stream));
+        }
+        /* leave the Observations as a single reference thread would: later calls (raw or phq_pack) continue from here */
+        for(size_t k(0); k < n_decoders && n_reads > 0; ++k) {
+            const DecoderSpec& d(h->chain[k]);
+            if(!d.tiled() || d.algorithm != PHQ_PAMLD) { continue; }
+            uint8_t code[PHQ_MAX_NUCLEOTIDES], quality[PHQ_MAX_NUCLEOTIDES];
+            const RawReader reader{ d, segments, phred_offset };
+            reader.state_after(n_reads - 1, h->scratch[k], code, quality);
+            for(int32_t sgm(0); sgm < d.segment_cardinality; ++sgm) {
+                for(int32_t i(0); i < d.segment_length[sgm]; ++i) {
+                    h->scratch[k][sgm].code[i] = code[d.segment_offset[sgm] + i];
+                    h->scratch[k][sgm].quality[i] = quality[d.segment_offset[sgm] + i];
+                }
+            }
+        }
+        for(int i(0); i < STAGING_SLOTS && i < turn; ++i) { PHQ_CUDA(cudaStreamSynchronize(h->slot[i].stream)); }
+    });
+}
+
+}   /* namespace */
+
+int phq_decode_batch_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
+                         const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out) {
+    return decode_raw(handle, n_reads, n_input_segments, segments, phred_offset, qcfail_in, results, NULL, qcfail_out);
+}
+int phq_decode_batch_raw_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
+                                 const uint8_t* qcfail_in, phq_compact_result* const* compact_results) {
+    return decode_raw(handle, n_reads, n_input_segments, segments, phred_offset, qcfail_in, NULL, compact_results, NULL);
 }
 
 int phq_host_alloc(void** pointer, size_t bytes) {

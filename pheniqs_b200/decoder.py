@@ -17,7 +17,7 @@ import json
 import numpy as np
 
 from . import binding
-from .binding import DecoderInfo, Tile, check, library
+from .binding import DecoderInfo, RawSegment, Tile, check, library
 
 RESULT_DTYPE = np.dtype([("index", np.int32), ("distance", np.int32), ("confidence", np.float64)])
 COMPACT_DTYPE = np.dtype([("packed", np.uint32), ("error_probability", np.float32)])
@@ -210,6 +210,37 @@ class DecoderChain:
         qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
         check(self.lib.phq_decode_batch_compact(self.handle, n_reads, self._tile_array(tiles), None if qin is None else qin.ctypes.data, pointers), self.handle)
         return results
+
+    def decode_raw(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, compact: bool = False, results=None, qcfail_out=None):
+        """phq_decode_batch_raw[_compact]: the bytes of the FASTQ records in, packing on the device.
+
+        segments[i] = (sequence uint8 [bytes], quality uint8 [bytes], offset int64 [n_reads + 1] or None, length) or None
+        for an input segment no token refers to."""
+        array = (RawSegment * max(len(segments), 1))()
+        keep = []
+        for i, g in enumerate(segments):
+            if g is None:
+                continue
+            sequence, quality, offset, length = g
+            sequence = np.ascontiguousarray(sequence, dtype=np.uint8)
+            quality = np.ascontiguousarray(quality, dtype=np.uint8)
+            offset = None if offset is None else np.ascontiguousarray(offset, dtype=np.int64)
+            keep.append((sequence, quality, offset))
+            array[i] = RawSegment(sequence.ctypes.data, quality.ctypes.data, None if offset is None else offset.ctypes.data, int(length))
+        if results is None:
+            dtype = COMPACT_DTYPE if compact else RESULT_DTYPE
+            results = [np.zeros(n_reads, dtype=dtype) if (info.has_tile or not compact) else None for info in self.info]
+        pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
+        qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
+        if compact:
+            check(self.lib.phq_decode_batch_raw_compact(self.handle, n_reads, len(segments), array, phred_offset,
+                                                        None if qin is None else qin.ctypes.data, pointers), self.handle)
+            return results
+        if qcfail_out is None:
+            qcfail_out = np.zeros(n_reads, dtype=np.uint8)
+        check(self.lib.phq_decode_batch_raw(self.handle, n_reads, len(segments), array, phred_offset,
+                                            None if qin is None else qin.ctypes.data, pointers, qcfail_out.ctypes.data), self.handle)
+        return results, qcfail_out
 
     def decode_device(self, device_tiles, n_reads: int, qcfail, results=None, stream=None):
         """Same over device-resident torch tensors; asynchronous on `stream` (phq_decode_batch_device).
