@@ -383,7 +383,25 @@ def main():
             line["e2e_full"] = e2e_full
         else:
             line["e2e"] = e2e_full
-        del host_tiles, full_results, keep
+        # e2e_raw: the bytes of the FASTQ records in (ASCII nucleotides and qualities of the barcode-bearing segments,
+        # pinned), packing on the device (phq_decode_batch_raw_compact): the host does no per-read work at all
+        raw = workload.raw_segments_from_device_tiles(chain, compiled, tiles, m) if lossless else None
+        if raw is not None:
+            segments = [None if g is None else g[:4] for g in raw]
+            raw_results = []
+            for info in chain.info:
+                if info.has_tile:
+                    buffer = torch.zeros(m, dtype=torch.float64).pin_memory()
+                    keep.append(buffer)
+                    raw_results.append(buffer.numpy().view(COMPACT_DTYPE).reshape(-1))
+                else:
+                    raw_results.append(None)
+            raw_value = time_host(lambda: chain.decode_raw(segments, m, 33, None, compact=True, results=raw_results))
+            assert all(a is None or np.array_equal(a["packed"], b["packed"]) for a, b in zip(raw_results, compact_results))
+            line["e2e_raw"] = {"value": raw_value, "unit": UNIT, "h2d_bytes_per_step": int(sum(2 * g[3] * m for g in raw if g is not None)), "d2h_bytes_per_step": int(d2h),
+                               "reads_per_gpu_per_step": m, "steps": e2e_steps,
+                               "call": "phq_decode_batch_raw_compact (FASTQ bytes of the barcode segments in, packed on the device; 8-byte records out)"}
+        del host_tiles, full_results, keep, raw
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         baseline, _, _ = time_cpu(compiled, spec)
