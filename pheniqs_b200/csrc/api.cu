@@ -83,6 +83,9 @@ struct phq_handle {
     std::vector< BarcodeEntry* > device_barcodes;
     std::vector< MddSlot* > device_mdd;        /* MDD lookup tables (kernels.cuh), NULL where the scan kernel is used */
     std::vector< std::vector< int32_t > > mdd_shape;    /* per decoder: first slot and mask of every table, total slots */
+    std::vector< unsigned char* > device_whitelist;    /* chunked whitelist blobs (kernels.cuh), NULL where not applicable */
+    std::vector< int32_t > whitelist_chunks;
+    std::vector< double > prior_maximum;
     std::vector< void* > device_grid;          /* combinatorial codec blobs (kernels.cuh), NULL where not applicable */
     std::vector< int32_t > grid_shape;         /* per decoder: grid_a, grid_b, grid_entries, grid_split, grid_dense, grid_uniform */
     double* device_phred;
@@ -258,6 +261,51 @@ void upload_grid(phq_handle* h, size_t k) {
     h->grid_shape[k * 6 + 5] = uniform ? 1 : 0;
 }
 
+/*  Large single-word codecs (a cellular whitelist): the chunked blob pamld_whitelist_kernel streams — per chunk of
+    WHITELIST_CHUNK barcodes the equality planes of its blocks of 32, the barcode words and the priors (kernels.cuh). */
+void upload_whitelist(phq_handle* h, size_t k) {
+    const DecoderSpec& d(h->chain[k]);
+    if(h->device_whitelist[k] != NULL) { cudaFree(h->device_whitelist[k]); h->device_whitelist[k] = NULL; }
+    h->whitelist_chunks[k] = 0;
+    h->prior_maximum[k] = 0;
+    long long minimum(WHITELIST_MINIMUM_BARCODES);
+    const char* const value(getenv("PHQ_WHITELIST_MINIMUM"));
+    if(value != NULL && atoll(value) > 0) { minimum = atoll(value); }
+    if(d.algorithm != PHQ_PAMLD || d.nucleotide_cardinality > WHITELIST_POSITIONS || d.barcode_cardinality < minimum) { return; }
+    const int32_t L(d.nucleotide_cardinality);
+    const size_t chunks((static_cast< size_t >(d.barcode_cardinality) + WHITELIST_CHUNK - 1) / WHITELIST_CHUNK);
+    std::vector< unsigned char > blob(chunks * WHITELIST_CHUNK_BYTES, 0);
+    double largest(0);
+    for(size_t c(0); c < chunks; ++c) {
+        uint32_t* const equality(reinterpret_cast< uint32_t* >(blob.data() + c * WHITELIST_CHUNK_BYTES));
+        uint32_t* const word(equality + WHITELIST_EQUALITY_WORDS);
+        double* const prior(reinterpret_cast< double* >(word + 2 * WHITELIST_CHUNK));
+        for(int32_t block(0); block < WHITELIST_BLOCKS; ++block) {
+            for(int32_t j(0); j < WHITELIST_POSITIONS; ++j) { equality[(block * WHITELIST_POSITIONS + j) * WHITELIST_PLANES + 4] = 0xffffffffu; }
+        }
+        for(int32_t i(0); i < WHITELIST_CHUNK; ++i) {
+            const size_t b(c * WHITELIST_CHUNK + static_cast< size_t >(i));
+            if(b >= static_cast< size_t >(d.barcode_cardinality)) { break; }      /* padding: no plane bit, prior 0 */
+            uint32_t lo(0), hi(0);
+            for(int32_t j(0); j < L; ++j) {
+                const uint8_t code(d.barcode[b * L + j]);
+                const uint32_t two(code == 1 ? 0u : code == 2 ? 1u : code == 4 ? 2u : 3u);
+                lo |= (two & 1u) << j;
+                hi |= (two >> 1) << j;
+                equality[((i >> 5) * WHITELIST_POSITIONS + j) * WHITELIST_PLANES + two] |= 1u << (i & 31);
+            }
+            word[2 * i] = lo;
+            word[2 * i + 1] = hi;
+            prior[i] = d.concentration[b];
+            if(d.concentration[b] > largest) { largest = d.concentration[b]; }
+        }
+    }
+    PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_whitelist[k]), blob.size()));
+    PHQ_CUDA(cudaMemcpy(h->device_whitelist[k], blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    h->whitelist_chunks[k] = static_cast< int32_t >(chunks);
+    h->prior_maximum[k] = largest;
+}
+
 /*  MDD lookup tables (MddSlot, kernels.cuh). Built when the reference's scan is provably a lookup: every segment
     is at most 16 nucleotides, at most four segments, and every tolerance is within the segment's Shannon bound
     (metric.h:87-111), so the spheres of radius `tolerance` around the distinct words of a segment are disjoint. */
@@ -427,6 +475,9 @@ void refresh_params(phq_handle* h, size_t k) {
         for(int32_t t(0); t <= d.segment_cardinality; ++t) { p.mdd_first[t] = shape[2 * t]; p.mdd_mask[t] = shape[2 * t + 1]; }
         p.mdd_slots = shape.back();
     }
+    p.whitelist = h->device_whitelist[k];
+    p.whitelist_chunks = h->whitelist_chunks[k];
+    p.prior_maximum = h->prior_maximum[k];
     p.grid = h->device_grid[k];
     p.grid_a = h->grid_shape[k * 6 + 0];
     p.grid_b = h->grid_shape[k * 6 + 1];
@@ -442,6 +493,7 @@ void destroy(phq_handle* h) {
     cudaSetDevice(h->device);
     for(auto* p : h->device_barcodes) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_grid) { if(p != NULL) { cudaFree(p); } }
+    for(auto* p : h->device_whitelist) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_mdd) { if(p != NULL) { cudaFree(p); } }
     if(h->device_phred != NULL) { cudaFree(h->device_phred); }
     if(h->device_accumulators != NULL) { cudaFree(h->device_accumulators); }
@@ -639,6 +691,9 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         h->params.resize(n);
         h->device_barcodes.assign(n, NULL);
         h->device_grid.assign(n, NULL);
+        h->device_whitelist.assign(n, NULL);
+        h->whitelist_chunks.assign(n, 0);
+        h->prior_maximum.assign(n, 0.0);
         h->device_mdd.assign(n, NULL);
         h->mdd_shape.assign(n, std::vector< int32_t >());
         h->grid_shape.assign(n * 6, 0);
@@ -669,6 +724,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
                 PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), static_cast< size_t >(chain[k].barcode_cardinality) * sizeof(BarcodeEntry)));
                 upload_barcodes(h, k);
                 upload_grid(h, k);
+                upload_whitelist(h, k);
                 upload_mdd_tables(h, k);
             }
             refresh_params(h, k);
@@ -1241,6 +1297,7 @@ int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* 
         PHQ_CUDA(cudaDeviceSynchronize());
         upload_barcodes(handle, static_cast< size_t >(decoder));
         upload_grid(handle, static_cast< size_t >(decoder));
+        upload_whitelist(handle, static_cast< size_t >(decoder));
         refresh_params(handle, static_cast< size_t >(decoder));
     });
 }

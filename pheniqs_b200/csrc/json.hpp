@@ -18,6 +18,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -59,17 +60,17 @@ class Json {
         const std::vector< Json >& items() const { expect(Array, "array"); return items_; }
         std::vector< Json >& items() { expect(Array, "array"); return items_; }
         const std::vector< Member >& members() const { expect(Object, "object"); return members_; }
-        std::vector< Member >& members() { expect(Object, "object"); return members_; }
+        std::vector< Member >& members() { expect(Object, "object"); index_.reset(); return members_; }
 
         const Json* find(const std::string& key) const {
             if(type_ != Object) { return NULL; }
-            for(const auto& m : members_) { if(m.first == key) { return &m.second; } }
-            return NULL;
+            const long at(position(key));
+            return at < 0 ? NULL : &members_[static_cast< size_t >(at)].second;
         }
         Json* find(const std::string& key) {
             if(type_ != Object) { return NULL; }
-            for(auto& m : members_) { if(m.first == key) { return &m.second; } }
-            return NULL;
+            const long at(position(key));
+            return at < 0 ? NULL : &members_[static_cast< size_t >(at)].second;
         }
         bool has(const std::string& key) const { const Json* v(find(key)); return v != NULL && !v->is_null(); }
         const Json& at(const std::string& key) const {
@@ -80,11 +81,14 @@ class Json {
         /* replace or append, like encode_key_value (RemoveMember + AddMember) */
         void set(const std::string& key, const Json& value) {
             expect(Object, "object");
-            for(auto& m : members_) { if(m.first == key) { m.second = value; return; } }
+            const long at(position(key));
+            if(at >= 0) { members_[static_cast< size_t >(at)].second = value; return; }
             members_.emplace_back(key, value);
+            if(index_.ready) { index_.map.emplace(key, members_.size() - 1); }
         }
         void erase(const std::string& key) {
             expect(Object, "object");
+            index_.reset();
             members_.erase(std::remove_if(members_.begin(), members_.end(), [&](const Member& m) { return m.first == key; }), members_.end());
         }
         void push(const Json& value) { expect(Array, "array"); items_.push_back(value); }
@@ -93,6 +97,7 @@ class Json {
         void sort_keys() {
             if(type_ == Object) {
                 for(auto& m : members_) { m.second.sort_keys(); }
+                index_.reset();
                 std::stable_sort(members_.begin(), members_.end(), [](const Member& a, const Member& b) { return a.first < b.first; });
             } else if(type_ == Array) {
                 for(auto& e : items_) { e.sort_keys(); }
@@ -120,6 +125,31 @@ class Json {
         std::string string_;
         std::vector< Json > items_;
         std::vector< Member > members_;
+        /* key -> position, built on the first lookup of a large object (a 737 K barcode codec is one object) and
+           never copied with the value */
+        struct KeyIndex {
+            std::unordered_map< std::string, size_t > map;
+            bool ready;
+            KeyIndex() : ready(false) {}
+            KeyIndex(const KeyIndex&) : ready(false) {}
+            KeyIndex& operator=(const KeyIndex&) { reset(); return *this; }
+            void reset() { if(ready) { map.clear(); ready = false; } }
+        };
+        mutable KeyIndex index_;
+        long position(const std::string& key) const {
+            if(members_.size() < 32) {
+                for(size_t i(0); i < members_.size(); ++i) { if(members_[i].first == key) { return static_cast< long >(i); } }
+                return -1;
+            }
+            if(!index_.ready) {
+                index_.map.clear();
+                index_.map.reserve(members_.size() * 2);
+                for(size_t i(0); i < members_.size(); ++i) { index_.map.emplace(members_[i].first, i); }     /* first occurrence wins */
+                index_.ready = true;
+            }
+            const auto found(index_.map.find(key));
+            return found == index_.map.end() ? -1 : static_cast< long >(found->second);
+        }
 
         void expect(Type t, const char* name) const {
             if(type_ != t) { throw JsonError(std::string("expected a JSON ") + name); }

@@ -952,6 +952,350 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
     block_epilogue(S, P);
 }
 
+/* ------------------------------------------------------------------ PAMLD scan for large whitelists
+   A cellular whitelist (C5: 737,280 x 16 nt) is three to four orders of magnitude larger than a sample codec,
+   and almost every (read, barcode) pair contributes nothing that survives rounding: a barcode with c
+   mismatches at confidently called positions has p_b <= prior_max * (product of the c largest mismatch
+   ratios of the read). The kernel therefore splits the scan:
+
+     fast path   32 barcodes per step and lane, bit sliced. The table holds, per block of 32 barcodes,
+                 position and base, the word of barcodes that have that base there (equality planes). A lane
+                 loads the 16 planes its read selects (5 distinct addresses per request: conflict free), adds
+                 them with a carry-save adder tree of 26 LOP3 (vertical counters) whose carry-in bits hold the
+                 lane's current limit, and the carry out of the tree is the word of barcodes with at most
+                 `limit` counted mismatches. About 45 instructions per 32 x 32 pairs.
+     exact path  every barcode of that word is evaluated exactly like pamld_kernel does (mismatch mask, subset
+                 product tables, prior, first-maximum selection, tie detection), in index order.
+
+   `limit` is the largest count c whose bound can still matter: bound[c] >= min(best / 2,
+   tolerance * (noise term + rest) / N). Everything below best / 2 cannot be the maximum or a tie; the N
+   barcodes together cannot add more than `tolerance` (2^-24) of the part of sigma_p that is not the winner, so
+   confidence and 1 - confidence move by less than 6e-8 relative, a sixteenth of the 1e-6 the path allows.
+   The bound only ever tightens (best and rest grow), so a stale limit is conservative. Positions that do not
+   discriminate (N, quality 0, ratios >= 1 i.e. Phred < 3, positions past the barcode) are not counted: they
+   select the all-ones plane, and ratios above 1 are folded into the bound. */
+constexpr int WHITELIST_WARPS = 12;
+constexpr int WHITELIST_GROUP = 4;              /* blocks of 32 barcodes per trip of the fast path: one vote and branch */
+constexpr double WHITELIST_TOLERANCE = 5.9604644775390625e-08;     /* 2^-24 */
+
+__host__ __device__ inline unsigned whitelist_fixed_bytes() {
+    /* two stage buffers, Phred tables, 4 counters, 2 mbarriers; then 4 KB of slack for the table alignment */
+    return align_up(2u * WHITELIST_CHUNK_BYTES + 256u * 8u + 16u + 16u, 256u) + 4096u;
+}
+
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));        /* a ^ b ^ c */
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));      /* majority */
+}
+__device__ __forceinline__ uint32_t majority(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t carry;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));
+    return carry;
+}
+/*  Bit k of the result is set when (number of the 16 words with bit k set) + bias >= 16, bias = b0 + 2 b1 + 4 b2
+    + 8 b3 given as all-zero / all-one words: a carry-save adder tree over vertical counters, 15 adders, 26 LOP3
+    (the low sum bit of every weight is never formed). */
+__device__ __forceinline__ uint32_t count_reaches_sixteen(const uint32_t (&e)[16], uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    uint32_t s0, s1, s2, s3, s4, t0, t1, c0, c1, c2, c3, c4, c5, c6;
+    full_add(e[0], e[1], e[2], s0, c0);
+    full_add(e[3], e[4], e[5], s1, c1);
+    full_add(e[6], e[7], e[8], s2, c2);
+    full_add(e[9], e[10], e[11], s3, c3);
+    full_add(e[12], e[13], e[14], s4, c4);
+    full_add(s0, s1, s2, t0, c5);
+    full_add(s3, s4, e[15], t1, c6);
+    const uint32_t c7 = majority(t0, t1, b0);
+    uint32_t u0, u1, u2, d0, d1, d2;
+    full_add(c0, c1, c2, u0, d0);
+    full_add(c3, c4, c5, u1, d1);
+    full_add(c6, c7, b1, u2, d2);
+    const uint32_t d3 = majority(u0, u1, u2);
+    uint32_t v0, f0;
+    full_add(d0, d1, d2, v0, f0);
+    const uint32_t f1 = majority(v0, d3, b2);
+    return majority(f0, f1, b3);
+}
+
+/* block U of the current group: the 16 planes this lane selects (immediate offsets from its cursors), then the count */
+template < int U >
+__device__ __forceinline__ uint32_t whitelist_block(const uint32_t (&cursor)[WHITELIST_POSITIONS], uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    uint32_t e[WHITELIST_POSITIONS];
+    #pragma unroll
+    for(int j = 0; j < WHITELIST_POSITIONS; ++j) {
+        asm volatile("ld.shared.u32 %0, [%1 + %2];" : "=r"(e[j]) : "r"(cursor[j]), "n"(U * WHITELIST_POSITIONS * WHITELIST_PLANES * 4));
+    }
+    return count_reaches_sixteen(e, b0, b1, b2, b3);
+}
+
+__global__ void __launch_bounds__(WHITELIST_WARPS * WARP_SIZE, 1)
+pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
+    constexpr int G = 4;
+    extern __shared__ __align__(256) unsigned char smem[];
+    unsigned char* const stage = smem;
+    double* const phred = reinterpret_cast< double* >(smem + 2 * WHITELIST_CHUNK_BYTES);
+    uint32_t* const misc = reinterpret_cast< uint32_t* >(phred + 256);
+    uint64_t* const mbarrier = reinterpret_cast< uint64_t* >(misc + 4);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    for(int i = tid; i < 256; i += blockDim.x) { phred[i] = P.phred[i]; }
+    if(tid < 4) { misc[tid] = 0; }
+    if(tid == 0) {
+        mbarrier_init(&mbarrier[0], 1);
+        mbarrier_init(&mbarrier[1], 1);
+        fence_mbarrier_init();
+    }
+    __syncthreads();
+    Accumulator accumulator;
+    accumulator.shared_u32 = nullptr; accumulator.shared_f64 = nullptr;
+    accumulator.global_u64 = P.acc_u64; accumulator.global_f64 = P.acc_f64;
+
+    const uint32_t window = shared_address(smem);
+    const uint32_t aligned_tables = ((window + whitelist_fixed_bytes() - 4096u + 4095u) & ~4095u) - window;
+    double* const table = reinterpret_cast< double* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE) + lane;
+    const uint32_t table_base = shared_address(table);
+    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
+    const int L = P.nucleotide_cardinality;
+    const int chunk_cardinality = P.whitelist_chunks;
+    const double tolerance_per_barcode = WHITELIST_TOLERANCE / static_cast< double >(P.barcode_cardinality);
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * chunk_cardinality;
+    unsigned iteration = 0;
+    auto issue = [&](unsigned it) {
+        const unsigned buffer = chunk_cardinality == 1 ? 0u : (it & 1u);
+        const unsigned chunk = it % static_cast< unsigned >(chunk_cardinality);
+        mbarrier_expect_tx(&mbarrier[buffer], WHITELIST_CHUNK_BYTES);
+        tma_bulk_load(stage + buffer * WHITELIST_CHUNK_BYTES, P.whitelist + static_cast< size_t >(chunk) * WHITELIST_CHUNK_BYTES, WHITELIST_CHUNK_BYTES, &mbarrier[buffer]);
+    };
+    if(tid == 0 && total_iterations > 0) { issue(0); }
+    const bool resident = chunk_cardinality == 1;
+    if(resident && total_iterations > 0) { mbarrier_wait(&mbarrier[0], 0); }
+
+    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+        const ObservedRead< G > observed = upcoming;
+        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
+        uint32_t qcfail = observed.qcfail;
+        uint32_t quality[G];
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
+
+        /* ---- per-read constant P0, subset product tables, high quality mask; the plane every position selects */
+        double base_probability = 1.0;
+        uint32_t high_quality_mask = 0;
+        int uniform_positions = 0;
+        uint32_t plane[WHITELIST_POSITIONS];        /* word offset of the lane's plane inside a block */
+        double counted_ratio[WHITELIST_POSITIONS];  /* the ratio of a counted position, 2 (above every ratio that counts) otherwise */
+        double loose = 1.0;                         /* product of the ratios above 1 */
+        #pragma unroll
+        for(int g = 0; g < G; ++g) {
+            double w[4];
+            #pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                const int j = g * 4 + k;
+                const uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
+                if(static_cast< int >(q) >= P.high_quality_threshold) { high_quality_mask |= 1u << j; }
+                const bool ambiguous = (nmask >> j) & 1u;
+                const PositionFactor f = position_factor(phred, uniform_factor, q, ambiguous);
+                uniform_positions += f.uniform ? 1 : 0;
+                base_probability *= f.factor;
+                w[k] = f.ratio;
+                const bool counted = valid && !ambiguous && j < L && f.ratio < 1.0;
+                const uint32_t code = ((o_lo >> j) & 1u) | (((o_hi >> j) & 1u) << 1);
+                plane[j] = static_cast< uint32_t >(j * WHITELIST_PLANES) + (counted ? code : 4u);
+                counted_ratio[j] = counted ? f.ratio : 2.0;
+                if(f.ratio > 1.0) { loose *= f.ratio; }
+            }
+            double* const t = table + g * 16 * WARP_SIZE;
+            const double w01 = w[0] * w[1];
+            const double w02 = w[0] * w[2];
+            const double w12 = w[1] * w[2];
+            const double w012 = w01 * w[2];
+            t[0 * WARP_SIZE] = 1.0;
+            t[1 * WARP_SIZE] = w[0];
+            t[2 * WARP_SIZE] = w[1];
+            t[3 * WARP_SIZE] = w01;
+            t[4 * WARP_SIZE] = w[2];
+            t[5 * WARP_SIZE] = w02;
+            t[6 * WARP_SIZE] = w12;
+            t[7 * WARP_SIZE] = w012;
+            t[8 * WARP_SIZE] = w[3];
+            t[9 * WARP_SIZE] = w[0] * w[3];
+            t[10 * WARP_SIZE] = w[1] * w[3];
+            t[11 * WARP_SIZE] = w01 * w[3];
+            t[12 * WARP_SIZE] = w[2] * w[3];
+            t[13 * WARP_SIZE] = w02 * w[3];
+            t[14 * WARP_SIZE] = w12 * w[3];
+            t[15 * WARP_SIZE] = w012 * w[3];
+        }
+        high_quality_mask &= (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+
+        /* ---- bound[c]: no barcode with c counted mismatches has a prior adjusted product above it. The
+           counted ratios in descending order by rank (ties by position), then the running product; the
+           factor 1 + 2^-20 covers the rounding of the products on either side. */
+        double bound[WHITELIST_POSITIONS + 1];
+        int counted_positions = 0;
+        {
+            double sorted[WHITELIST_POSITIONS];
+            #pragma unroll
+            for(int j = 0; j < WHITELIST_POSITIONS; ++j) { sorted[j] = 0.0; }
+            #pragma unroll
+            for(int j = 0; j < WHITELIST_POSITIONS; ++j) {
+                if(counted_ratio[j] < 1.0) {
+                    int rank = 0;
+                    #pragma unroll
+                    for(int i = 0; i < WHITELIST_POSITIONS; ++i) {
+                        if(counted_ratio[i] < 1.0 && (counted_ratio[i] > counted_ratio[j] || (counted_ratio[i] == counted_ratio[j] && i < j))) { ++rank; }
+                    }
+                    sorted[rank] = counted_ratio[j];
+                    ++counted_positions;
+                }
+            }
+            double running = P.prior_maximum * loose * (1.0 + 9.5367431640625e-07);
+            bound[0] = running;
+            for(int c = 1; c <= WHITELIST_POSITIONS; ++c) {
+                running *= sorted[c - 1];           /* 0 beyond the counted positions: such counts do not occur */
+                bound[c] = running;
+            }
+        }
+        uint32_t plane_address[WHITELIST_POSITIONS];
+        #pragma unroll
+        for(int j = 0; j < WHITELIST_POSITIONS; ++j) { plane_address[j] = window + plane[j] * 4u; }
+        int limit = counted_positions;
+        double limit_bound = bound[limit];
+        double threshold = 0.0;                     /* min(best / 2, tolerance share of the rest of sigma_p): only ever grows */
+        const double noise_term = P.adjusted_noise_probability / base_probability;
+        const uint32_t valid_mask = valid ? 0xffffffffu : 0u;
+        uint32_t b0, b1, b2, b3, take_all;
+        auto set_limit = [&]() {
+            b0 = 0u - (static_cast< uint32_t >(limit) & 1u);
+            b1 = 0u - ((static_cast< uint32_t >(limit) >> 1) & 1u);
+            b2 = 0u - ((static_cast< uint32_t >(limit) >> 2) & 1u);
+            b3 = 0u - ((static_cast< uint32_t >(limit) >> 3) & 1u);
+            take_all = 0u - ((static_cast< uint32_t >(limit) >> 4) & 1u);
+        };
+        set_limit();
+        __syncwarp();
+
+        Selection selection;
+        selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
+        for(int chunk = 0; chunk < chunk_cardinality; ++chunk) {
+            const unsigned buffer = resident ? 0u : (iteration & 1u);
+            if(!resident) {
+                if(tid == 0 && iteration + 1 < total_iterations) { issue(iteration + 1); }
+                mbarrier_wait(&mbarrier[buffer], (iteration >> 1) & 1u);
+            }
+            const uint32_t* const equality = reinterpret_cast< const uint32_t* >(stage + buffer * WHITELIST_CHUNK_BYTES);
+            const uint2* const word = reinterpret_cast< const uint2* >(equality + WHITELIST_EQUALITY_WORDS);
+            const double* const prior = reinterpret_cast< const double* >(word + WHITELIST_CHUNK);
+            const int first = chunk * WHITELIST_CHUNK;
+            /* this lane's plane addresses inside the chunk: the only per-lane address arithmetic of the fast path */
+            uint32_t cursor[WHITELIST_POSITIONS];
+            #pragma unroll
+            for(int j = 0; j < WHITELIST_POSITIONS; ++j) { cursor[j] = plane_address[j] + buffer * WHITELIST_CHUNK_BYTES; }
+            const int live = P.barcode_cardinality - first < WHITELIST_CHUNK ? P.barcode_cardinality - first : WHITELIST_CHUNK;
+            const int group_cardinality = (live + 32 * WHITELIST_GROUP - 1) / (32 * WHITELIST_GROUP);
+            #pragma unroll 1
+            for(int group = 0; group < group_cardinality; ++group) {
+                uint32_t pass[WHITELIST_GROUP];
+                uint32_t any = 0;
+                static_assert(WHITELIST_GROUP == 4, "the fast path is written out for four blocks per trip");
+                pass[0] = whitelist_block< 0 >(cursor, b0, b1, b2, b3) | take_all;
+                pass[1] = whitelist_block< 1 >(cursor, b0, b1, b2, b3) | take_all;
+                pass[2] = whitelist_block< 2 >(cursor, b0, b1, b2, b3) | take_all;
+                pass[3] = whitelist_block< 3 >(cursor, b0, b1, b2, b3) | take_all;
+                any = (pass[0] | pass[1]) | (pass[2] | pass[3]);
+                #pragma unroll
+                for(int j = 0; j < WHITELIST_POSITIONS; ++j) { cursor[j] += WHITELIST_GROUP * WHITELIST_POSITIONS * WHITELIST_PLANES * 4; }
+                if(__any_sync(FULL_MASK, (any & valid_mask) != 0u)) {
+                    const int previous = limit;
+                    int u = 0;
+                    uint32_t pending = pass[0] & valid_mask;
+                    while(true) {
+                        #pragma unroll
+                        for(int v = 1; v < WHITELIST_GROUP; ++v) {
+                            if(pending == 0u && u < v) { u = v; pending = pass[v] & valid_mask; }
+                        }
+                        if(pending == 0u) { break; }
+                        const int k = __ffs(static_cast< int >(pending)) - 1;
+                        pending &= pending - 1u;
+                        const int i = (group * WHITELIST_GROUP + u) * 32 + k;
+                        const uint2 raw = word[i];
+                        const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
+                        const double p = subset_product< G >(table_base, m) * prior[i];
+                        if(p < threshold) {
+                            /* below half the maximum: not the winner, not a tie, and too small to move the threshold */
+                            selection.rest += p;
+                        } else {
+                            select_one(selection, p, first + i);
+                            threshold = fmin(0.5 * selection.best, tolerance_per_barcode * (noise_term + selection.rest));
+                            while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
+                        }
+                    }
+                    if(limit != previous) { set_limit(); }
+                }
+            }
+            if(!resident) {
+                __syncthreads();
+                ++iteration;
+            }
+        }
+
+        /* ---- structural ties are queued for pamld_tie_kernel, everything else is decided here (as pamld_kernel) */
+        const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
+        const unsigned queued = __ballot_sync(FULL_MASK, tied);
+        if(queued) {
+            unsigned slot = 0;
+            if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
+            slot = __shfl_sync(FULL_MASK, slot, 0);
+            if(tied) {
+                const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
+                TieRecord record;
+                record.best = selection.best;
+                record.rest = selection.rest;
+                record.base_probability = base_probability;
+                record.high_quality_mask = high_quality_mask;
+                record.uniform = uniform_positions == L ? 1u : 0u;
+                record.o_lo = o_lo;
+                record.o_hi = o_hi;
+                record.nmask = nmask;
+                record.read = static_cast< uint32_t >(r);
+                #pragma unroll
+                for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
+                P.tie_record[at] = record;
+            }
+        }
+        const bool decided = valid && !tied;
+        if(decided) {
+            const BarcodeEntry e = P.barcodes[selection.index];
+            const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, e.lo, e.hi);
+            const double t = subset_product< G >(table_base, m);
+            const Verdict v = pamld_decide(P, accumulator, &misc[3], selection.index, m, t, e.prior, selection.rest, base_probability,
+                                           uniform_positions == L, high_quality_mask, qcfail);
+            qcfail = v.qcfail;
+            A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
+            store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
+        }
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, decided);
+            const unsigned passing = __ballot_sync(FULL_MASK, decided && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&misc[1], static_cast< uint32_t >(__popc(passing)));
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if(tid < 2 && P.totals != nullptr && misc[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(misc[tid])); }
+    if(tid >= 2 && tid < 4 && P.diagnostics != nullptr && misc[tid]) { atomicAdd(&P.diagnostics[tid - 2], static_cast< unsigned long long >(misc[tid])); }
+}
+
 /* ------------------------------------------------------------------ PAMLD tie kernel
    Structural ties (equal multisets of mismatch qualities under equal priors) are common for noise reads
    (~2 % of the synthetic workloads). The reference resolves them by the rounding of its position ordered
@@ -1554,8 +1898,32 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
 
 }   /* namespace */
 
+static cudaError_t launch_pamld_whitelist(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    constexpr int G = 4;
+    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double);
+    const size_t fixed = whitelist_fixed_bytes();
+    if(fixed + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - fixed) / per_warp);
+    warps = warps > WHITELIST_WARPS ? WHITELIST_WARPS : warps;
+    const size_t bytes = fixed + per_warp * warps;
+    cudaError_t status = cudaFuncSetAttribute(pamld_whitelist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    if(status != cudaSuccess) { return status; }
+    const int threads = warps * WARP_SIZE;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
+    status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
+    if(status != cudaSuccess) { return status; }
+    pamld_whitelist_kernel<<< grid, threads, bytes, stream >>>(params, tile);
+    status = cudaGetLastError();
+    if(status != cudaSuccess) { return status; }
+    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
+    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     if(tile.n_reads <= 0) { return cudaSuccess; }
+    if(params.whitelist != nullptr) { return launch_pamld_whitelist(params, tile, geometry, stream); }
     if(params.grid != nullptr) {
         if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_grid< 6, 6, false >(params, tile, geometry, stream); }
         if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_grid< 8, 8, true >(params, tile, geometry, stream); }
@@ -1660,7 +2028,9 @@ void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, 
     const int L = params.nucleotide_cardinality;
     if(algorithm == 0) {
         const bool grid = params.grid != nullptr && grid_shape_supported(params.grid_split, L);
-        if(grid) {
+        if(params.whitelist != nullptr) {
+            snprintf(buffer, capacity, "pamld_whitelist_kernel + pamld_tie_kernel<4>");
+        } else if(grid) {
             const bool dense = params.grid_dense != 0 && (params.grid_split == 8 || params.grid_split == 10);
             snprintf(buffer, capacity, "pamld_grid_kernel<%d, %d, %d, %d, %d> + pamld_tie_kernel<%d>", params.grid_split, L - params.grid_split,
                      GRID_GROUP_WIDTH, params.grid_uniform ? 1 : (dense ? params.grid_dense : 0), params.grid_uniform ? 1 : 0, (L + 3) / 4);

@@ -60,6 +60,21 @@ __host__ __device__ inline uint32_t mdd_hash(uint32_t key_lo, uint32_t key_hi) {
     return h;
 }
 
+/*  Whitelist blob (pamld_whitelist_kernel; large single-word codecs such as a 737 K x 16 nt cellular whitelist).
+    The table is cut into chunks of WHITELIST_CHUNK barcodes, each one contiguous so that ONE TMA bulk copy stages it:
+      equality planes  [block of 32 barcodes][position 0..15][code A, C, G, T, "not counted"] u32 — bit k of
+                       plane (block, j, c) is set when barcode 32 * block + k has base c at position j; the
+                       fifth plane is all ones (positions a read does not count read it)
+      words            [WHITELIST_CHUNK] {low plane, high plane} of every barcode (the exact path)
+      priors           [WHITELIST_CHUNK] f64 (0 for the padding of the last chunk: such entries never win) */
+constexpr int WHITELIST_CHUNK = 512;
+constexpr int WHITELIST_POSITIONS = 16;
+constexpr int WHITELIST_PLANES = 5;
+constexpr int WHITELIST_BLOCKS = WHITELIST_CHUNK / 32;
+constexpr int WHITELIST_EQUALITY_WORDS = WHITELIST_BLOCKS * WHITELIST_POSITIONS * WHITELIST_PLANES;
+constexpr int WHITELIST_CHUNK_BYTES = WHITELIST_EQUALITY_WORDS * 4 + WHITELIST_CHUNK * 8 + WHITELIST_CHUNK * 8;
+constexpr int WHITELIST_MINIMUM_BARCODES = 4096;    /* smaller codecs use the exhaustive scans (PHQ_WHITELIST_MINIMUM overrides, for tests) */
+
 /* what the scan kernel hands to the tie kernel for a queued read */
 struct __align__(16) TieRecord {
     double best;                /* the scan's maximum prior adjusted product (relative to P0) */
@@ -108,6 +123,9 @@ struct DecoderParams {
     int32_t grid_split;                         /* nucleotides of the first segment */
     int32_t grid_dense;                         /* 0, or the padded B word count (8 / 16) of the dense form: entries = grid_a x grid_dense */
     int32_t grid_uniform;                       /* dense form with every combination present under one prior */
+    const unsigned char* whitelist;             /* chunked blob of pamld_whitelist_kernel (WhitelistLayout); NULL = the other scans */
+    int32_t whitelist_chunks;
+    double prior_maximum;                       /* largest barcode prior: the pruning bound of pamld_whitelist_kernel */
     TieRecord* tie_record;                      /* [reads of the launch] queue of reads whose winner needs the exact tie path (PAMLD) */
     unsigned* tie_count;                        /* queue length, reset before every scan */
 };

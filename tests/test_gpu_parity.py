@@ -14,7 +14,7 @@ from pheniqs_b200 import DecoderChain, compile_job, workload
 pytestmark = pytest.mark.gpu
 
 
-def run_both(job, code, quality, offset, qcfail=None, compiled=None, device_path=False):
+def run_both(job, code, quality, offset, qcfail=None, compiled=None, device_path=False, oracle_threads=1):
     compiled = compiled or compile_job(job)
     n = int(offset[0].shape[0] - 1)
     chain = DecoderChain(compiled, device=0)
@@ -32,7 +32,7 @@ def run_both(job, code, quality, offset, qcfail=None, compiled=None, device_path
     else:
         results, flags_out = chain.decode(tiles, n, qcfail)
     checker = O.best_oracle(compiled, len(code))
-    expected = checker.decode(O.ReadBatch(code, quality, offset, qcfail))
+    expected = checker.decode(O.ReadBatch(code, quality, offset, qcfail), threads=oracle_threads)
     return chain, checker, results, flags_out, expected
 
 
@@ -76,6 +76,49 @@ def test_whitelist_config_reduced():
     compiled = compile_job(spec["job"])
     code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 3000, seed=4)
     check(*run_both(None, code, quality, offset, compiled=compiled))
+
+
+@pytest.mark.parametrize("variant", ["single", "two_segments_hq", "reverse_short", "flat_priors_no_noise"])
+def test_whitelist_kernel_on_small_codecs(variant, monkeypatch):
+    """pamld_whitelist_kernel (bit sliced pruning scan + exact path) forced onto small codecs, where the oracle is
+    cheap: several blocks per chunk with a ragged last block, the high quality filter, short reads (absent
+    positions are not counted), reverse complemented tokens, a decoder without noise (no absolute floor for
+    the pruning threshold) and unequal priors."""
+    monkeypatch.setenv("PHQ_WHITELIST_MINIMUM", "1")
+    rng = np.random.default_rng(77)
+    short = 0.0
+    if variant == "single":
+        decoder = helpers.random_job(rng, "pamld", (8,), 150, minimum_distance=2)
+    elif variant == "two_segments_hq":
+        decoder = helpers.random_job(rng, "pamld", (6, 7), 100, **{"high quality threshold": 20, "high quality distance threshold": 1})
+    elif variant == "reverse_short":
+        decoder = helpers.random_job(rng, "pamld", (9, 7), 700, reverse=True, minimum_distance=2)
+        short = 0.2
+    else:
+        decoder = helpers.random_job(rng, "pamld", (12,), 1100, noise=0.0, minimum_distance=2)
+        for record in decoder["codec"].values():
+            record["concentration"] = 1.0
+    job = {"sample": decoder, "cellular": [helpers.random_job(rng, "pamld", (16,), 40)]}
+    job["cellular"][0]["transform"]["token"] = ["0:1:17"]
+    compiled = compile_job(job)
+    n = 12000
+    code, quality, offset, _ = workload.synthesize(compiled, [0], n, seed=9, short_fraction=short)
+    qcfail = (rng.random(n) < 0.1).astype(np.uint8)
+    state = run_both(None, code, quality, offset, qcfail, compiled=compiled)
+    assert all("pamld_whitelist_kernel" in state[0].kernel_description(k) for k in range(state[0].n_decoders))
+    check(*state)
+
+
+def test_whitelist_config_full_size():
+    """Config 5 at its full table size: 737,280 x 16 nt, 1,440 chunks streamed per tile of reads; a few
+    hundred reads, which is what the CPU oracle finishes in seconds."""
+    spec = workload.load("c5")
+    compiled = compile_job(spec["job"])
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 600, seed=11)
+    import os
+    state = run_both(None, code, quality, offset, compiled=compiled, oracle_threads=os.cpu_count() or 1)
+    assert "pamld_whitelist_kernel" in state[0].kernel_description(1) or "pamld_whitelist_kernel" in state[0].kernel_description(0)
+    check(*state)
 
 
 def test_bdggg_golden_through_the_gpu():
