@@ -211,6 +211,31 @@ int phq_decode_batch_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_se
 int phq_decode_batch_raw_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
                                  int32_t phred_offset, const uint8_t* qcfail_in, phq_compact_result* const* compact_results);
 
+/* ------------------------------------------------------------------ tags out
+
+   What Read::flush (read.h:187-237) assembles from the decoders' verdicts and Auxiliary::encode
+   (auxiliary.cpp:320-361) appends to every output record, produced on the device as the BAM auxiliary bytes
+   themselves (tag, type, value; strings NUL terminated, floats little endian) in the reference's order:
+
+       RG:Z                    ID of the sample barcode the read was assigned to (pamld.cpp:139, mdd.cpp:101)
+       BC:Z QT:Z XB:f          raw sample barcode, its qualities (Phred + 33), float(1 - sample confidence)
+       RX:Z QX:Z OX:Z BZ:Z XM:f corrected / raw molecular barcode and qualities (sequence.h:382-398: a corrected
+                               base carries `corrected quality`)
+       CB:Z CR:Z CY:Z XC:f      corrected / raw cellular barcode, its qualities, float(1 - cellular confidence)
+
+   A string tag is left out when empty, a float tag unless 0 < confidence < 1, like the reference. Confidences of
+   several decoders of a topic are multiplied in f64 first (read.h:279-285); an undetermined cellular or molecular
+   decoder zeroes its topic (pamld.cpp:153-159). The host appends aux[r * aux_stride .. + aux_length[r]) to record r
+   (every segment of the read carries the same block, read.h:219-231) and sets the QC fail flag from qcfail_out.
+   Known divergence: QX of a second corrected molecular segment — the reference indexes the observed bases from
+   the length the corrected barcode already has (sequence.h:388) and can run past the segment into stale memory;
+   positions past the segment's terminator count as different here. */
+int phq_tag_record_bytes(phq_handle* handle, int32_t* bytes);   /* the smallest aux_stride the job needs (multiple of 16) */
+/* phq_decode_batch_raw that also writes the auxiliary block of every read; `results` may be NULL */
+int phq_decode_batch_raw_tags(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
+                              const uint8_t* qcfail_in, uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out,
+                              phq_result* const* results);
+
 int phq_host_alloc(void** pointer, size_t bytes);       /* pinned host memory */
 void phq_host_free(void* pointer);
 

@@ -509,6 +509,32 @@ class RefOracle:
         out.seconds = seconds
         return out
 
+    TAG_NAMES = ("RG", "BC", "QT", "RX", "QX", "OX", "BZ", "CB", "CR", "CY")
+
+    def tags(self, batch: ReadBatch, stride: int = 256):
+        """Per read, the tags Read::flush / Auxiliary::encode produce (read.h:187-237, auxiliary.cpp:320-361):
+        [{"RG": ..., "BC": ..., ..., "XB": float32, ...}] with absent tags left out, and the final qcfail flags."""
+        code, quality, offset, qcfail = batch._pointers()
+        text = np.zeros((batch.n_reads, 10, stride), dtype=np.uint8)
+        probability = np.zeros((batch.n_reads, 3), dtype=np.float32)
+        flags = np.zeros(batch.n_reads, dtype=np.uint8)
+        status = self.lib.phq_ref_tags(self.handle, C.c_int64(batch.n_reads), batch.n_segments, code, quality, offset, qcfail, stride,
+                                       _p(text, C.c_char), _p(probability, C.c_float), _p(flags, C.c_uint8))
+        if status != 0:
+            raise RuntimeError(self.lib.phq_ref_last_error(self.handle).decode())
+        out = []
+        for r in range(batch.n_reads):
+            record = {}
+            for t, name in enumerate(self.TAG_NAMES):
+                value = text[r, t].tobytes().split(b"\0", 1)[0]
+                if value:
+                    record[name] = value.decode("latin-1")
+            for t, name in enumerate(("XB", "XM", "XC")):
+                if probability[r, t] > 0:
+                    record[name] = np.float32(probability[r, t])
+            out.append(record)
+        return out, flags
+
     def accumulators(self, k: int):
         nb = self.n_barcodes[k]
         u = np.zeros((nb + 1, 6), dtype=np.uint64)

@@ -310,6 +310,58 @@ double phq_ref_decode(void* handle, int64_t n_reads, int32_t n_segments,
     }
 }
 
+/*  The tags the reference's OUTPUT carries for every read: one reference thread classifies the
+    reads in order, Read::flush (read.h:187-237) assembles the auxiliary fields, and the strings Auxiliary::encode
+    (auxiliary.cpp:320-361) would append are copied out: text[r][t] (stride bytes each, NUL terminated) for t =
+    RG BC QT RX QX OX BZ CB CR CY, and XB XM XC as floats (0 = absent). Accumulates like phq_ref_decode. */
+int32_t phq_ref_tags(void* handle, int64_t n_reads, int32_t n_segments,
+                     const uint8_t* const* code, const uint8_t* const* quality, const int64_t* const* offset,
+                     const uint8_t* qcfail_in, int32_t stride, char* text, float* error_probability, uint8_t* out_qcfail) {
+    Handle* h(static_cast< Handle* >(handle));
+    try {
+        DecoderSet set(h->job);
+        Read input(n_segments, Platform::ILLUMINA, 0);
+        Read output(1, Platform::ILLUMINA, 0);
+        input.clear();
+        output.clear();
+        for(int64_t r(0); r < n_reads; ++r) {
+            for(int32_t s(0); s < n_segments; ++s) {
+                const int64_t from(offset[s][r]);
+                const int64_t to(offset[s][r + 1]);
+                input[s].fill(code[s] + from, quality[s] + from, static_cast< int32_t >(to - from));
+            }
+            const bool qcfail(qcfail_in != NULL && qcfail_in[r]);
+            input.set_qcfail(qcfail);
+            for(auto& segment : output) { segment.set_qcfail(qcfail); }
+            for(auto& slot : set.chain) { slot.classifier->classify(input, output); }
+            ++set.count;
+            if(!output.qcfail()) { ++set.pf_count; }
+            output.flush();
+            const Auxiliary& a(output.auxiliary());
+            const kstring_t* field[10] = { &a.RG, &a.BC, &a.QT, &a.RX, &a.QX, &a.OX, &a.BZ, &a.CB, &a.CR, &a.CY };
+            for(int32_t t(0); t < 10; ++t) {
+                char* const to(text + (static_cast< size_t >(r) * 10 + t) * stride);
+                memset(to, 0, stride);
+                if(field[t]->l > 0 && field[t]->s != NULL) {
+                    if(static_cast< int32_t >(field[t]->l) >= stride) { throw InternalError("tag longer than the stride"); }
+                    memcpy(to, field[t]->s, field[t]->l);
+                }
+            }
+            error_probability[r * 3 + 0] = a.XB;
+            error_probability[r * 3 + 1] = a.XM;
+            error_probability[r * 3 + 2] = a.XC;
+            if(out_qcfail != NULL) { out_qcfail[r] = output.qcfail() ? 1 : 0; }
+            input.clear();
+            output.clear();
+        }
+        h->total->collect(set);
+        return 0;
+    } catch(std::exception& e) {
+        h->error.assign(e.what());
+        return -1;
+    }
+}
+
 /* raw accumulator tables of decoder k: row 0 = undetermined, rows 1..NB = codec order */
 void phq_ref_accumulators(void* handle, int32_t decoder, uint64_t* u64_table /* [(NB+1)*6] */, double* f64_table /* [(NB+1)*2] */) {
     Handle* h(static_cast< Handle* >(handle));

@@ -69,6 +69,7 @@ EXPORTS = (
     "phq_compile_job", "phq_free", "phq_last_global_error", "phq_create", "phq_destroy", "phq_last_error",
     "phq_decoder_count", "phq_decoder_describe", "phq_pack", "phq_decode_batch", "phq_decode_batch_compact",
     "phq_decode_batch_device", "phq_decode_batch_device_compact", "phq_decode_batch_raw", "phq_decode_batch_raw_compact",
+    "phq_decode_batch_raw_tags", "phq_tag_record_bytes",
     "phq_host_alloc", "phq_host_free", "phq_accumulators", "phq_totals", "phq_accumulator_buffer",
     "phq_reset_accumulators", "phq_estimate_priors", "phq_set_priors", "phq_report", "phq_encode_report", "phq_adjust_job",
     "phq_statistics", "phq_kernel_description",
@@ -106,6 +107,8 @@ def library() -> C.CDLL:
     lib.phq_decode_batch_device_compact.argtypes = [C.c_void_p, C.c_int64, P(Tile), C.c_void_p, P(C.c_void_p), C.c_void_p]
     lib.phq_decode_batch_raw.argtypes = [C.c_void_p, C.c_int64, C.c_int32, P(RawSegment), C.c_int32, C.c_void_p, P(C.c_void_p), C.c_void_p]
     lib.phq_decode_batch_raw_compact.argtypes = [C.c_void_p, C.c_int64, C.c_int32, P(RawSegment), C.c_int32, C.c_void_p, P(C.c_void_p)]
+    lib.phq_decode_batch_raw_tags.argtypes = [C.c_void_p, C.c_int64, C.c_int32, P(RawSegment), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, P(C.c_void_p)]
+    lib.phq_tag_record_bytes.argtypes = [C.c_void_p, P(C.c_int32)]
     lib.phq_host_alloc.argtypes = [P(C.c_void_p), C.c_size_t]
     lib.phq_host_free.argtypes = [C.c_void_p]
     lib.phq_host_free.restype = None

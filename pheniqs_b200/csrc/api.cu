@@ -67,6 +67,8 @@ struct StagingSlot {
     std::vector< DeviceBuffer< uint8_t > > raw_sequence;    /* feed bytes of phq_decode_batch_raw, per input segment */
     std::vector< DeviceBuffer< uint8_t > > raw_quality;
     std::vector< DeviceBuffer< long long > > raw_offset;
+    DeviceBuffer< uint8_t > aux;                /* tag synthesis: auxiliary records and their lengths */
+    DeviceBuffer< int32_t > aux_length;
 };
 
 constexpr int STAGING_SLOTS = 3;
@@ -83,6 +85,11 @@ struct phq_handle {
     std::vector< BarcodeEntry* > device_barcodes;
     std::vector< MddSlot* > device_mdd;        /* MDD lookup tables (kernels.cuh), NULL where the scan kernel is used */
     std::vector< std::vector< int32_t > > mdd_shape;    /* per decoder: first slot and mask of every table, total slots */
+    std::vector< uint8_t* > device_barcode_code;   /* tag synthesis: [(N + 1)][L] BAM codes per coded decoder, row 0 undetermined */
+    uint8_t* device_read_group_text;            /* tag synthesis: read group IDs of the sample decoder */
+    int32_t* device_read_group_offset;
+    int32_t read_group_longest;
+    bool tags_ready;
     std::vector< unsigned char* > device_whitelist;    /* chunked whitelist blobs (kernels.cuh), NULL where not applicable */
     std::vector< int32_t > whitelist_chunks;
     std::vector< double > prior_maximum;
@@ -106,7 +113,8 @@ struct phq_handle {
     long long sub_batch_reads;              /* reads per in-flight sub-batch of the host-buffer calls */
     std::string error;
 
-    phq_handle() : device(0), device_phred(NULL), device_accumulators(NULL), n_u64(0), n_f64(0), slots_ready(false),
+    phq_handle() : device(0), device_read_group_text(NULL), device_read_group_offset(NULL), read_group_longest(0), tags_ready(false),
+        device_phred(NULL), device_accumulators(NULL), n_u64(0), n_f64(0), slots_ready(false),
         timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0), sub_batch_reads(SUB_BATCH_READS) {
         /* PHQ_SUB_BATCH_READS: smaller sub-batches (tests exercise the boundaries with small inputs) */
         const char* const value(getenv("PHQ_SUB_BATCH_READS"));
@@ -494,6 +502,9 @@ void destroy(phq_handle* h) {
     for(auto* p : h->device_barcodes) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_grid) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_whitelist) { if(p != NULL) { cudaFree(p); } }
+    for(auto* p : h->device_barcode_code) { if(p != NULL) { cudaFree(p); } }
+    if(h->device_read_group_text != NULL) { cudaFree(h->device_read_group_text); }
+    if(h->device_read_group_offset != NULL) { cudaFree(h->device_read_group_offset); }
     for(auto* p : h->device_mdd) { if(p != NULL) { cudaFree(p); } }
     if(h->device_phred != NULL) { cudaFree(h->device_phred); }
     if(h->device_accumulators != NULL) { cudaFree(h->device_accumulators); }
@@ -504,6 +515,8 @@ void destroy(phq_handle* h) {
             for(auto& b : s.quality) { b.release(); }
             for(auto& b : s.results) { b.release(); }
             s.qcfail.release();
+            s.aux.release();
+            s.aux_length.release();
             s.tie_list.release();
             cudaEventDestroy(s.done);
             cudaStreamDestroy(s.stream);
@@ -1046,10 +1059,77 @@ struct RawReader {
     }
 };
 
+/* bytes one read's auxiliary record can take: every tag of every topic at its longest (Auxiliary::encode, auxiliary.cpp:320-361) */
+int32_t tag_record_bytes(const phq_handle* h) {
+    int32_t bytes(0);
+    for(int topic(0); topic < 3; ++topic) {
+        int32_t raw(0), corrected(0);
+        bool present(false), probabilistic(false);
+        for(const auto& d : h->chain) {
+            if(d.topic != topic) { continue; }
+            present = true;
+            if(!d.transform.empty()) { raw += d.nucleotide_cardinality; }
+            if(d.tiled()) { corrected += d.nucleotide_cardinality; }
+            probabilistic = probabilistic || d.algorithm == PHQ_PAMLD;
+        }
+        if(!present) { continue; }
+        if(topic == PHQ_SAMPLE) { bytes += 3 + h->read_group_longest + 1; }
+        if(raw > 0) { bytes += 2 * (3 + raw + 1); }
+        if(corrected > 0 && topic != PHQ_SAMPLE) { bytes += (topic == PHQ_MOLECULAR ? 2 : 1) * (3 + corrected + 1); }
+        if(probabilistic) { bytes += 3 + 4; }
+    }
+    return (bytes + 15) / 16 * 16;
+}
+
+/* device tables of the tag kernel: barcode codes by index (row 0 = undetermined) and the read group IDs */
+void ensure_tags(phq_handle* h) {
+    if(h->tags_ready) { return; }
+    const size_t n(h->chain.size());
+    h->device_barcode_code.assign(n, NULL);
+    const char* name[3] = { "sample", "molecular", "cellular" };
+    for(size_t k(0); k < n; ++k) {
+        const DecoderSpec& d(h->chain[k]);
+        if(!d.tiled()) { continue; }
+        const size_t L(static_cast< size_t >(d.nucleotide_cardinality));
+        std::vector< uint8_t > table((static_cast< size_t >(d.barcode_cardinality) + 1) * L, 0);
+        memcpy(table.data() + L, d.barcode.data(), static_cast< size_t >(d.barcode_cardinality) * L);
+        PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcode_code[k]), table.size() ? table.size() : 1));
+        PHQ_CUDA(cudaMemcpy(h->device_barcode_code[k], table.data(), table.size(), cudaMemcpyHostToDevice));
+        if(d.topic == PHQ_SAMPLE) {
+            /* decode_tag_id_by_index (classifier.h): the ID of the undetermined element, then of every barcode by index */
+            const Json* element(h->job.find(name[0]));
+            std::vector< int32_t > offset(1, 0);
+            std::string text;
+            auto push = [&](const Json* record) {
+                if(record != NULL && record->is_object()) { text += get_string(*record, "ID"); }
+                offset.push_back(static_cast< int32_t >(text.size()));
+                const int32_t length(offset[offset.size() - 1] - offset[offset.size() - 2]);
+                if(length > h->read_group_longest) { h->read_group_longest = length; }
+            };
+            push(element != NULL ? element->find("undetermined") : NULL);
+            const Json* codec(element != NULL ? element->find("codec") : NULL);
+            for(const auto& key : d.barcode_key) { push(codec != NULL ? codec->find(key) : NULL); }
+            PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_read_group_text), text.size() ? text.size() : 1));
+            PHQ_CUDA(cudaMemcpy(h->device_read_group_text, text.data(), text.size(), cudaMemcpyHostToDevice));
+            PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_read_group_offset), offset.size() * sizeof(int32_t)));
+            PHQ_CUDA(cudaMemcpy(h->device_read_group_offset, offset.data(), offset.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+    }
+    h->tags_ready = true;
+}
+
 int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
-               const uint8_t* qcfail_in, phq_result* const* results, phq_compact_result* const* compact, uint8_t* qcfail_out) {
+               const uint8_t* qcfail_in, phq_result* const* results, phq_compact_result* const* compact, uint8_t* qcfail_out,
+               uint8_t* aux = NULL, int32_t* aux_length = NULL, int32_t aux_stride = 0) {
     return guarded(handle, [&]() {
         phq_handle* h(handle);
+        const bool tags(aux != NULL);
+        if(tags) {
+            if(aux_length == NULL) { throw InternalError("illegal argument"); }
+            if(h->chain.size() > static_cast< size_t >(TAG_MAX_DECODERS)) { throw ConfigurationError("more than " + std::to_string(TAG_MAX_DECODERS) + " decoders are not supported by the tag path"); }
+            ensure_tags(h);
+            if(aux_stride < tag_record_bytes(h) || aux_stride % 4 != 0) { throw ConfigurationError("auxiliary record stride must be a multiple of 4 and at least " + std::to_string(tag_record_bytes(h))); }
+        }
         if(n_reads < 0 || n_input_segments < 0 || (n_input_segments > 0 && segments == NULL)) { throw InternalError("illegal argument"); }
         if(n_input_segments > PACK_MAX_INPUT_SEGMENTS) { throw ConfigurationError("more than " + std::to_string(PACK_MAX_INPUT_SEGMENTS) + " input segments are not supported on this path"); }
         ensure_slots(h);
@@ -1057,7 +1137,8 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
         std::vector< bool > used(static_cast< size_t >(n_input_segments), false);
         for(size_t k(0); k < n_decoders; ++k) {
             const DecoderSpec& d(h->chain[k]);
-            if(!d.tiled()) { continue; }
+            if(!d.tiled() && !(tags && !d.transform.empty())) { continue; }
+            if(tags && d.transform.size() > static_cast< size_t >(TAG_MAX_TOKENS)) { throw ConfigurationError("more than " + std::to_string(TAG_MAX_TOKENS) + " tokens per decoder are not supported by the tag path"); }
             if(d.transform.size() > static_cast< size_t >(PACK_MAX_TOKENS)) { throw ConfigurationError("more than " + std::to_string(PACK_MAX_TOKENS) + " tokens per decoder are not supported on this path"); }
             for(const auto& t : d.transform) {
                 if(t.input_segment_index >= n_input_segments) {
@@ -1151,16 +1232,52 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
                     device_tiles[k].pitch = sub;
                     device_tiles[k].quality_bits = 8;
                 }
-                const bool wanted((results != NULL && results[k] != NULL) || (compact != NULL && compact[k] != NULL));
+                const bool wanted((results != NULL && results[k] != NULL) || (compact != NULL && compact[k] != NULL) || (tags && d.tiled()));
                 if(wanted) {
                     s.results[k].reserve(static_cast< size_t >(sub));
-                    if(compact != NULL) { device_compact[k] = reinterpret_cast< phq_compact_result* >(s.results[k].pointer); }
+                    if(compact != NULL && !tags) { device_compact[k] = reinterpret_cast< phq_compact_result* >(s.results[k].pointer); }
                     else { device_results[k] = s.results[k].pointer; }
                 }
             }
-            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, compact != NULL ? NULL : device_results.data(), compact != NULL ? device_compact.data() : NULL, s.tie_list, s.stream);
+            launch_chain(h, count, device_tiles.data(), s.qcfail.pointer, (compact != NULL && !tags) ? NULL : device_results.data(), (compact != NULL && !tags) ? device_compact.data() : NULL, s.tie_list, s.stream);
+            if(tags) {
+                TagPlan plan;
+                memset(&plan, 0, sizeof(plan));
+                plan.decoder_cardinality = static_cast< int32_t >(n_decoders);
+                plan.phred_offset = phred_offset;
+                plan.stride = aux_stride;
+                plan.read_group_text = h->device_read_group_text;
+                plan.read_group_offset = h->device_read_group_offset;
+                memcpy(plan.input, view, sizeof(view));
+                for(int32_t i(0); i < n_input_segments; ++i) { if(plan.input[i].offset == NULL) { plan.input[i].first = begin; } }
+                for(size_t k(0); k < n_decoders; ++k) {
+                    const DecoderSpec& d(h->chain[k]);
+                    TagDecoder& to(plan.decoder[k]);
+                    to.topic = d.topic;
+                    to.algorithm = d.algorithm;
+                    to.corrected_quality = d.corrected_quality;
+                    to.token_cardinality = static_cast< int32_t >(d.transform.size());
+                    to.segment_cardinality = d.transform.empty() ? 0 : d.segment_cardinality;
+                    to.nucleotide_cardinality = d.nucleotide_cardinality;
+                    for(int32_t i(0); i <= d.segment_cardinality && i <= PHQ_MAX_SEGMENTS && !d.transform.empty(); ++i) { to.segment_offset[i] = d.segment_offset[i]; }
+                    for(size_t i(0); i < d.transform.size(); ++i) {
+                        const TransformSpec& t(d.transform[i]);
+                        PackToken& token(to.token[i]);
+                        token.input_segment = t.input_segment_index; token.start = t.start; token.end = t.end; token.end_terminated = t.end_terminated ? 1 : 0;
+                        token.output_segment = t.output_segment_index; token.reverse_complement = t.reverse_complement ? 1 : 0;
+                    }
+                    to.results = d.tiled() ? device_results[k] : NULL;
+                    to.barcode_code = h->device_barcode_code[k];
+                }
+                s.aux.reserve(static_cast< size_t >(sub) * aux_stride);
+                s.aux_length.reserve(static_cast< size_t >(sub));
+                PHQ_CUDA(launch_tags(plan, count, s.aux.pointer, s.aux_length.pointer, h->geometry.multiprocessor_count, s.stream));
+                h->kernel_launches += 1;
+                PHQ_CUDA(cudaMemcpyAsync(aux + begin * aux_stride, s.aux.pointer, static_cast< size_t >(count) * aux_stride, cudaMemcpyDeviceToHost, s.stream));
+                PHQ_CUDA(cudaMemcpyAsync(aux_length + begin, s.aux_length.pointer, static_cast< size_t >(count) * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+            }
             for(size_t k(0); k < n_decoders; ++k) {
-                if(device_results[k] != NULL) {
+                if(device_results[k] != NULL && results != NULL && results[k] != NULL) {
                     PHQ_CUDA(cudaMemcpyAsync(results[k] + begin, device_results[k], static_cast< size_t >(count) * sizeof(phq_result), cudaMemcpyDeviceToHost, s.stream));
                 }
                 if(device_compact[k] != NULL) {
@@ -1197,6 +1314,19 @@ int phq_decode_batch_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_se
 int phq_decode_batch_raw_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
                                  const uint8_t* qcfail_in, phq_compact_result* const* compact_results) {
     return decode_raw(handle, n_reads, n_input_segments, segments, phred_offset, qcfail_in, NULL, compact_results, NULL);
+}
+
+int phq_tag_record_bytes(phq_handle* handle, int32_t* bytes) {
+    return guarded(handle, [&]() {
+        if(bytes == NULL) { throw InternalError("illegal argument"); }
+        ensure_tags(handle);
+        *bytes = tag_record_bytes(handle);
+    });
+}
+int phq_decode_batch_raw_tags(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
+                              const uint8_t* qcfail_in, uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out, phq_result* const* results) {
+    if(aux == NULL) { return PHQ_INTERNAL_ERROR; }
+    return decode_raw(handle, n_reads, n_input_segments, segments, phred_offset, qcfail_in, results, NULL, qcfail_out, aux, aux_length, aux_stride);
 }
 
 int phq_host_alloc(void** pointer, size_t bytes) {

@@ -50,6 +50,41 @@ struct PackPlan {
     RawSegmentView input[PACK_MAX_INPUT_SEGMENTS];
 };
 
+/* ------------------------------------------------------------------ tag synthesis
+   What Read::flush and Auxiliary::encode (read.h:187-237, auxiliary.cpp:320-361) append to every output record
+   for the decoders of this path, as the BAM auxiliary bytes themselves, in the reference's order:
+       RG:Z  BC:Z QT:Z XB:f  RX:Z QX:Z OX:Z BZ:Z XM:f  CB:Z CR:Z CY:Z XC:f
+   from the raw segments (raw barcodes and their qualities), the per-decoder results (read group, corrected
+   barcodes, error probabilities) and the barcode tables. */
+constexpr int TAG_MAX_DECODERS = 6;
+constexpr int TAG_MAX_TOKENS = 8;
+
+struct TagDecoder {
+    int32_t topic;                  /* phq_topic: 0 sample, 1 molecular, 2 cellular */
+    int32_t algorithm;              /* phq_algorithm */
+    int32_t corrected_quality;
+    int32_t token_cardinality;
+    int32_t segment_cardinality;
+    int32_t nucleotide_cardinality;
+    int32_t segment_offset[PHQ_MAX_SEGMENTS + 1];
+    PackToken token[TAG_MAX_TOKENS];
+    const phq_result* results;      /* device, [reads of the launch]; NULL for a naive decoder */
+    const uint8_t* barcode_code;    /* device, [(N + 1)][nucleotide_cardinality] BAM codes; row 0 = undetermined ('=') */
+};
+
+struct TagPlan {
+    int32_t decoder_cardinality;
+    int32_t phred_offset;
+    int32_t stride;                 /* bytes per record in `aux` (multiple of 4) */
+    const uint8_t* read_group_text; /* device: read group IDs of the sample decoder, row i at [offset[i], offset[i + 1]) */
+    const int32_t* read_group_offset;
+    RawSegmentView input[PACK_MAX_INPUT_SEGMENTS];
+    TagDecoder decoder[TAG_MAX_DECODERS];
+};
+
+/* aux[r * stride ..] receives the auxiliary bytes of read r (zero padded), aux_length[r] their count */
+cudaError_t launch_tags(const TagPlan& plan, long long n_reads, uint8_t* aux, int32_t* aux_length, int multiprocessor_count, cudaStream_t stream);
+
 /* tile planes of one decoder for `n_reads` reads from the raw segments; asynchronous on `stream` */
 cudaError_t launch_pack(const PackPlan& plan, long long n_reads, uint32_t* bases, uint16_t* nmask, uint32_t* quality, long long pitch,
                         int multiprocessor_count, cudaStream_t stream);

@@ -53,6 +53,25 @@ def adjust_job(job, report, precision: int = 15, text: bool = False):
         lib.phq_free(out)
 
 
+def parse_auxiliary(record) -> dict:
+    """The tags of one BAM auxiliary block (bytes): Z tags as str, f tags as numpy float32; order kept."""
+    data = bytes(record)
+    out, at = {}, 0
+    while at + 3 <= len(data):
+        tag, kind = data[at:at + 2].decode("latin-1"), chr(data[at + 2])
+        at += 3
+        if kind == "Z":
+            end = data.index(b"\0", at)
+            out[tag] = data[at:end].decode("latin-1")
+            at = end + 1
+        elif kind == "f":
+            out[tag] = np.frombuffer(data[at:at + 4], dtype="<f4")[0]
+            at += 4
+        else:
+            raise ValueError("unexpected auxiliary type " + kind)
+    return out
+
+
 def shard_range(n_reads: int, rank: int, world_size: int):
     """Contiguous read range of one rank, as the reference slices nothing but threads pull in turn
     (transcode.cpp:287-316); reads are independent, any partition is valid."""
@@ -241,6 +260,38 @@ class DecoderChain:
         check(self.lib.phq_decode_batch_raw(self.handle, n_reads, len(segments), array, phred_offset,
                                             None if qin is None else qin.ctypes.data, pointers, qcfail_out.ctypes.data), self.handle)
         return results, qcfail_out
+
+    def tag_record_bytes(self) -> int:
+        """The smallest auxiliary record stride the job needs (phq_tag_record_bytes)."""
+        value = C.c_int32()
+        check(self.lib.phq_tag_record_bytes(self.handle, C.byref(value)), self.handle)
+        return value.value
+
+    def decode_raw_tags(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, stride: int = 0, want_results: bool = False):
+        """phq_decode_batch_raw_tags: FASTQ bytes in, the BAM auxiliary block of every read out.
+        Returns (aux uint8 [n_reads, stride], aux_length int32 [n_reads], qcfail uint8 [n_reads][, results])."""
+        array = (RawSegment * max(len(segments), 1))()
+        keep = []
+        for i, g in enumerate(segments):
+            if g is None:
+                continue
+            sequence, quality, offset, length = g
+            sequence = np.ascontiguousarray(sequence, dtype=np.uint8)
+            quality = np.ascontiguousarray(quality, dtype=np.uint8)
+            offset = None if offset is None else np.ascontiguousarray(offset, dtype=np.int64)
+            keep.append((sequence, quality, offset))
+            array[i] = RawSegment(sequence.ctypes.data, quality.ctypes.data, None if offset is None else offset.ctypes.data, int(length))
+        stride = stride or self.tag_record_bytes()
+        aux = np.zeros((max(n_reads, 1), stride), dtype=np.uint8)
+        aux_length = np.zeros(max(n_reads, 1), dtype=np.int32)
+        qcfail_out = np.zeros(max(n_reads, 1), dtype=np.uint8)
+        results = [np.zeros(n_reads, dtype=RESULT_DTYPE) if (want_results and info.has_tile) else None for info in self.info]
+        pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
+        qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
+        check(self.lib.phq_decode_batch_raw_tags(self.handle, n_reads, len(segments), array, phred_offset, None if qin is None else qin.ctypes.data,
+                                                 aux.ctypes.data, stride, aux_length.ctypes.data, qcfail_out.ctypes.data, pointers), self.handle)
+        out = (aux[:n_reads], aux_length[:n_reads], qcfail_out[:n_reads])
+        return out + (results,) if want_results else out
 
     def decode_device(self, device_tiles, n_reads: int, qcfail, results=None, stream=None):
         """Same over device-resident torch tensors; asynchronous on `stream` (phq_decode_batch_device).

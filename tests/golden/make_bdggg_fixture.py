@@ -9,7 +9,8 @@ Writes, next to this script:
                        convention (BAM 4-bit code per base, Phred value per base, offsets, chastity qcfail)
   bdggg_job.json       the sample / molecular / cellular decoder directives of BDGGG_annotated.json with the
                        `base` decoder of BDGGG_interleave.json merged in (what the reference compiles)
-  bdggg_expected.json  per output read of valid/annotated.out: name, flag, RG, BC, XB, CB, XC, OX (first segment)
+  bdggg_expected.json  per output read of valid/annotated.out: name, flag and every tag (RG BC QT XB OX BZ CB CR CY XC) of the first
+                       segment, with the order they are written in
   bdggg_report.json    valid/annotated.err (the JSON report with every accumulator and estimated prior)
   bdggg_compiled.json  the sample/molecular/cellular sections of valid/compile_annotated.out
   prior_report.json / prior_estimated.json   test/api/prior input report and valid/BDGGG_annotated_estimated.json
@@ -80,7 +81,8 @@ def main():
             continue
         tag = {f[:2]: f[5:] for f in field[11:]}
         expected.append({"name": field[0], "flag": flag, "RG": tag.get("RG"), "BC": tag.get("BC"), "XB": tag.get("XB"),
-                         "CB": tag.get("CB"), "CR": tag.get("CR"), "XC": tag.get("XC"), "OX": tag.get("OX")})
+                         "CB": tag.get("CB"), "CR": tag.get("CR"), "XC": tag.get("XC"), "OX": tag.get("OX"),
+                         "QT": tag.get("QT"), "BZ": tag.get("BZ"), "CY": tag.get("CY"), "order": [f[:2] for f in field[11:]]})
     json.dump(expected, open(os.path.join(HERE, "bdggg_expected.json"), "w"), indent=0)
 
     report = json.load(open(os.path.join(T, "valid", "annotated.err")))
