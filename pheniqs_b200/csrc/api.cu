@@ -286,10 +286,9 @@ void upload_whitelist(phq_handle* h, size_t k) {
     double largest(0);
     for(size_t c(0); c < chunks; ++c) {
         uint32_t* const equality(reinterpret_cast< uint32_t* >(blob.data() + c * WHITELIST_CHUNK_BYTES));
-        uint32_t* const word(equality + WHITELIST_EQUALITY_WORDS);
-        double* const prior(reinterpret_cast< double* >(word + 2 * WHITELIST_CHUNK));
+        /* plane (position j, code c) of block b at word ((j * planes + c) * blocks + b): one 16-byte load per position covers the group */
         for(int32_t block(0); block < WHITELIST_BLOCKS; ++block) {
-            for(int32_t j(0); j < WHITELIST_POSITIONS; ++j) { equality[(block * WHITELIST_POSITIONS + j) * WHITELIST_PLANES + 4] = 0xffffffffu; }
+            for(int32_t j(0); j < WHITELIST_POSITIONS; ++j) { equality[(j * WHITELIST_PLANES + 4) * WHITELIST_BLOCKS + block] = 0xffffffffu; }
         }
         for(int32_t i(0); i < WHITELIST_CHUNK; ++i) {
             const size_t b(c * WHITELIST_CHUNK + static_cast< size_t >(i));
@@ -300,11 +299,8 @@ void upload_whitelist(phq_handle* h, size_t k) {
                 const uint32_t two(code == 1 ? 0u : code == 2 ? 1u : code == 4 ? 2u : 3u);
                 lo |= (two & 1u) << j;
                 hi |= (two >> 1) << j;
-                equality[((i >> 5) * WHITELIST_POSITIONS + j) * WHITELIST_PLANES + two] |= 1u << (i & 31);
+                equality[(j * WHITELIST_PLANES + static_cast< int32_t >(two)) * WHITELIST_BLOCKS + (i >> 5)] |= 1u << (i & 31);
             }
-            word[2 * i] = lo;
-            word[2 * i + 1] = hi;
-            prior[i] = d.concentration[b];
             if(d.concentration[b] > largest) { largest = d.concentration[b]; }
         }
     }
@@ -734,7 +730,10 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
 
         for(size_t k(0); k < n; ++k) {
             if(chain[k].tiled()) {
-                PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), static_cast< size_t >(chain[k].barcode_cardinality) * sizeof(BarcodeEntry)));
+                /* padded to whole whitelist groups with zero entries (prior 0): pamld_whitelist_kernel may look a padding barcode up */
+                const size_t padded((static_cast< size_t >(chain[k].barcode_cardinality) + WHITELIST_CHUNK - 1) / WHITELIST_CHUNK * WHITELIST_CHUNK);
+                PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), padded * sizeof(BarcodeEntry)));
+                PHQ_CUDA(cudaMemset(h->device_barcodes[k], 0, padded * sizeof(BarcodeEntry)));
                 upload_barcodes(h, k);
                 upload_grid(h, k);
                 upload_whitelist(h, k);

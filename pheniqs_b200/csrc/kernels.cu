@@ -963,9 +963,11 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                  loads the 16 planes its read selects (5 distinct addresses per request: conflict free), adds
                  them with a carry-save adder tree of 26 LOP3 (vertical counters) whose carry-in bits hold the
                  lane's current limit, and the carry out of the tree is the word of barcodes with at most
-                 `limit` counted mismatches. About 45 instructions per 32 x 32 pairs.
-     exact path  every barcode of that word is evaluated exactly like pamld_kernel does (mismatch mask, subset
-                 product tables, prior, first-maximum selection, tie detection), in index order.
+                 `limit` counted mismatches. About 50 instructions per 32 x 32 pairs.
+     exact path  the surviving (read, barcode) pairs of a group of 128 barcodes are pooled over the warp and
+                 evaluated one per lane exactly like pamld_kernel does (mismatch mask, subset products, prior),
+                 then every read folds its own candidates in, in index order (first-maximum selection, tie
+                 detection). Pooling makes the cost follow the number of candidates, not the worst lane.
 
    `limit` is the largest count c whose bound can still matter: bound[c] >= min(best / 2,
    tolerance * (noise term + rest) / N). Everything below best / 2 cannot be the maximum or a tie; the N
@@ -973,15 +975,29 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
    confidence and 1 - confidence move by less than 6e-8 relative, a sixteenth of the 1e-6 the path allows.
    The bound only ever tightens (best and rest grow), so a stale limit is conservative. Positions that do not
    discriminate (N, quality 0, ratios >= 1 i.e. Phred < 3, positions past the barcode) are not counted: they
-   select the all-ones plane, and ratios above 1 are folded into the bound. */
-constexpr int WHITELIST_WARPS = 12;
-constexpr int WHITELIST_GROUP = 4;              /* blocks of 32 barcodes per trip of the fast path: one vote and branch */
+   select the all-ones plane, and ratios above 1 are folded into the bound.
+
+   Every warp is its own pipeline: it owns 32 reads at a time (taken from a global counter, so slow reads do
+   not hold a CTA back), streams the table through a private three-stage ring of TMA bulk copies (one 3.3 KB
+   group per stage, completion on the warp's own mbarriers) and never meets a CTA-wide barrier. */
+constexpr int WHITELIST_STAGES = 4;
+constexpr int WHITELIST_QUEUE = 64;             /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
+constexpr int WHITELIST_MAX_WARPS = 12;
 constexpr double WHITELIST_TOLERANCE = 5.9604644775390625e-08;     /* 2^-24 */
 
-__host__ __device__ inline unsigned whitelist_fixed_bytes() {
-    /* two stage buffers, Phred tables, 4 counters, 2 mbarriers; then 4 KB of slack for the table alignment */
-    return align_up(2u * WHITELIST_CHUNK_BYTES + 256u * 8u + 16u + 16u, 256u) + 4096u;
-}
+/* per-warp shared memory of pamld_whitelist_kernel */
+constexpr unsigned WL_OFF_TABLE = 0;                                                    /* 32 entries x 256 B: subset products of 8 groups of 2 positions, lane skewed */
+constexpr unsigned WL_OFF_RING = 8192;                                                  /* WHITELIST_STAGES groups of equality planes */
+constexpr unsigned WL_OFF_VALUE = WL_OFF_RING + WHITELIST_STAGES * WHITELIST_CHUNK_BYTES;  /* f64 [32]: products of the batch being folded */
+constexpr unsigned WL_OFF_KEY = WL_OFF_VALUE + 32 * 8;                                  /* u32 [queue]: owner lane << 27 | barcode index */
+constexpr unsigned WL_OFF_OWN = WL_OFF_KEY + WHITELIST_QUEUE * 4;                       /* u32 [32]: batch slots that belong to every lane's read */
+constexpr unsigned WL_OFF_OBSERVATION = WL_OFF_OWN + 32 * 4;                            /* u32 [3][32]: low plane, high plane, no-call mask of every lane's read */
+constexpr unsigned WL_OFF_MBARRIER = WL_OFF_OBSERVATION + 3 * 32 * 4;                   /* u64 [WHITELIST_STAGES] */
+constexpr unsigned WL_WARP_BYTES = (WL_OFF_MBARRIER + WHITELIST_STAGES * 8 + 255u) / 256u * 256u;
+constexpr unsigned WL_FIXED_BYTES = 256u * 8u + 256u;                                   /* Phred tables, counters */
+static_assert(WHITELIST_CHUNK == 128 && WHITELIST_BLOCKS == 4, "the fast path is written out for groups of four blocks");
+static_assert(WHITELIST_CHUNK_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+static_assert((WHITELIST_QUEUE & (WHITELIST_QUEUE - 1)) == 0 && WHITELIST_QUEUE >= 64, "queue positions are masked");
 
 __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
     asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));        /* a ^ b ^ c */
@@ -1016,33 +1032,43 @@ __device__ __forceinline__ uint32_t count_reaches_sixteen(const uint32_t (&e)[16
     return majority(f0, f1, b3);
 }
 
-/* block U of the current group: the 16 planes this lane selects (immediate offsets from its cursors), then the count */
-template < int U >
-__device__ __forceinline__ uint32_t whitelist_block(const uint32_t (&cursor)[WHITELIST_POSITIONS], uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
-    uint32_t e[WHITELIST_POSITIONS];
+/*  Product of the mismatch ratios of `owner`'s read over the mismatch set m: eight groups of two positions, entry
+    e = 4 * group + subset of owner o at table + e * 256 + ((o + e) & 31) * 8, so that the entries of one read
+    spread over the banks (pooled candidates often share a read) and one entry of all reads is conflict free.
+    Fixed association (((T0 T1) T2) ...) T7: equal mismatch sets give bit-equal products. */
+__device__ __forceinline__ double whitelist_product(uint32_t table, uint32_t owner, uint32_t m) {
+    double t = 1.0;
     #pragma unroll
-    for(int j = 0; j < WHITELIST_POSITIONS; ++j) {
-        asm volatile("ld.shared.u32 %0, [%1 + %2];" : "=r"(e[j]) : "r"(cursor[j]), "n"(U * WHITELIST_POSITIONS * WHITELIST_PLANES * 4));
+    for(int g = 0; g < 8; ++g) {
+        const uint32_t e = 4u * g + ((m >> (2 * g)) & 3u);
+        double value;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(value) : "r"(table + e * 256u + ((owner + e) & 31u) * 8u));
+        t = g == 0 ? value : t * value;
     }
-    return count_reaches_sixteen(e, b0, b1, b2, b3);
+    return t;
 }
 
-__global__ void __launch_bounds__(WHITELIST_WARPS * WARP_SIZE, 1)
-pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
-    constexpr int G = 4;
+__global__ void __launch_bounds__(WHITELIST_MAX_WARPS * WARP_SIZE, 1)
+pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* const work_counter) {
     extern __shared__ __align__(256) unsigned char smem[];
-    unsigned char* const stage = smem;
-    double* const phred = reinterpret_cast< double* >(smem + 2 * WHITELIST_CHUNK_BYTES);
-    uint32_t* const misc = reinterpret_cast< uint32_t* >(phred + 256);
-    uint64_t* const mbarrier = reinterpret_cast< uint64_t* >(misc + 4);
+    double* const phred = reinterpret_cast< double* >(smem);
+    uint32_t* const misc = reinterpret_cast< uint32_t* >(smem + 256 * 8);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    unsigned char* const mine = smem + WL_FIXED_BYTES + static_cast< size_t >(warp) * WL_WARP_BYTES;
+    double* const value = reinterpret_cast< double* >(mine + WL_OFF_VALUE);
+    uint32_t* const queue_key = reinterpret_cast< uint32_t* >(mine + WL_OFF_KEY);
+    uint32_t* const own = reinterpret_cast< uint32_t* >(mine + WL_OFF_OWN);
+    uint32_t* const observation = reinterpret_cast< uint32_t* >(mine + WL_OFF_OBSERVATION);
+    uint64_t* const mbarrier = reinterpret_cast< uint64_t* >(mine + WL_OFF_MBARRIER);
+    const uint32_t table = shared_address(mine + WL_OFF_TABLE);
+    const uint32_t ring = shared_address(mine + WL_OFF_RING);
+
     for(int i = tid; i < 256; i += blockDim.x) { phred[i] = P.phred[i]; }
     if(tid < 4) { misc[tid] = 0; }
-    if(tid == 0) {
-        mbarrier_init(&mbarrier[0], 1);
-        mbarrier_init(&mbarrier[1], 1);
+    if(lane == 0) {
+        for(int s = 0; s < WHITELIST_STAGES; ++s) { mbarrier_init(&mbarrier[s], 1); }
         fence_mbarrier_init();
     }
     __syncthreads();
@@ -1050,55 +1076,58 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
     accumulator.shared_u32 = nullptr; accumulator.shared_f64 = nullptr;
     accumulator.global_u64 = P.acc_u64; accumulator.global_f64 = P.acc_f64;
 
-    const uint32_t window = shared_address(smem);
-    const uint32_t aligned_tables = ((window + whitelist_fixed_bytes() - 4096u + 4095u) & ~4095u) - window;
-    double* const table = reinterpret_cast< double* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * 16 * WARP_SIZE) + lane;
-    const uint32_t table_base = shared_address(table);
     const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
     const int L = P.nucleotide_cardinality;
-    const int chunk_cardinality = P.whitelist_chunks;
+    const int group_cardinality = P.whitelist_chunks;
     const double tolerance_per_barcode = WHITELIST_TOLERANCE / static_cast< double >(P.barcode_cardinality);
+    const long long unit_cardinality = (A.n_reads + 31) / 32;
+    /* the ring: groups are copied and consumed in one running order; the stage and the mbarrier phase of the next
+       group to consume and of the next one to copy are carried along */
+    unsigned consume_stage = 0, consume_phase = 0, copy_stage = 0;
 
-    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
-    const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * chunk_cardinality;
-    unsigned iteration = 0;
-    auto issue = [&](unsigned it) {
-        const unsigned buffer = chunk_cardinality == 1 ? 0u : (it & 1u);
-        const unsigned chunk = it % static_cast< unsigned >(chunk_cardinality);
-        mbarrier_expect_tx(&mbarrier[buffer], WHITELIST_CHUNK_BYTES);
-        tma_bulk_load(stage + buffer * WHITELIST_CHUNK_BYTES, P.whitelist + static_cast< size_t >(chunk) * WHITELIST_CHUNK_BYTES, WHITELIST_CHUNK_BYTES, &mbarrier[buffer]);
-    };
-    if(tid == 0 && total_iterations > 0) { issue(0); }
-    const bool resident = chunk_cardinality == 1;
-    if(resident && total_iterations > 0) { mbarrier_wait(&mbarrier[0], 0); }
-
-    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
-    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
-        const long long r = tile * blockDim.x + tid;
+    while(true) {
+        /* ---- the next 32 reads */
+        unsigned unit = 0;
+        if(lane == 0) { unit = atomicAdd(work_counter, 1u); }
+        unit = __shfl_sync(FULL_MASK, unit, 0);
+        if(unit >= unit_cardinality) { break; }
+        const long long r = static_cast< long long >(unit) * 32 + lane;
         const bool valid = r < A.n_reads;
-        const ObservedRead< G > observed = upcoming;
-        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        /* start the table stream before the per-read work */
+        auto issue = [&](int group) {           /* every lane keeps copy_stage; lane 0 starts the copy */
+            if(lane == 0) {
+                mbarrier_expect_tx(&mbarrier[copy_stage], WHITELIST_CHUNK_BYTES);
+                tma_bulk_load(mine + WL_OFF_RING + copy_stage * WHITELIST_CHUNK_BYTES, P.whitelist + static_cast< size_t >(group) * WHITELIST_CHUNK_BYTES, WHITELIST_CHUNK_BYTES, &mbarrier[copy_stage]);
+            }
+            copy_stage = copy_stage + 1 == WHITELIST_STAGES ? 0u : copy_stage + 1;
+        };
+        __syncwarp();
+        for(int g = 0; g < WHITELIST_STAGES - 1 && g < group_cardinality; ++g) { issue(g); }
+
+        const ObservedRead< 4 > observed = fetch_read< 4 >(A, r);
         const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
         uint32_t qcfail = observed.qcfail;
-        uint32_t quality[G];
+        uint32_t quality[4];
         #pragma unroll
-        for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
+        for(int g = 0; g < 4; ++g) { quality[g] = decode_quality< 4 >(A, observed.raw, g); }
+        observation[lane] = o_lo;
+        observation[32 + lane] = o_hi;
+        observation[64 + lane] = nmask;
 
-        /* ---- per-read constant P0, subset product tables, high quality mask; the plane every position selects */
+        /* ---- per-read constant P0, subset product table, high quality mask; the plane every position selects */
         double base_probability = 1.0;
         uint32_t high_quality_mask = 0;
         int uniform_positions = 0;
-        uint32_t plane[WHITELIST_POSITIONS];        /* word offset of the lane's plane inside a block */
-        double counted_ratio[WHITELIST_POSITIONS];  /* the ratio of a counted position, 2 (above every ratio that counts) otherwise */
-        double loose = 1.0;                         /* product of the ratios above 1 */
+        uint32_t plane_address[WHITELIST_POSITIONS];    /* shared address of the lane's plane of position j in stage 0, block 0 */
+        double counted_ratio[WHITELIST_POSITIONS];      /* the ratio of a counted position, 2 (above every ratio that counts) otherwise */
+        double loose = 1.0;                             /* product of the ratios above 1 */
         #pragma unroll
-        for(int g = 0; g < G; ++g) {
-            double w[4];
+        for(int g = 0; g < 8; ++g) {
+            double w[2];
             #pragma unroll
-            for(int k = 0; k < 4; ++k) {
-                const int j = g * 4 + k;
-                const uint32_t q = (quality[g] >> (8 * k)) & 0xffu;
+            for(int k = 0; k < 2; ++k) {
+                const int j = g * 2 + k;
+                const uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
                 if(static_cast< int >(q) >= P.high_quality_threshold) { high_quality_mask |= 1u << j; }
                 const bool ambiguous = (nmask >> j) & 1u;
                 const PositionFactor f = position_factor(phred, uniform_factor, q, ambiguous);
@@ -1107,31 +1136,17 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
                 w[k] = f.ratio;
                 const bool counted = valid && !ambiguous && j < L && f.ratio < 1.0;
                 const uint32_t code = ((o_lo >> j) & 1u) | (((o_hi >> j) & 1u) << 1);
-                plane[j] = static_cast< uint32_t >(j * WHITELIST_PLANES) + (counted ? code : 4u);
+                plane_address[j] = ring + (static_cast< uint32_t >(j * WHITELIST_PLANES) + (counted ? code : 4u)) * 16u;
                 counted_ratio[j] = counted ? f.ratio : 2.0;
                 if(f.ratio > 1.0) { loose *= f.ratio; }
             }
-            double* const t = table + g * 16 * WARP_SIZE;
-            const double w01 = w[0] * w[1];
-            const double w02 = w[0] * w[2];
-            const double w12 = w[1] * w[2];
-            const double w012 = w01 * w[2];
-            t[0 * WARP_SIZE] = 1.0;
-            t[1 * WARP_SIZE] = w[0];
-            t[2 * WARP_SIZE] = w[1];
-            t[3 * WARP_SIZE] = w01;
-            t[4 * WARP_SIZE] = w[2];
-            t[5 * WARP_SIZE] = w02;
-            t[6 * WARP_SIZE] = w12;
-            t[7 * WARP_SIZE] = w012;
-            t[8 * WARP_SIZE] = w[3];
-            t[9 * WARP_SIZE] = w[0] * w[3];
-            t[10 * WARP_SIZE] = w[1] * w[3];
-            t[11 * WARP_SIZE] = w01 * w[3];
-            t[12 * WARP_SIZE] = w[2] * w[3];
-            t[13 * WARP_SIZE] = w02 * w[3];
-            t[14 * WARP_SIZE] = w12 * w[3];
-            t[15 * WARP_SIZE] = w012 * w[3];
+            const double both = w[0] * w[1];
+            #pragma unroll
+            for(int e = 0; e < 4; ++e) {
+                const uint32_t entry = 4u * g + e;
+                const double v = e == 0 ? 1.0 : (e == 1 ? w[0] : (e == 2 ? w[1] : both));
+                asm volatile("st.shared.f64 [%0], %1;" :: "r"(table + entry * 256u + ((static_cast< uint32_t >(lane) + entry) & 31u) * 8u), "d"(v) : "memory");
+            }
         }
         high_quality_mask &= (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
 
@@ -1163,9 +1178,6 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
                 bound[c] = running;
             }
         }
-        uint32_t plane_address[WHITELIST_POSITIONS];
-        #pragma unroll
-        for(int j = 0; j < WHITELIST_POSITIONS; ++j) { plane_address[j] = window + plane[j] * 4u; }
         int limit = counted_positions;
         double limit_bound = bound[limit];
         double threshold = 0.0;                     /* min(best / 2, tolerance share of the rest of sigma_p): only ever grows */
@@ -1184,66 +1196,110 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
 
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
-        for(int chunk = 0; chunk < chunk_cardinality; ++chunk) {
-            const unsigned buffer = resident ? 0u : (iteration & 1u);
-            if(!resident) {
-                if(tid == 0 && iteration + 1 < total_iterations) { issue(iteration + 1); }
-                mbarrier_wait(&mbarrier[buffer], (iteration >> 1) & 1u);
+        unsigned head = 0, tail = 0;            /* candidates evaluated / appended so far (warp uniform) */
+
+        /*  Evaluate candidates [head, head + n) of the queue, one per lane, and let every read fold its own in, in the
+            order they were appended (= barcode order). The barcode word and prior come from the table in L2 (one
+            16-byte load per lane and batch); match.any finds the slots that share a read. */
+        auto process = [&](unsigned n) {
+            const bool active = static_cast< unsigned >(lane) < n;
+            uint32_t owner = 32u + lane;
+            if(active) {
+                const uint32_t key = queue_key[(head + lane) & (WHITELIST_QUEUE - 1)];
+                owner = key >> 27;
+                const uint4 raw = *reinterpret_cast< const uint4* >(P.barcodes + (key & 0x7ffffffu));
+                const uint32_t m = mismatch_mask(observation[owner], observation[32 + owner], observation[64 + owner], raw.x, raw.y);
+                value[lane] = whitelist_product(table, owner, m) * __hiloint2double(raw.w, raw.z);
             }
-            const uint32_t* const equality = reinterpret_cast< const uint32_t* >(stage + buffer * WHITELIST_CHUNK_BYTES);
-            const uint2* const word = reinterpret_cast< const uint2* >(equality + WHITELIST_EQUALITY_WORDS);
-            const double* const prior = reinterpret_cast< const double* >(word + WHITELIST_CHUNK);
-            const int first = chunk * WHITELIST_CHUNK;
-            /* this lane's plane addresses inside the chunk: the only per-lane address arithmetic of the fast path */
-            uint32_t cursor[WHITELIST_POSITIONS];
-            #pragma unroll
-            for(int j = 0; j < WHITELIST_POSITIONS; ++j) { cursor[j] = plane_address[j] + buffer * WHITELIST_CHUNK_BYTES; }
-            const int live = P.barcode_cardinality - first < WHITELIST_CHUNK ? P.barcode_cardinality - first : WHITELIST_CHUNK;
-            const int group_cardinality = (live + 32 * WHITELIST_GROUP - 1) / (32 * WHITELIST_GROUP);
-            #pragma unroll 1
-            for(int group = 0; group < group_cardinality; ++group) {
-                uint32_t pass[WHITELIST_GROUP];
-                uint32_t any = 0;
-                static_assert(WHITELIST_GROUP == 4, "the fast path is written out for four blocks per trip");
-                pass[0] = whitelist_block< 0 >(cursor, b0, b1, b2, b3) | take_all;
-                pass[1] = whitelist_block< 1 >(cursor, b0, b1, b2, b3) | take_all;
-                pass[2] = whitelist_block< 2 >(cursor, b0, b1, b2, b3) | take_all;
-                pass[3] = whitelist_block< 3 >(cursor, b0, b1, b2, b3) | take_all;
-                any = (pass[0] | pass[1]) | (pass[2] | pass[3]);
-                #pragma unroll
-                for(int j = 0; j < WHITELIST_POSITIONS; ++j) { cursor[j] += WHITELIST_GROUP * WHITELIST_POSITIONS * WHITELIST_PLANES * 4; }
-                if(__any_sync(FULL_MASK, (any & valid_mask) != 0u)) {
-                    const int previous = limit;
-                    int u = 0;
-                    uint32_t pending = pass[0] & valid_mask;
-                    while(true) {
-                        #pragma unroll
-                        for(int v = 1; v < WHITELIST_GROUP; ++v) {
-                            if(pending == 0u && u < v) { u = v; pending = pass[v] & valid_mask; }
-                        }
-                        if(pending == 0u) { break; }
-                        const int k = __ffs(static_cast< int >(pending)) - 1;
-                        pending &= pending - 1u;
-                        const int i = (group * WHITELIST_GROUP + u) * 32 + k;
-                        const uint2 raw = word[i];
-                        const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
-                        const double p = subset_product< G >(table_base, m) * prior[i];
-                        if(p < threshold) {
-                            /* below half the maximum: not the winner, not a tie, and too small to move the threshold */
-                            selection.rest += p;
-                        } else {
-                            select_one(selection, p, first + i);
-                            threshold = fmin(0.5 * selection.best, tolerance_per_barcode * (noise_term + selection.rest));
-                            while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
-                        }
-                    }
-                    if(limit != previous) { set_limit(); }
+            own[lane] = 0u;
+            __syncwarp();
+            const unsigned peers = __match_any_sync(FULL_MASK, owner);
+            if(active) { own[owner] = peers; }
+            __syncwarp();
+            unsigned pending = own[lane];
+            while(pending != 0u) {
+                const int e = __ffs(static_cast< int >(pending)) - 1;
+                pending &= pending - 1u;
+                const double p = value[e];
+                if(p < threshold) {
+                    /* below half the maximum: not the winner, not a tie, and too small to move the threshold */
+                    selection.rest += p;
+                } else {
+                    select_one(selection, p, static_cast< int >(queue_key[(head + e) & (WHITELIST_QUEUE - 1)] & 0x7ffffffu));
+                    threshold = fmin(0.5 * selection.best, tolerance_per_barcode * (noise_term + selection.rest));
+                    while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
                 }
             }
-            if(!resident) {
-                __syncthreads();
-                ++iteration;
+            head += n;
+            __syncwarp();
+        };
+
+        for(int group = 0; group < group_cardinality; ++group) {
+            /* keep the ring full: the stage freed by the previous group receives group + stages - 1 */
+            if(group + WHITELIST_STAGES - 1 < group_cardinality) { issue(group + WHITELIST_STAGES - 1); }
+            mbarrier_wait(&mbarrier[consume_stage], consume_phase);
+            const int first = group * WHITELIST_CHUNK;
+
+            /* ---- fast path: one 16-byte load per position covers the four blocks of the group */
+            uint32_t pass[4];
+            {
+                const uint32_t stage_offset = consume_stage * WHITELIST_CHUNK_BYTES;
+                uint32_t e0[WHITELIST_POSITIONS], e1[WHITELIST_POSITIONS], e2[WHITELIST_POSITIONS], e3[WHITELIST_POSITIONS];
+                #pragma unroll
+                for(int j = 0; j < WHITELIST_POSITIONS; ++j) {
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0[j]), "=r"(e1[j]), "=r"(e2[j]), "=r"(e3[j]) : "r"(plane_address[j] + stage_offset));
+                }
+                pass[0] = (count_reaches_sixteen(e0, b0, b1, b2, b3) | take_all) & valid_mask;
+                pass[1] = (count_reaches_sixteen(e1, b0, b1, b2, b3) | take_all) & valid_mask;
+                pass[2] = (count_reaches_sixteen(e2, b0, b1, b2, b3) | take_all) & valid_mask;
+                pass[3] = (count_reaches_sixteen(e3, b0, b1, b2, b3) | take_all) & valid_mask;
             }
+            consume_stage = consume_stage + 1 == WHITELIST_STAGES ? 0u : consume_stage + 1;
+            consume_phase ^= consume_stage == 0 ? 1u : 0u;
+
+            /* ---- append the candidates of all lanes to the queue: every read's in barcode order, positions by a
+               prefix sum over the lanes (no divergent work but the short loop that writes the keys) */
+            unsigned long long low = (static_cast< unsigned long long >(pass[1]) << 32) | pass[0];
+            unsigned long long high = (static_cast< unsigned long long >(pass[3]) << 32) | pass[2];
+            const int previous = limit;
+            while(true) {
+                const int pending = __popcll(low) + __popcll(high);
+                int inclusive = pending;
+                #pragma unroll
+                for(int step = 1; step < 32; step <<= 1) {
+                    const int other = __shfl_up_sync(FULL_MASK, inclusive, step);
+                    if(lane >= step) { inclusive += other; }
+                }
+                const int total = __shfl_sync(FULL_MASK, inclusive, 31);
+                if(total == 0) { break; }
+                const int space = WHITELIST_QUEUE - static_cast< int >(tail - head);
+                const int offset = inclusive - pending;
+                int take = space - offset;
+                take = take < 0 ? 0 : (take > pending ? pending : take);
+                for(int j = 0; j < take; ++j) {
+                    const bool from_low = low != 0ull;
+                    unsigned long long bits = from_low ? low : high;
+                    const int i = __ffsll(static_cast< long long >(bits)) - 1 + (from_low ? 0 : 64);
+                    bits &= bits - 1ull;
+                    if(from_low) { low = bits; } else { high = bits; }
+                    queue_key[(tail + offset + j) & (WHITELIST_QUEUE - 1)] = (static_cast< uint32_t >(lane) << 27) | static_cast< uint32_t >(first + i);
+                }
+                const int appended = total < space ? total : space;
+                tail += static_cast< unsigned >(appended);
+                __syncwarp();
+                while(tail - head >= 32u || (appended < total && tail != head)) {
+                    process(tail - head < 32u ? tail - head : 32u);
+                }
+                if(appended == total) { break; }
+            }
+            if(limit != previous) { set_limit(); }
+            __syncwarp();       /* the stage is free for the copy the next trip issues */
+        }
+        /* ---- what is left in the queue */
+        {
+            const int previous = limit;
+            while(tail != head) { process(tail - head < 32u ? tail - head : 32u); }
+            if(limit != previous) { set_limit(); }
         }
 
         /* ---- structural ties are queued for pamld_tie_kernel, everything else is decided here (as pamld_kernel) */
@@ -1266,7 +1322,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
                 record.nmask = nmask;
                 record.read = static_cast< uint32_t >(r);
                 #pragma unroll
-                for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
+                for(int g = 0; g < 8; ++g) { record.quality[g] = g < 4 ? quality[g < 4 ? g : 0] : 0u; }
                 P.tie_record[at] = record;
             }
         }
@@ -1274,7 +1330,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A) {
         if(decided) {
             const BarcodeEntry e = P.barcodes[selection.index];
             const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, e.lo, e.hi);
-            const double t = subset_product< G >(table_base, m);
+            const double t = whitelist_product(table, static_cast< uint32_t >(lane), m);
             const Verdict v = pamld_decide(P, accumulator, &misc[3], selection.index, m, t, e.prior, selection.rest, base_probability,
                                            uniform_positions == L, high_quality_mask, qcfail);
             qcfail = v.qcfail;
@@ -1335,11 +1391,13 @@ __device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, do
 /* warps per CTA of the tie kernel: its per-warp workspace is static shared memory (48 KB limit) */
 __host__ __device__ constexpr int tie_warps(int G) { return G <= 4 ? 8 : 4; }
 constexpr int TIE_STAGE_ENTRIES = 1024;
-constexpr int TIE_READS = 4;                    /* reads per warp: eight lanes each */
-constexpr int TIE_LANES = WARP_SIZE / TIE_READS;
+/* reads per warp: four (eight lanes each) for the small codecs, one (all 32 lanes) when the table is long, where the
+   scan over the barcodes is what takes the time and there are few queued reads to fill the machine with */
+constexpr int TIE_READS_SMALL = 4;
+constexpr int TIE_LONG_TABLE = 8192;
 
 /* per warp scratch of the tie kernel */
-template < int G >
+template < int G, int TIE_READS >
 struct TieWorkspace {
     double table[TIE_READS][G * 16];            /* linear subset product tables */
     double match_value[TIE_READS][G * 4];       /* per position substitution lookup when the base matches (phred.cpp:39-72) */
@@ -1351,13 +1409,14 @@ struct TieWorkspace {
     uint32_t o_lo[TIE_READS], o_hi[TIE_READS], nmask[TIE_READS];
 };
 
-template < int G >
+template < int G, int TIE_READS >
 __global__ void __launch_bounds__(tie_warps(G) * WARP_SIZE, 3)
 pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
+    constexpr int TIE_LANES = WARP_SIZE / TIE_READS;
     extern __shared__ __align__(16) unsigned char tie_smem[];   /* barcode table when it fits TIE_STAGE_ENTRIES */
     __shared__ double phred_shared[PHRED_TABLE_SIZE];
     constexpr int TIE_WARPS = tie_warps(G);
-    __shared__ TieWorkspace< G > workspace[TIE_WARPS];
+    __shared__ TieWorkspace< G, TIE_READS > workspace[TIE_WARPS];
     __shared__ uint32_t block_counter[4];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -1387,7 +1446,7 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     const int L = P.nucleotide_cardinality;
     const double uniform_quality = phred_shared[PHRED_UNIFORM_QUALITY];
     const double base = phred_shared[PHRED_BASE];
-    TieWorkspace< G >& W = workspace[warp];
+    TieWorkspace< G, TIE_READS >& W = workspace[warp];
     const unsigned stride = gridDim.x * TIE_WARPS * TIE_READS;
 
     for(unsigned first_item = (blockIdx.x * TIE_WARPS + warp) * TIE_READS; first_item < tie_cardinality; first_item += stride) {
@@ -1406,7 +1465,9 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
             const int j = sub + step * TIE_LANES;
             if(j >= G * 4) { break; }
             /* word j >> 2 = 2 * step + (sub >> 2): picked with a select so the record stays in registers */
-            const uint32_t word = (sub & 4) ? record.quality[(2 * step + 1) < 8 ? (2 * step + 1) : 7] : record.quality[2 * step < 8 ? 2 * step : 7];
+            uint32_t word = record.quality[0];
+            #pragma unroll
+            for(int g = 1; g < 8; ++g) { if((j >> 2) == g) { word = record.quality[g]; } }
             uint32_t q = live ? (word >> (8 * (j & 3))) & 0xffu : 0u;
             q = q > 127u ? 127u : q;
             const bool ambiguous = (nmask >> j) & 1u;
@@ -1835,6 +1896,18 @@ count_kernel(const DecoderParams P, const TileArguments A) {
     }
 }
 
+/* the tie pass over the reads the scan queued; the queue length is only known on the device: a fixed grid strides over it */
+template < int G >
+cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
+    if(params.barcode_cardinality >= TIE_LONG_TABLE) {
+        pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+    } else {
+        pamld_tie_kernel< G, TIE_READS_SMALL ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+    }
+    return cudaGetLastError();
+}
+
 template < int G >
 cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     const SharedPlan plan = make_plan(params.barcode_cardinality, true);
@@ -1853,10 +1926,7 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
     pamld_kernel< G ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
-    /* the queue length is only known on the device: a fixed grid strides over it */
-    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
-    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
-    return cudaGetLastError();
+    return launch_tie< G >(params, tile, geometry, stream);
 }
 
 /* the combinatorial scan: staging area = the grid blob instead of the barcode table */
@@ -1884,9 +1954,7 @@ cudaError_t launch_pamld_grid_as(const DecoderParams& params, const TileArgument
     pamld_grid_kernel< LA, LB, W, KBP, UNIFORM ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
-    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
-    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
-    return cudaGetLastError();
+    return launch_tie< G >(params, tile, geometry, stream);
 }
 template < int LA, int LB, bool DENSE >
 cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
@@ -1900,25 +1968,22 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
 
 static cudaError_t launch_pamld_whitelist(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     constexpr int G = 4;
-    const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double);
-    const size_t fixed = whitelist_fixed_bytes();
-    if(fixed + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
-    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - fixed) / per_warp);
-    warps = warps > WHITELIST_WARPS ? WHITELIST_WARPS : warps;
-    const size_t bytes = fixed + per_warp * warps;
+    if(WL_FIXED_BYTES + WL_WARP_BYTES > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - WL_FIXED_BYTES) / WL_WARP_BYTES);
+    warps = warps > WHITELIST_MAX_WARPS ? WHITELIST_MAX_WARPS : warps;
+    const size_t bytes = WL_FIXED_BYTES + static_cast< size_t >(WL_WARP_BYTES) * warps;
     cudaError_t status = cudaFuncSetAttribute(pamld_whitelist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
     if(status != cudaSuccess) { return status; }
-    const int threads = warps * WARP_SIZE;
-    const long long tiles = (tile.n_reads + threads - 1) / threads;
-    const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
-    status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
+    const long long units = (tile.n_reads + 31) / 32;
+    const long long wanted = (units + warps - 1) / warps;
+    const int grid = static_cast< int >(wanted < geometry.multiprocessor_count ? wanted : geometry.multiprocessor_count);
+    /* the queue header: [0] tie queue length, [1] the next unit of 32 reads */
+    status = cudaMemsetAsync(params.tie_count, 0, 2 * sizeof(unsigned), stream);
     if(status != cudaSuccess) { return status; }
-    pamld_whitelist_kernel<<< grid, threads, bytes, stream >>>(params, tile);
+    pamld_whitelist_kernel<<< grid, warps * WARP_SIZE, bytes, stream >>>(params, tile, params.tie_count + 1);
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
-    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
-    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
-    return cudaGetLastError();
+    return launch_tie< G >(params, tile, geometry, stream);
 }
 
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {

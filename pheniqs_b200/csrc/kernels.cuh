@@ -61,18 +61,19 @@ __host__ __device__ inline uint32_t mdd_hash(uint32_t key_lo, uint32_t key_hi) {
 }
 
 /*  Whitelist blob (pamld_whitelist_kernel; large single-word codecs such as a 737 K x 16 nt cellular whitelist).
-    The table is cut into chunks of WHITELIST_CHUNK barcodes, each one contiguous so that ONE TMA bulk copy stages it:
-      equality planes  [block of 32 barcodes][position 0..15][code A, C, G, T, "not counted"] u32 — bit k of
-                       plane (block, j, c) is set when barcode 32 * block + k has base c at position j; the
-                       fifth plane is all ones (positions a read does not count read it)
-      words            [WHITELIST_CHUNK] {low plane, high plane} of every barcode (the exact path)
-      priors           [WHITELIST_CHUNK] f64 (0 for the padding of the last chunk: such entries never win) */
-constexpr int WHITELIST_CHUNK = 512;
+    The table is cut into groups of WHITELIST_CHUNK barcodes, each one contiguous so that ONE TMA bulk copy stages it:
+      equality planes  [position 0..15][code A, C, G, T, "not counted"][block of 32 barcodes] u32 — bit k of
+                       plane (j, c, block) is set when barcode 32 * block + k has base c at position j; the
+                       fifth plane is all ones (positions a read does not count read it); the four blocks of a
+                       (position, code) are one 16-byte load
+    The exact path reads the barcode word and prior of a candidate from `barcodes`; the padding of the last group
+    has no plane bit set, so it is never a candidate. */
+constexpr int WHITELIST_CHUNK = 128;
 constexpr int WHITELIST_POSITIONS = 16;
 constexpr int WHITELIST_PLANES = 5;
 constexpr int WHITELIST_BLOCKS = WHITELIST_CHUNK / 32;
 constexpr int WHITELIST_EQUALITY_WORDS = WHITELIST_BLOCKS * WHITELIST_POSITIONS * WHITELIST_PLANES;
-constexpr int WHITELIST_CHUNK_BYTES = WHITELIST_EQUALITY_WORDS * 4 + WHITELIST_CHUNK * 8 + WHITELIST_CHUNK * 8;
+constexpr int WHITELIST_CHUNK_BYTES = WHITELIST_EQUALITY_WORDS * 4;
 constexpr int WHITELIST_MINIMUM_BARCODES = 4096;    /* smaller codecs use the exhaustive scans (PHQ_WHITELIST_MINIMUM overrides, for tests) */
 
 /* what the scan kernel hands to the tie kernel for a queued read */
