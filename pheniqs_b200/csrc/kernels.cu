@@ -981,8 +981,9 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
    not hold a CTA back), streams the table through a private three-stage ring of TMA bulk copies (one 3.3 KB
    group per stage, completion on the warp's own mbarriers) and never meets a CTA-wide barrier. */
 constexpr int WHITELIST_STAGES = 4;
-constexpr int WHITELIST_QUEUE = 64;             /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
-constexpr int WHITELIST_MAX_WARPS = 12;
+constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
+constexpr int WHITELIST_WORDS = 256;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 4 x 32); expanded up to 32 at a time */
+constexpr int WHITELIST_MAX_WARPS = 13;
 constexpr double WHITELIST_TOLERANCE = 5.9604644775390625e-08;     /* 2^-24 */
 
 /* per-warp shared memory of pamld_whitelist_kernel */
@@ -990,7 +991,8 @@ constexpr unsigned WL_OFF_TABLE = 0;                                            
 constexpr unsigned WL_OFF_RING = 8192;                                                  /* WHITELIST_STAGES groups of equality planes */
 constexpr unsigned WL_OFF_VALUE = WL_OFF_RING + WHITELIST_STAGES * WHITELIST_CHUNK_BYTES;  /* f64 [32]: products of the batch being folded */
 constexpr unsigned WL_OFF_KEY = WL_OFF_VALUE + 32 * 8;                                  /* u32 [queue]: owner lane << 27 | barcode index */
-constexpr unsigned WL_OFF_OWN = WL_OFF_KEY + WHITELIST_QUEUE * 4;                       /* u32 [32]: batch slots that belong to every lane's read */
+constexpr unsigned WL_OFF_WORD = WL_OFF_KEY + WHITELIST_QUEUE * 4;                      /* uint2 [words]: pass word, lane | block << 5 */
+constexpr unsigned WL_OFF_OWN = WL_OFF_WORD + WHITELIST_WORDS * 8;                      /* u32 [32]: batch slots that belong to every lane's read */
 constexpr unsigned WL_OFF_OBSERVATION = WL_OFF_OWN + 32 * 4;                            /* u32 [3][32]: low plane, high plane, no-call mask of every lane's read */
 constexpr unsigned WL_OFF_MBARRIER = WL_OFF_OBSERVATION + 3 * 32 * 4;                   /* u64 [WHITELIST_STAGES] */
 constexpr unsigned WL_WARP_BYTES = (WL_OFF_MBARRIER + WHITELIST_STAGES * 8 + 255u) / 256u * 256u;
@@ -1059,6 +1061,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
     unsigned char* const mine = smem + WL_FIXED_BYTES + static_cast< size_t >(warp) * WL_WARP_BYTES;
     double* const value = reinterpret_cast< double* >(mine + WL_OFF_VALUE);
     uint32_t* const queue_key = reinterpret_cast< uint32_t* >(mine + WL_OFF_KEY);
+    uint2* const queue_word = reinterpret_cast< uint2* >(mine + WL_OFF_WORD);
     uint32_t* const own = reinterpret_cast< uint32_t* >(mine + WL_OFF_OWN);
     uint32_t* const observation = reinterpret_cast< uint32_t* >(mine + WL_OFF_OBSERVATION);
     uint64_t* const mbarrier = reinterpret_cast< uint64_t* >(mine + WL_OFF_MBARRIER);
@@ -1198,10 +1201,12 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
         unsigned head = 0, tail = 0;            /* candidates evaluated / appended so far (warp uniform) */
 
-        /*  Evaluate candidates [head, head + n) of the queue, one per lane, and let every read fold its own in, in the
-            order they were appended (= barcode order). The barcode word and prior come from the table in L2 (one
-            16-byte load per lane and batch); match.any finds the slots that share a read. */
+        /*  Evaluate candidates [head, head + n) of the queue, one per lane (the barcode word and prior come from the
+            table in L2: one 16-byte load per lane and batch), then every read's lane folds its own in, in the order
+            they were appended (= barcode order); match.any finds the slots that share a read. All loops run a warp
+            uniform number of trips with predicated bodies, so the lanes stay converged. */
         auto process = [&](unsigned n) {
+            __syncwarp();
             const bool active = static_cast< unsigned >(lane) < n;
             uint32_t owner = 32u + lane;
             if(active) {
@@ -1217,21 +1222,65 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
             if(active) { own[owner] = peers; }
             __syncwarp();
             unsigned pending = own[lane];
-            while(pending != 0u) {
-                const int e = __ffs(static_cast< int >(pending)) - 1;
-                pending &= pending - 1u;
-                const double p = value[e];
-                if(p < threshold) {
-                    /* below half the maximum: not the winner, not a tie, and too small to move the threshold */
-                    selection.rest += p;
-                } else {
-                    select_one(selection, p, static_cast< int >(queue_key[(head + e) & (WHITELIST_QUEUE - 1)] & 0x7ffffffu));
-                    threshold = fmin(0.5 * selection.best, tolerance_per_barcode * (noise_term + selection.rest));
-                    while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
+            const unsigned trips = __reduce_max_sync(FULL_MASK, static_cast< unsigned >(__popc(pending)));
+            for(unsigned trip = 0; trip < trips; ++trip) {
+                if(pending != 0u) {
+                    const int e = __ffs(static_cast< int >(pending)) - 1;
+                    pending &= pending - 1u;
+                    const double p = value[e];
+                    if(p < threshold) {
+                        /* below half the maximum: not the winner, not a tie, and too small to move the threshold */
+                        selection.rest += p;
+                    } else {
+                        select_one(selection, p, static_cast< int >(queue_key[(head + e) & (WHITELIST_QUEUE - 1)] & 0x7ffffffu));
+                        threshold = fmin(0.5 * selection.best, tolerance_per_barcode * (noise_term + selection.rest));
+                        while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
+                    }
                 }
+                __syncwarp();
             }
             head += n;
             __syncwarp();
+        };
+
+        /*  Second level of the compaction. The fast path leaves a 32 x 128 bit matrix per group with a handful of
+            bits set; its non-empty words are appended to `queue_word` with one ballot per block (no loop at all),
+            and 32 words at a time are expanded here into candidate keys: one word per lane, positions by a prefix
+            sum, a warp uniform number of trips (a word rarely holds more than two candidates). Words are queued in
+            (block, lane) order and bits expanded in order, so every read's candidates stay in barcode order. */
+        unsigned word_head = 0, word_tail = 0;
+        auto expand = [&](unsigned n) {         /* expands as many of the next n <= 32 words as the candidate queue has room for (at least one) */
+            while(tail - head >= 32u) { process(32u); }
+            __syncwarp();
+            uint32_t bits = 0u, tag = 0u;
+            if(static_cast< unsigned >(lane) < n) {
+                const uint2 entry = queue_word[(word_head + lane) & (WHITELIST_WORDS - 1)];
+                bits = entry.x; tag = entry.y;
+            }
+            const int pending = __popc(bits);
+            int inclusive = pending;
+            #pragma unroll
+            for(int step = 1; step < 32; step <<= 1) {
+                const int other = __shfl_up_sync(FULL_MASK, inclusive, step);
+                if(lane >= step) { inclusive += other; }
+            }
+            /* fewer than 32 candidates are waiting, so the first word always fits: space >= queue - 31 >= 32 */
+            const int space = WHITELIST_QUEUE - static_cast< int >(tail - head);
+            const unsigned fitting = __ballot_sync(FULL_MASK, static_cast< unsigned >(lane) < n && inclusive <= space);
+            const unsigned words = static_cast< unsigned >(__popc(fitting));      /* inclusive is monotonic: a prefix of the lanes */
+            const bool mine_fits = (fitting >> lane) & 1u;
+            const int total = __shfl_sync(FULL_MASK, inclusive, static_cast< int >(words) - 1);
+            const int offset = inclusive - pending;
+            const int trips = __reduce_max_sync(FULL_MASK, mine_fits ? pending : 0);
+            for(int j = 0; j < trips; ++j) {
+                if(mine_fits && bits != 0u) {
+                    const int k = __ffs(static_cast< int >(bits)) - 1;
+                    bits &= bits - 1u;
+                    queue_key[(tail + offset + j) & (WHITELIST_QUEUE - 1)] = ((tag & 31u) << 27) | ((tag >> 5) * 32u + k);
+                }
+            }
+            tail += static_cast< unsigned >(total);
+            word_head += words;
         };
 
         for(int group = 0; group < group_cardinality; ++group) {
@@ -1257,47 +1306,31 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
             consume_stage = consume_stage + 1 == WHITELIST_STAGES ? 0u : consume_stage + 1;
             consume_phase ^= consume_stage == 0 ? 1u : 0u;
 
-            /* ---- append the candidates of all lanes to the queue: every read's in barcode order, positions by a
-               prefix sum over the lanes (no divergent work but the short loop that writes the keys) */
-            unsigned long long low = (static_cast< unsigned long long >(pass[1]) << 32) | pass[0];
-            unsigned long long high = (static_cast< unsigned long long >(pass[3]) << 32) | pass[2];
+            /* ---- first level of the compaction: the non-empty pass words, one ballot per block */
             const int previous = limit;
-            while(true) {
-                const int pending = __popcll(low) + __popcll(high);
-                int inclusive = pending;
-                #pragma unroll
-                for(int step = 1; step < 32; step <<= 1) {
-                    const int other = __shfl_up_sync(FULL_MASK, inclusive, step);
-                    if(lane >= step) { inclusive += other; }
+            #pragma unroll
+            for(int u = 0; u < 4; ++u) {
+                const bool some = pass[u] != 0u;
+                const unsigned lanes = __ballot_sync(FULL_MASK, some);
+                if(lanes != 0u) {
+                    if(some) {
+                        queue_word[(word_tail + static_cast< unsigned >(__popc(lanes & ((1u << lane) - 1u)))) & (WHITELIST_WORDS - 1)] =
+                            make_uint2(pass[u], static_cast< uint32_t >(lane) | (static_cast< uint32_t >(group * 4 + u) << 5));
+                    }
+                    word_tail += static_cast< unsigned >(__popc(lanes));
                 }
-                const int total = __shfl_sync(FULL_MASK, inclusive, 31);
-                if(total == 0) { break; }
-                const int space = WHITELIST_QUEUE - static_cast< int >(tail - head);
-                const int offset = inclusive - pending;
-                int take = space - offset;
-                take = take < 0 ? 0 : (take > pending ? pending : take);
-                for(int j = 0; j < take; ++j) {
-                    const bool from_low = low != 0ull;
-                    unsigned long long bits = from_low ? low : high;
-                    const int i = __ffsll(static_cast< long long >(bits)) - 1 + (from_low ? 0 : 64);
-                    bits &= bits - 1ull;
-                    if(from_low) { low = bits; } else { high = bits; }
-                    queue_key[(tail + offset + j) & (WHITELIST_QUEUE - 1)] = (static_cast< uint32_t >(lane) << 27) | static_cast< uint32_t >(first + i);
-                }
-                const int appended = total < space ? total : space;
-                tail += static_cast< unsigned >(appended);
-                __syncwarp();
-                while(tail - head >= 32u || (appended < total && tail != head)) {
-                    process(tail - head < 32u ? tail - head : 32u);
-                }
-                if(appended == total) { break; }
             }
+            #pragma unroll 1
+            while(word_tail - word_head >= 32u) { expand(32u); }
             if(limit != previous) { set_limit(); }
             __syncwarp();       /* the stage is free for the copy the next trip issues */
         }
-        /* ---- what is left in the queue */
+        /* ---- what is left in the queues */
         {
             const int previous = limit;
+            #pragma unroll 1
+            while(word_tail != word_head) { expand(word_tail - word_head < 32u ? word_tail - word_head : 32u); }
+            #pragma unroll 1
             while(tail != head) { process(tail - head < 32u ? tail - head : 32u); }
             if(limit != previous) { set_limit(); }
         }
