@@ -127,6 +127,14 @@ typedef struct {
     JSON (same keys as the reference's --compile output for those sections) is returned in a
     buffer the caller releases with phq_free. Host only; no GPU needed. */
 int phq_compile_job(const char* job_json, char** compiled_json);
+/*  The job document at `path` with the documents its "import" list names merged underneath it, depth first, each
+    path relative to the importing document and visited once (Job::load_instruction_with_import, job.cpp:160-224).
+    phq_compile_job then resolves `base` references between the decoders of the "decoder" repository and from the
+    sample / molecular / cellular decoders into it (Transcode::apply_inheritance, transcode.cpp:328-442), values
+    the "<topic>:decoder" / "<topic>:barcode" projections from the job root and the decoder
+    (Transcode::compile_topic, transcode.cpp:769-823; configuration.json:423-501) and infers PU / ID of every
+    barcode (transcode.cpp:1224-1260), so an unmodified reference job file can be fed in. Host only. */
+int phq_load_job(const char* path, char** job_json);
 void phq_free(void* pointer);
 /* message of the last failure of a call that had no handle to attach it to (calling thread) */
 const char* phq_last_global_error(void);

@@ -5,6 +5,6 @@ kernels for sm_100a in pheniqs_b200/csrc). This package is the thin host-side la
 the tests and the benchmark; importing it never builds or substitutes anything.
 """
 from .binding import ConfigurationError, PheniqsError, LIBRARY_PATH  # noqa: F401
-from .decoder import DecoderChain, compile_job, adjust_job, shard_range, all_reduce_accumulators, RESULT_DTYPE, COMPACT_DTYPE  # noqa: F401
+from .decoder import DecoderChain, compile_job, load_job, adjust_job, shard_range, all_reduce_accumulators, RESULT_DTYPE, COMPACT_DTYPE  # noqa: F401
 
 __version__ = "0.1.0"

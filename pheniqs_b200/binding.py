@@ -66,7 +66,7 @@ class Result(C.Structure):
 
 
 EXPORTS = (
-    "phq_compile_job", "phq_free", "phq_last_global_error", "phq_create", "phq_destroy", "phq_last_error",
+    "phq_compile_job", "phq_load_job", "phq_free", "phq_last_global_error", "phq_create", "phq_destroy", "phq_last_error",
     "phq_decoder_count", "phq_decoder_describe", "phq_pack", "phq_decode_batch", "phq_decode_batch_compact",
     "phq_decode_batch_device", "phq_decode_batch_device_compact", "phq_decode_batch_raw", "phq_decode_batch_raw_compact",
     "phq_decode_batch_raw_tags", "phq_tag_record_bytes",
@@ -90,6 +90,7 @@ def library() -> C.CDLL:
     lib = C.CDLL(LIBRARY_PATH)
     P = C.POINTER
     lib.phq_compile_job.argtypes = [C.c_char_p, P(C.c_void_p)]
+    lib.phq_load_job.argtypes = [C.c_char_p, P(C.c_void_p)]
     lib.phq_free.argtypes = [C.c_void_p]
     lib.phq_free.restype = None
     lib.phq_last_global_error.restype = C.c_char_p

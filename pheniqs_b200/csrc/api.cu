@@ -659,6 +659,22 @@ int phq_compile_job(const char* job_json, char** compiled_json) {
     catch(const std::exception& e) { global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
 }
 
+int phq_load_job(const char* path, char** job_json) {
+    if(path == NULL || job_json == NULL) { global_error = "Internal error : illegal argument"; return PHQ_INTERNAL_ERROR; }
+    *job_json = NULL;
+    try {
+        std::set< std::string > visited;
+        const Json job(load_job_with_import(path, visited));
+        const std::string text(job.dump(-1, 4));
+        *job_json = static_cast< char* >(malloc(text.size() + 1));
+        if(*job_json == NULL) { global_error = "Out of memory error"; return PHQ_OUT_OF_MEMORY_ERROR; }
+        memcpy(*job_json, text.c_str(), text.size() + 1);
+        return PHQ_OK;
+    } catch(const phq::Error& e) { global_error = e.what(); return e.code; }
+    catch(const JsonError& e) { global_error = std::string("Configuration error : ") + e.what(); return PHQ_CONFIGURATION_ERROR; }
+    catch(const std::exception& e) { global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
+}
+
 int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
     phq_handle* h(NULL);
     try {

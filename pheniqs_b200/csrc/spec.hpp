@@ -380,6 +380,182 @@ inline std::vector< DecoderSpec > parse_compiled_job(const Json& job) {
     return chain;
 }
 
+/* ------------------------------------------------------------------ job level JSON semantics of the reference */
+
+/* merge_json_value (json.cpp:780-803): members of `base` the ontology lacks are copied in, common objects recurse, the ontology wins */
+inline void merge_json(const Json& base, Json& ontology) {
+    if(base.is_null()) { return; }
+    if(ontology.is_null()) { ontology = base; return; }
+    if(!base.is_object()) { return; }
+    if(!ontology.is_object()) { throw ConfigurationError("element is not a dictionary"); }
+    for(const auto& m : base.members()) {
+        Json* found(ontology.find(m.first));
+        if(found != NULL) {
+            try { merge_json(m.second, *found); }
+            catch(ConfigurationError& e) { throw ConfigurationError(m.first + " " + (e.what() + strlen("Configuration error : "))); }
+        } else {
+            ontology.set(m.first, m.second);
+        }
+    }
+}
+/* project_json_value (json.cpp:804-832): the keys of `base`, valued from the ontology where it has them */
+inline Json project_json(const Json& base, const Json& ontology) {
+    Json container;
+    if(!base.is_null() && !ontology.is_null() && base.is_object()) {
+        if(ontology.is_object()) {
+            container = Json::object();
+            for(const auto& m : base.members()) {
+                const Json* element(ontology.find(m.first));
+                container.set(m.first, element != NULL ? project_json(m.second, *element) : m.second);
+            }
+        } else if(ontology.is_array()) {
+            container = Json::array();
+            for(const auto& e : ontology.items()) { container.push(project_json(base, e)); }
+        }
+    }
+    if(!ontology.is_null() && container.is_null()) { container = ontology; }
+    return container;
+}
+/* clean_json_value (json.cpp:833-874): false, empty strings, empty containers and nulls disappear */
+inline void clean_json(Json& v) {
+    if(v.is_bool()) { if(!v.as_bool()) { v = Json(); } }
+    else if(v.is_string()) { if(v.as_string().empty()) { v = Json(); } }
+    else if(v.is_object()) {
+        Json clean(Json::object());
+        for(auto& m : v.members()) {
+            Json child(m.second);
+            clean_json(child);
+            if(!child.is_null()) { clean.set(m.first, child); }
+        }
+        v = clean.members().empty() ? Json() : clean;
+    } else if(v.is_array()) {
+        Json clean(Json::array());
+        for(auto& e : v.items()) {
+            Json child(e);
+            clean_json(child);
+            if(!child.is_null()) { clean.push(child); }
+        }
+        v = clean.items().empty() ? Json() : clean;
+    }
+}
+
+/*  Transcode::apply_inheritance (transcode.cpp:328-442): `base` references between the decoders of the job's
+    `decoder` repository are resolved from the roots down, then the sample / molecular / cellular decoders inherit
+    from the repository, and the repository is dropped. */
+inline int32_t inheritance_depth(const std::string& key, Json& repository, std::map< std::string, int32_t >& depth) {
+    auto known(depth.find(key));
+    if(known != depth.end()) { return known->second; }
+    Json* value(repository.find(key));
+    if(value == NULL || value->is_null()) { throw ConfigurationError("referencing an unknown parent " + key); }
+    int32_t d(0);
+    const std::string base(value->is_object() ? get_string(*value, "base") : std::string());
+    if(!base.empty()) {
+        if(base == key) { throw ConfigurationError(key + " references itself as parent"); }
+        d = inheritance_depth(base, repository, depth) + 1;
+    }
+    depth[key] = d;
+    return d;
+}
+inline void apply_decoder_inheritance(Json& value, const Json* repository) {
+    if(!value.is_object()) { return; }
+    const std::string base(get_string(value, "base"));
+    if(!base.empty() && repository != NULL) {
+        const Json* parent(repository->find(base));
+        if(parent == NULL) { throw ConfigurationError("reference to an unknown base " + base); }
+        merge_json(*parent, value);
+    }
+    value.erase("base");
+    clean_json(value);
+}
+inline void apply_inheritance(Json& job) {
+    Json* repository(job.find("decoder"));
+    if(repository != NULL && repository->is_object()) {
+        std::map< std::string, int32_t > depth;
+        int32_t deepest(0);
+        for(const auto& m : repository->members()) {
+            if(!m.second.is_null()) { deepest = std::max(deepest, inheritance_depth(m.first, *repository, depth)); }
+        }
+        for(int32_t level(1); level <= deepest; ++level) {
+            for(const auto& record : depth) {
+                if(record.second != level) { continue; }
+                Json* value(repository->find(record.first));
+                const std::string base(get_string(*value, "base"));
+                if(!base.empty()) {
+                    const Json parent(repository->at(base));
+                    merge_json(parent, *value);
+                    value->erase("base");
+                }
+            }
+        }
+    }
+    const char* name[3] = { "sample", "molecular", "cellular" };
+    for(int t(0); t < 3; ++t) {
+        Json* e(job.find(name[t]));
+        if(e == NULL || e->is_null()) { continue; }
+        try {
+            if(e->is_object()) { apply_decoder_inheritance(*e, repository); }
+            else if(e->is_array()) { for(auto& d : e->items()) { apply_decoder_inheritance(d, repository); } }
+        } catch(ConfigurationError& error) {
+            throw ConfigurationError(std::string(name[t]) + " decoder : " + (error.what() + strlen("Configuration error : ")));
+        }
+    }
+    if(repository != NULL) { job.erase("decoder"); }
+}
+
+/* the "<topic>:decoder" and "<topic>:barcode" projections (configuration.json:423-501) */
+inline Json decoder_template(const char* topic) {
+    Json t(Json::object());
+    const bool sample(strcmp(topic, "sample") == 0);
+    if(sample) { for(const char* k : { "CN", "DT", "LB", "PG", "PI", "PL", "PM", "SM" }) { t.set(k, Json()); } }
+    t.set("algorithm", Json::string(strcmp(topic, "molecular") == 0 ? "naive" : "pamld"));
+    t.set("codec", Json());
+    t.set("confidence threshold", Json::number(0.95));
+    t.set("corrected quality", Json());
+    t.set("distance tolerance", Json());
+    if(sample) { t.set("flowcell id", Json()); t.set("flowcell lane number", Json()); }
+    t.set("high quality distance threshold", Json::integer(0));
+    t.set("high quality threshold", Json::integer(30));
+    t.set("noise", Json::number(0.01));
+    t.set("quality masking threshold", Json::integer(0));
+    t.set("segment cardinality", Json::integer(0));
+    t.set("undetermined", Json());
+    return t;
+}
+inline Json barcode_template(const char* topic) {
+    Json t(Json::object());
+    const bool sample(strcmp(topic, "sample") == 0);
+    if(sample) { for(const char* k : { "CN", "DT", "LB", "PG", "PI", "PL", "PM", "SM" }) { t.set(k, Json()); } }
+    t.set("algorithm", Json());
+    t.set("concentration", Json::integer(1));
+    if(sample) { t.set("flowcell id", Json()); t.set("flowcell lane number", Json()); }
+    t.set("segment cardinality", Json());
+    return t;
+}
+/* Transcode::infer_PU / infer_ID (transcode.cpp:1224-1260): PU = [flowcell id:[lane:]]barcode, ID = PU, unless given */
+inline void infer_platform_unit(Json& container, bool undetermined) {
+    if(get_string(container, "PU").empty()) {
+        std::string suffix;
+        if(!undetermined) {
+            const Json* barcode(container.find("barcode"));
+            if(barcode != NULL && barcode->is_array()) { for(const auto& segment : barcode->items()) { suffix += segment.as_string(); } }
+        } else { suffix = "undetermined"; }
+        if(!suffix.empty()) {
+            std::string buffer(get_string(container, "flowcell id"));
+            if(!buffer.empty()) {
+                buffer.push_back(':');
+                const Json* lane(container.find("flowcell lane number"));
+                if(lane != NULL && lane->is_number()) { buffer += std::to_string(lane->as_int()); buffer.push_back(':'); }
+            }
+            buffer += suffix;
+            container.set("PU", Json::string(buffer));
+        }
+    }
+    if(get_string(container, "ID").empty()) {
+        const std::string unit(get_string(container, "PU"));
+        if(!unit.empty()) { container.set("ID", Json::string(unit)); }
+    }
+}
+
 /* ------------------------------------------------------------------ job compile (decoder sections only) */
 
 /* WordMetric::find_shannon_bound over the distinct words of one segment (metric.h:87-111) */
@@ -402,22 +578,18 @@ inline int32_t shannon_bound(const std::set< std::string >& words, int32_t lengt
     return (minimum - 1) / 2;
 }
 
-inline Json compile_decoder(const Json& directive, const char* topic, int32_t index) {
+inline Json compile_decoder(const Json& directive, const char* topic, int32_t index, const Json& default_decoder, const Json& default_barcode) {
     if(!directive.is_object()) { throw ConfigurationError("decoder element must be a dictionary"); }
-    /* defaults: configuration.json:423-501 (projection <topic>:decoder) and :368-376 */
-    Json value(Json::object());
-    value.set("algorithm", Json::string(strcmp(topic, "molecular") == 0 ? "naive" : "pamld"));
-    value.set("confidence threshold", Json::number(0.95));
-    value.set("corrected quality", Json::integer(30));
-    value.set("high quality distance threshold", Json::integer(0));
-    value.set("high quality threshold", Json::integer(30));
-    value.set("noise", Json::number(0.01));
-    value.set("quality masking threshold", Json::integer(0));
-    value.set("multiplexing classifier", Json::boolean(false));
-    for(const auto& m : directive.members()) {
-        if(!m.second.is_null()) { value.set(m.first, m.second); }      /* merge_json_value: the directive wins; clean removes nulls */
-    }
+    /* Transcode::compile_decoder (transcode.cpp:937-966): overlay on the default decoder (the "<topic>:decoder"
+       projection valued from the job root, transcode.cpp:769-790), then clean */
+    Json value(directive);
     value.set("index", Json::integer(index));
+    merge_json(default_decoder, value);
+    clean_json(value);
+    /* the default barcode of this codec: the "<topic>:barcode" projection valued from the decoder */
+    Json default_codec_barcode(project_json(default_barcode, value));
+    clean_json(default_codec_barcode);
+    if(default_codec_barcode.is_null()) { default_codec_barcode = Json::object(); }
     const int32_t algorithm(algorithm_from_string(get_string(value, "algorithm")));
 
     std::vector< int32_t > barcode_length;
@@ -469,13 +641,14 @@ inline Json compile_decoder(const Json& directive, const char* topic, int32_t in
     const double noise(get_double(value, "noise"));
     {
         Json undetermined(value.has("undetermined") ? value.at("undetermined") : Json::object());
+        merge_json(default_codec_barcode, undetermined);
         Json barcode(Json::array());
         for(int32_t n : barcode_length) { barcode.push(Json::string(std::string(static_cast< size_t >(n), '='))); }
         undetermined.set("barcode", barcode);
         undetermined.set("segment cardinality", Json::integer(segment_cardinality));
         undetermined.set("index", Json::integer(0));
+        infer_platform_unit(undetermined, true);
         undetermined.set("concentration", Json::number(noise));
-        if(!undetermined.has("ID")) { undetermined.set("ID", Json::string("undetermined")); }
         value.set("undetermined", undetermined);
     }
 
@@ -490,6 +663,7 @@ inline Json compile_decoder(const Json& directive, const char* topic, int32_t in
         for(auto& record : codec.members()) {
             Json& element(record.second);
             if(!element.is_object()) { throw ConfigurationError("codec element " + record.first + " must be a dictionary"); }
+            merge_json(default_codec_barcode, element);
             const Json* barcode(element.find("barcode"));
             if(barcode == NULL || !barcode->is_array()) { throw ConfigurationError("barcode " + record.first + " has no barcode array"); }
             if(static_cast< int32_t >(barcode->items().size()) != segment_cardinality) {
@@ -510,7 +684,7 @@ inline Json compile_decoder(const Json& directive, const char* topic, int32_t in
             element.set("index", Json::integer(barcode_index++));
             element.set("segment cardinality", Json::integer(segment_cardinality));
             element.set("BC", Json::string(hyphenated));
-            if(!element.has("ID")) { element.set("ID", Json::string(hyphenated)); }
+            infer_platform_unit(element, false);
             double concentration(element.has("concentration") ? get_double(element, "concentration") : 1.0);    /* <topic>:barcode projection */
             if(!(concentration >= 0)) { throw ConfigurationError("barcode concentration must be a positive number"); }
             element.set("concentration", Json::number(concentration));
@@ -558,27 +732,92 @@ inline Json compile_decoder(const Json& directive, const char* topic, int32_t in
     return value;
 }
 
-inline Json compile_job(const Json& job) {
-    if(!job.is_object()) { throw ConfigurationError("job element must be a dictionary"); }
+inline Json compile_job(const Json& directive) {
+    if(!directive.is_object()) { throw ConfigurationError("job element must be a dictionary"); }
+    Json job(directive);
+    apply_inheritance(job);
+    /* the job level defaults this path consumes (configuration.json "default") */
+    if(!job.has("corrected quality")) { job.set("corrected quality", Json::integer(30)); }
     Json out(Json::object());
     const char* name[3] = { "sample", "molecular", "cellular" };
     for(int t(0); t < 3; ++t) {
         const Json* e(job.find(name[t]));
         if(e == NULL || e->is_null()) { continue; }
+        /* Transcode::compile_topic (transcode.cpp:769-823): defaults are the projections valued from the job root */
+        const Json default_decoder(project_json(decoder_template(name[t]), job));
+        const Json default_barcode(barcode_template(name[t]));
         try {
             if(e->is_object()) {
-                out.set(name[t], compile_decoder(*e, name[t], 0));
+                out.set(name[t], compile_decoder(*e, name[t], 0, default_decoder, default_barcode));
             } else if(e->is_array()) {
                 Json list(Json::array());
                 int32_t index(0);
-                for(const auto& d : e->items()) { list.push(compile_decoder(d, name[t], index++)); }
+                for(const auto& d : e->items()) { list.push(compile_decoder(d, name[t], index++, default_decoder, default_barcode)); }
                 out.set(name[t], list);
             } else { throw ConfigurationError("decoder element must be a dictionary or an array"); }
         } catch(ConfigurationError& error) {
             throw ConfigurationError(std::string(name[t]) + " decoder : " + (error.what() + strlen("Configuration error : ")));
         }
     }
+    /*  Transcode::find_multiplexing_decoder (transcode.cpp:1120-1222): the decoder that mentions `output` (on itself, its
+        undetermined element or a codec element) routes reads to channels; when none does, the sample decoder. */
+    {
+        auto mentions_output = [](const Json& d) {
+            if(d.find("output") != NULL) { return true; }
+            const Json* u(d.find("undetermined"));
+            if(u != NULL && u->is_object() && u->find("output") != NULL) { return true; }
+            const Json* codec(d.find("codec"));
+            if(codec != NULL && codec->is_object()) {
+                for(const auto& record : codec->members()) { if(record.second.is_object() && record.second.find("output") != NULL) { return true; } }
+            }
+            return false;
+        };
+        std::vector< Json* > candidate;
+        for(int t(0); t < 3; ++t) {
+            Json* e(out.find(name[t]));
+            if(e == NULL) { continue; }
+            if(e->is_object()) { if(mentions_output(*e)) { candidate.push_back(e); } }
+            else { for(auto& d : e->items()) { if(mentions_output(d)) { candidate.push_back(&d); } } }
+        }
+        if(candidate.size() > 1) { throw ConfigurationError("multiple multiplexing classifier candidates found"); }
+        Json* chosen(candidate.empty() ? out.find("sample") : candidate.front());
+        if(chosen != NULL && chosen->is_object()) { chosen->set("multiplexing classifier", Json::boolean(true)); }
+    }
     return out;
+}
+
+/*  Job::load_instruction_with_import (job.cpp:160-224): the document at `path` with the documents its `import`
+    list names merged underneath it, depth first; an import path is relative to the importing document and a
+    document is only visited once. */
+inline Json load_job_with_import(const std::string& path, std::set< std::string >& visited) {
+    FILE* const file(fopen(path.c_str(), "rb"));
+    if(file == NULL) { throw ConfigurationError("unable to read instruction file from " + path); }
+    std::string text;
+    char buffer[1 << 16];
+    size_t got;
+    while((got = fread(buffer, 1, sizeof(buffer), file)) > 0) { text.append(buffer, got); }
+    fclose(file);
+    Json document(Json::parse(text));
+    if(!document.is_object()) { throw ConfigurationError("instruction " + path + " is not a dictionary"); }
+    visited.insert(path);
+    const Json* import(document.find("import"));
+    if(import != NULL && import->is_array()) {
+        const size_t slash(path.find_last_of('/'));
+        const std::string directory(slash == std::string::npos ? std::string() : path.substr(0, slash + 1));
+        Json aggregated;
+        for(const auto& record : import->items()) {
+            std::string target(record.as_string());
+            if(target.empty()) { continue; }
+            if(target[0] != '/') { target = directory + target; }
+            if(visited.count(target)) { continue; }
+            Json imported(load_job_with_import(target, visited));
+            merge_json(aggregated, imported);
+            aggregated = imported;
+        }
+        merge_json(aggregated, document);
+    }
+    document.erase("import");
+    return document;
 }
 
 }   /* namespace phq */

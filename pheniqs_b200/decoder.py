@@ -39,6 +39,17 @@ def compile_job(job) -> dict:
         lib.phq_free(out)
 
 
+def load_job(path: str) -> dict:
+    """The job file at `path` with its imports merged in (phq_load_job; Job::load_instruction_with_import). Host only."""
+    lib = library()
+    out = C.c_void_p()
+    check(lib.phq_load_job(str(path).encode(), C.byref(out)))
+    try:
+        return json.loads(C.string_at(out).decode())
+    finally:
+        lib.phq_free(out)
+
+
 def adjust_job(job, report, precision: int = 15, text: bool = False):
     """The prior adjusted job (phq_adjust_job): tool/pheniqs-prior-api.py:39-56 / classifier.h:125-160. Host only."""
     lib = library()

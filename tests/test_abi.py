@@ -166,3 +166,46 @@ def test_pack_reproduces_rule_apply(short):
     with pytest.raises(ConfigurationError):
         noisy = [rng.integers(0, 40, size=q.shape).astype(np.uint8) for q in quality]
         DecoderChain(compiled, device=-1).pack(code, noisy, offset, quality_bits=2)
+
+
+def test_job_file_with_import_and_base_compiles_like_the_reference():
+    """the reference's own test job (test/BDGGG/BDGGG_annotated.json, which imports
+    BDGGG_interleave.json and inherits its decoders from the `decoder` repository through `base`) loaded with
+    phq_load_job and compiled with phq_compile_job gives the decoder sections of the reference's own compile output
+    (test/BDGGG/valid/compile_annotated.out -> tests/golden/bdggg_compiled.json): every key and value, barcode
+    index, normalised concentration, read group ID / PU, Shannon bound and default tolerance. The keys of the
+    multiplexer (output, TC, base output url: not on this path) are the only ones left out."""
+    import json
+    import os
+    from pheniqs_b200 import compile_job, load_job
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    job = load_job(os.path.join(golden, "bdggg_import", "BDGGG_annotated.json"))
+    assert "import" not in job and job["flowcell id"] == "BDGGG" and "BDGGG_sample" in job["decoder"]
+    compiled = compile_job(job)
+    expected = json.load(open(os.path.join(golden, "bdggg_compiled.json")))
+    outside = {"output", "TC", "base output url"}
+
+    def same(mine, theirs, path):
+        if isinstance(theirs, dict):
+            assert isinstance(mine, dict), path
+            assert set(mine) == set(theirs) - outside, "%s: %s" % (path, sorted(set(mine) ^ (set(theirs) - outside)))
+            for key in mine:
+                same(mine[key], theirs[key], path + "/" + key)
+        elif isinstance(theirs, list):
+            assert isinstance(mine, list) and len(mine) == len(theirs), path
+            for i, (a, b) in enumerate(zip(mine, theirs)):
+                same(a, b, "%s[%d]" % (path, i))
+        elif isinstance(theirs, float):
+            assert abs(mine - theirs) <= 1e-12 * max(1.0, abs(theirs)), path     # the golden is printed with 15 decimals
+        else:
+            assert mine == theirs, path
+    same(compiled, expected, "")
+
+
+def test_inheritance_errors():
+    import pytest
+    from pheniqs_b200 import ConfigurationError, compile_job
+    with pytest.raises(ConfigurationError):
+        compile_job({"sample": {"base": "nowhere", "transform": {"token": ["0::8"]}}, "decoder": {"a": {"noise": 0.1}}})
+    with pytest.raises(ConfigurationError):
+        compile_job({"decoder": {"a": {"base": "a"}}, "sample": {"base": "a", "transform": {"token": ["0::8"]}}})
