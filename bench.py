@@ -401,6 +401,17 @@ def main():
             line["e2e_raw"] = {"value": raw_value, "unit": UNIT, "h2d_bytes_per_step": int(sum(2 * g[3] * m for g in raw if g is not None)), "d2h_bytes_per_step": int(d2h),
                                "reads_per_gpu_per_step": m, "steps": e2e_steps,
                                "call": "phq_decode_batch_raw_compact (FASTQ bytes of the barcode segments in, packed on the device; 8-byte records out)"}
+            # e2e_tags: the same bytes in, the BAM auxiliary block of every read out (RG BC QT XB ... as Read::flush and
+            # Auxiliary::encode write them) + the qcfail byte: phq_decode_batch_raw_tags
+            stride = chain.tag_record_bytes()
+            aux_buffer = torch.zeros((m, stride), dtype=torch.uint8).pin_memory()
+            length_buffer = torch.zeros(m, dtype=torch.int32).pin_memory()
+            flag_buffer = torch.zeros(m, dtype=torch.uint8).pin_memory()
+            keep += [aux_buffer, length_buffer, flag_buffer]
+            tags_value = time_host(lambda: chain.decode_raw_tags(segments, m, 33, None, stride=stride, aux=aux_buffer.numpy(), aux_length=length_buffer.numpy(), qcfail_out=flag_buffer.numpy()))
+            line["e2e_tags"] = {"value": tags_value, "unit": UNIT, "h2d_bytes_per_step": int(sum(2 * g[3] * m for g in raw if g is not None)), "d2h_bytes_per_step": int(m * (stride + 5)),
+                                "reads_per_gpu_per_step": m, "steps": e2e_steps, "record_bytes": stride,
+                                "call": "phq_decode_batch_raw_tags (FASTQ bytes of the barcode segments in; the auxiliary block RG BC QT XB ... of every read + its length + qcfail out)"}
         del host_tiles, full_results, keep, raw
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

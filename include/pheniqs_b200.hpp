@@ -61,6 +61,15 @@ inline std::string compile_job(const std::string& job_json) {
     return compiled;
 }
 
+/* the job file with its imports merged underneath (Job::load_instruction_with_import, job.cpp:160-224) */
+inline std::string load_job(const std::string& path) {
+    char* out(NULL);
+    raise(phq_load_job(path.c_str(), &out), phq_last_global_error());
+    std::string job(out);
+    phq_free(out);
+    return job;
+}
+
 /* the prior adjusted job (tool/pheniqs-prior-api.py:39-56, classifier.h:125-160) */
 inline std::string adjust_job(const std::string& job_json, const std::string& report_json, int precision = 15) {
     char* out(NULL);
@@ -139,6 +148,18 @@ class BatchDecoder {
         void classify(int64_t n_reads, const std::vector< phq_tile >& tiles, const uint8_t* qcfail_in,
                       const std::vector< phq_result* >& results, uint8_t* qcfail_out) {
             check(phq_decode_batch(handle_, n_reads, tiles.data(), qcfail_in, results.data(), qcfail_out));
+        }
+        /* FASTQ bytes of the barcode bearing segments in; the BAM auxiliary block of every read out (Read::flush +
+           Auxiliary::encode, read.h:187-237, auxiliary.cpp:320-361): aux[r * stride .. + aux_length[r]) */
+        int32_t tag_record_bytes() {
+            int32_t bytes(0);
+            check(phq_tag_record_bytes(handle_, &bytes));
+            return bytes;
+        }
+        void classify_raw_tags(int64_t n_reads, const std::vector< phq_raw_segment >& segments, int32_t phred_offset, const uint8_t* qcfail_in,
+                               uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out) {
+            check(phq_decode_batch_raw_tags(handle_, n_reads, static_cast< int32_t >(segments.size()), segments.data(), phred_offset, qcfail_in,
+                                            aux, aux_stride, aux_length, qcfail_out, NULL));
         }
         /* device pointers, asynchronous on `stream` */
         void classify_device(int64_t n_reads, const std::vector< phq_tile >& tiles, uint8_t* qcfail, const std::vector< phq_result* >& results, void* stream) {

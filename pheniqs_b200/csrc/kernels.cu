@@ -483,8 +483,12 @@ __device__ __forceinline__ PositionFactor position_factor(const double* __restri
 }
 
 /* ------------------------------------------------------------------ PAMLD scan kernel */
+/* warps per CTA of the generic scan: as many as the per-warp tables (G x 4 KB) and the register file allow; short
+   barcodes leave room for more warps, which is what hides the latency of the dependent lookup -> multiply chains */
+__host__ __device__ constexpr int pamld_warps(int G) { return G <= 2 ? 20 : (G == 3 ? 16 : MAX_WARPS); }
+
 template < int G >
-__global__ void __launch_bounds__(MAX_WARPS * WARP_SIZE, 1)
+__global__ void __launch_bounds__(pamld_warps(G) * WARP_SIZE, 1)
 pamld_kernel(const DecoderParams P, const TileArguments A) {
     extern __shared__ __align__(256) unsigned char smem[];
     const BlockState S = block_prologue(smem, P, true);
@@ -1947,7 +1951,7 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
     const size_t per_warp = static_cast< size_t >(G) * 16 * WARP_SIZE * sizeof(double);
     if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
     int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
-    warps = warps > MAX_WARPS ? MAX_WARPS : warps;
+    warps = warps > pamld_warps(G) ? pamld_warps(G) : warps;
     const size_t bytes = plan.fixed_bytes + per_warp * warps;
     cudaError_t status = cudaFuncSetAttribute(pamld_kernel< G >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
     if(status != cudaSuccess) { return status; }

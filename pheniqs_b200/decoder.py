@@ -278,7 +278,8 @@ class DecoderChain:
         check(self.lib.phq_tag_record_bytes(self.handle, C.byref(value)), self.handle)
         return value.value
 
-    def decode_raw_tags(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, stride: int = 0, want_results: bool = False):
+    def decode_raw_tags(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, stride: int = 0, want_results: bool = False,
+                        aux=None, aux_length=None, qcfail_out=None):
         """phq_decode_batch_raw_tags: FASTQ bytes in, the BAM auxiliary block of every read out.
         Returns (aux uint8 [n_reads, stride], aux_length int32 [n_reads], qcfail uint8 [n_reads][, results])."""
         array = (RawSegment * max(len(segments), 1))()
@@ -293,9 +294,9 @@ class DecoderChain:
             keep.append((sequence, quality, offset))
             array[i] = RawSegment(sequence.ctypes.data, quality.ctypes.data, None if offset is None else offset.ctypes.data, int(length))
         stride = stride or self.tag_record_bytes()
-        aux = np.zeros((max(n_reads, 1), stride), dtype=np.uint8)
-        aux_length = np.zeros(max(n_reads, 1), dtype=np.int32)
-        qcfail_out = np.zeros(max(n_reads, 1), dtype=np.uint8)
+        aux = np.zeros((max(n_reads, 1), stride), dtype=np.uint8) if aux is None else aux
+        aux_length = np.zeros(max(n_reads, 1), dtype=np.int32) if aux_length is None else aux_length
+        qcfail_out = np.zeros(max(n_reads, 1), dtype=np.uint8) if qcfail_out is None else qcfail_out
         results = [np.zeros(n_reads, dtype=RESULT_DTYPE) if (want_results and info.has_tile) else None for info in self.info]
         pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
         qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
