@@ -220,22 +220,28 @@ __device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const 
     return s;
 }
 
+/* per-CTA accumulator tables -> global, one atomic per non-zero cell (call after a __syncthreads) */
+__device__ __forceinline__ void flush_accumulators(const Accumulator& accumulator, int rows, const DecoderParams& P) {
+    const int tid = threadIdx.x;
+    for(int i = tid; i < rows * ACC_U64_COLUMNS; i += blockDim.x) {
+        const int column = i % ACC_U64_COLUMNS;
+        unsigned long long v = accumulator.shared_u32[i];
+        /* split pairs (Accumulator): the total column also receives what went to its pass-filter column */
+        if(column == ACC_COUNT) { v += accumulator.shared_u32[i - ACC_COUNT + ACC_PF_COUNT]; }
+        if(column == ACC_DISTANCE) { v += accumulator.shared_u32[i - ACC_DISTANCE + ACC_PF_DISTANCE]; }
+        if(v) { atomicAdd(&P.acc_u64[i], v); }
+    }
+    for(int i = tid; i < rows * ACC_F64_COLUMNS; i += blockDim.x) {
+        double v = accumulator.shared_f64[i];
+        if(i % ACC_F64_COLUMNS == ACC_CONFIDENCE) { v += accumulator.shared_f64[i - ACC_CONFIDENCE + ACC_PF_CONFIDENCE]; }
+        if(v != 0.0) { atomicAdd(&P.acc_f64[i], v); }
+    }
+}
+
 __device__ __forceinline__ void block_epilogue(const BlockState& s, const DecoderParams& P) {
     __syncthreads();
     const int tid = threadIdx.x;
-    for(int i = tid; i < s.plan.accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) {
-        const int column = i % ACC_U64_COLUMNS;
-        unsigned long long v = s.accumulator.shared_u32[i];
-        /* split pairs (Accumulator): the total column also receives what went to its pass-filter column */
-        if(column == ACC_COUNT) { v += s.accumulator.shared_u32[i - ACC_COUNT + ACC_PF_COUNT]; }
-        if(column == ACC_DISTANCE) { v += s.accumulator.shared_u32[i - ACC_DISTANCE + ACC_PF_DISTANCE]; }
-        if(v) { atomicAdd(&P.acc_u64[i], v); }
-    }
-    for(int i = tid; i < s.plan.accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) {
-        double v = s.accumulator.shared_f64[i];
-        if(i % ACC_F64_COLUMNS == ACC_CONFIDENCE) { v += s.accumulator.shared_f64[i - ACC_CONFIDENCE + ACC_PF_CONFIDENCE]; }
-        if(v != 0.0) { atomicAdd(&P.acc_f64[i], v); }
-    }
+    flush_accumulators(s.accumulator, s.plan.accumulator_rows, P);
     if(tid < 2 && P.totals != nullptr && s.misc[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(s.misc[tid])); }
     if(tid >= 2 && tid < 4 && P.diagnostics != nullptr && s.misc[tid]) { atomicAdd(&P.diagnostics[tid - 2], static_cast< unsigned long long >(s.misc[tid])); }
 }
@@ -1428,6 +1434,9 @@ __device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, do
 /* warps per CTA of the tie kernel: its per-warp workspace is static shared memory (48 KB limit) */
 __host__ __device__ constexpr int tie_warps(int G) { return G <= 4 ? 8 : 4; }
 constexpr int TIE_STAGE_ENTRIES = 1024;
+/* rows of the tie kernel's per-CTA accumulator tables (N + 1), 0 when they stay in global memory; the kernel's static
+   shared memory (workspaces, Phred tables) leaves room for 300 rows next to the staged barcodes at three CTAs per SM */
+__host__ __device__ constexpr int tie_accumulator_rows(int N) { return N + 1 <= 300 ? N + 1 : 0; }
 /* reads per warp: four (eight lanes each) for the small codecs, one (all 32 lanes) when the table is long, where the
    scan over the barcodes is what takes the time and there are few queued reads to fill the machine with */
 constexpr int TIE_READS_SMALL = 4;
@@ -1473,13 +1482,22 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     }
     for(int i = tid; i < PHRED_TABLE_SIZE; i += blockDim.x) { phred_shared[i] = P.phred[i]; }
     if(tid < 4) { block_counter[tid] = 0; }
-    __syncthreads();
-
+    /* per-CTA accumulator tables behind the staged barcodes (small codecs): the queued reads of a batch hit a handful
+       of rows — the undetermined one above all — and global atomics on one address serialise */
+    const int accumulator_rows = tie_accumulator_rows(N);
     Accumulator accumulator;
     accumulator.shared_u32 = nullptr;
     accumulator.shared_f64 = nullptr;
     accumulator.global_u64 = P.acc_u64;
     accumulator.global_f64 = P.acc_f64;
+    if(accumulator_rows > 0) {
+        accumulator.shared_f64 = reinterpret_cast< double* >(tie_smem + static_cast< size_t >(N) * sizeof(BarcodeEntry));
+        accumulator.shared_u32 = reinterpret_cast< uint32_t* >(accumulator.shared_f64 + accumulator_rows * ACC_F64_COLUMNS);
+        for(int i = tid; i < accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) { accumulator.shared_f64[i] = 0.0; }
+        for(int i = tid; i < accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) { accumulator.shared_u32[i] = 0u; }
+    }
+    __syncthreads();
+
     const int L = P.nucleotide_cardinality;
     const double uniform_quality = phred_shared[PHRED_UNIFORM_QUALITY];
     const double base = phred_shared[PHRED_BASE];
@@ -1621,6 +1639,7 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     }
     __syncthreads();
     if(tid < 2 && P.totals != nullptr && block_counter[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(block_counter[tid])); }
+    if(accumulator_rows > 0) { flush_accumulators(accumulator, accumulator_rows, P); }
     if(tid == 3 && P.diagnostics != nullptr && block_counter[3]) { atomicAdd(&P.diagnostics[DIAG_THRESHOLD_BAND], static_cast< unsigned long long >(block_counter[3])); }
     if(tid == 2 && P.diagnostics != nullptr && blockIdx.x == 0 && tie_cardinality) { atomicAdd(&P.diagnostics[DIAG_EXACT_PATH], static_cast< unsigned long long >(tie_cardinality)); }
 }
@@ -1936,7 +1955,12 @@ count_kernel(const DecoderParams P, const TileArguments A) {
 /* the tie pass over the reads the scan queued; the queue length is only known on the device: a fixed grid strides over it */
 template < int G >
 cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
-    const size_t tie_bytes = params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0;
+    const size_t tie_bytes = (params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0)
+                           + static_cast< size_t >(tie_accumulator_rows(params.barcode_cardinality)) * (ACC_F64_COLUMNS * 8 + ACC_U64_COLUMNS * 4);
+    /* static + dynamic shared memory can pass the 48 KB a kernel gets without opting in */
+    cudaError_t status = cudaFuncSetAttribute(pamld_tie_kernel< G, 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024);
+    if(status == cudaSuccess) { status = cudaFuncSetAttribute(pamld_tie_kernel< G, TIE_READS_SMALL >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024); }
+    if(status != cudaSuccess) { return status; }
     if(params.barcode_cardinality >= TIE_LONG_TABLE) {
         pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     } else {
