@@ -981,8 +981,10 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
    `limit` is the largest count c whose bound can still matter: bound[c] >= min(best / 2,
    tolerance * (noise term + rest) / N). Everything below best / 2 cannot be the maximum or a tie; the N
-   barcodes together cannot add more than `tolerance` (2^-24) of the part of sigma_p that is not the winner, so
-   confidence and 1 - confidence move by less than 6e-8 relative, a sixteenth of the 1e-6 the path allows.
+   barcodes together cannot add more than `tolerance` (2^-21) of the part of sigma_p that is not the winner, so
+   confidence and 1 - confidence move by less than 4.8e-7 relative even if every barcode sat exactly at its bound
+   (half of the 1e-6 the path allows; the mass actually dropped is one to two orders below that, because only a
+   few percent of the barcodes are one mismatch beyond the limit).
    The bound only ever tightens (best and rest grow), so a stale limit is conservative. Positions that do not
    discriminate (N, quality 0, ratios >= 1 i.e. Phred < 3, positions past the barcode) are not counted: they
    select the all-ones plane, and ratios above 1 are folded into the bound.
@@ -994,7 +996,7 @@ constexpr int WHITELIST_STAGES = 4;
 constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
 constexpr int WHITELIST_WORDS = 256;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 4 x 32); expanded up to 32 at a time */
 constexpr int WHITELIST_MAX_WARPS = 13;
-constexpr double WHITELIST_TOLERANCE = 5.9604644775390625e-08;     /* 2^-24 */
+constexpr double WHITELIST_TOLERANCE = 4.76837158203125e-07;       /* 2^-21: half of the 1e-6 the path allows, as a worst case bound */
 
 /* per-warp shared memory of pamld_whitelist_kernel */
 constexpr unsigned WL_OFF_TABLE = 0;                                                    /* 32 entries x 256 B: subset products of 8 groups of 2 positions, lane skewed */
@@ -1233,21 +1235,26 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
             __syncwarp();
             unsigned pending = own[lane];
             const unsigned trips = __reduce_max_sync(FULL_MASK, static_cast< unsigned >(__popc(pending)));
+            const bool mine = pending != 0u;
+            double half_best = 0.5 * selection.best;
             for(unsigned trip = 0; trip < trips; ++trip) {
                 if(pending != 0u) {
                     const int e = __ffs(static_cast< int >(pending)) - 1;
                     pending &= pending - 1u;
                     const double p = value[e];
-                    if(p < threshold) {
-                        /* below half the maximum: not the winner, not a tie, and too small to move the threshold */
+                    if(p < half_best) {
+                        /* below half the maximum: neither the winner nor a tie, it only adds to the rest */
                         selection.rest += p;
                     } else {
                         select_one(selection, p, static_cast< int >(queue_key[(head + e) & (WHITELIST_QUEUE - 1)] & 0x7ffffffu));
-                        threshold = fmin(0.5 * selection.best, tolerance_per_barcode * (noise_term + selection.rest));
-                        while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
+                        half_best = 0.5 * selection.best;
                     }
                 }
-                __syncwarp();
+            }
+            if(mine) {
+                /* the threshold follows the maximum and the rest once per batch: it only grows, so the older one was conservative */
+                threshold = fmin(half_best, tolerance_per_barcode * (noise_term + selection.rest));
+                while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
             }
             head += n;
             __syncwarp();
