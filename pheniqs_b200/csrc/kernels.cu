@@ -1013,6 +1013,28 @@ static_assert(WHITELIST_CHUNK == 128 && WHITELIST_BLOCKS == 4, "the fast path is
 static_assert(WHITELIST_CHUNK_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 static_assert((WHITELIST_QUEUE & (WHITELIST_QUEUE - 1)) == 0 && WHITELIST_QUEUE >= 64, "queue positions are masked");
 
+/*  P(Binomial(H, 3/4) <= l): the chance that a random barcode mismatches a read in at most l of H counted positions;
+    [H][l], H and l in 0..16. Only used to choose which positions a read counts (a performance heuristic). */
+__constant__ float WHITELIST_PASS_PROBABILITY[17][17] = {
+    { 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 2.500000e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 6.250000e-02f, 4.375000e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 1.562500e-02f, 1.562500e-01f, 5.781250e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 3.906250e-03f, 5.078125e-02f, 2.617188e-01f, 6.835938e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 9.765625e-04f, 1.562500e-02f, 1.035156e-01f, 3.671875e-01f, 7.626953e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 2.441406e-04f, 4.638672e-03f, 3.759766e-02f, 1.694336e-01f, 4.660645e-01f, 8.220215e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 6.103516e-05f, 1.342773e-03f, 1.287842e-02f, 7.055664e-02f, 2.435913e-01f, 5.550537e-01f, 8.665161e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 1.525879e-05f, 3.814697e-04f, 4.226685e-03f, 2.729797e-02f, 1.138153e-01f, 3.214569e-01f, 6.329193e-01f, 8.998871e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 3.814697e-06f, 1.068115e-04f, 1.342773e-03f, 9.994507e-03f, 4.892731e-02f, 1.657257e-01f, 3.993225e-01f, 6.996613e-01f, 9.249153e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 9.536743e-07f, 2.956390e-05f, 4.158020e-04f, 3.505707e-03f, 1.972771e-02f, 7.812691e-02f, 2.241249e-01f, 4.744072e-01f, 7.559748e-01f, 9.436865e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 2.384186e-07f, 8.106232e-06f, 1.261234e-04f, 1.188278e-03f, 7.561207e-03f, 3.432751e-02f, 1.146264e-01f, 2.866955e-01f, 5.447991e-01f, 8.029027e-01f, 9.577649e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 5.960464e-08f, 2.205372e-06f, 3.761053e-05f, 3.916621e-04f, 2.781510e-03f, 1.425278e-02f, 5.440223e-02f, 1.576437e-01f, 3.512214e-01f, 6.093250e-01f, 8.416182e-01f, 9.683236e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 1.490116e-08f, 5.960464e-07f, 1.105666e-05f, 1.261234e-04f, 9.891242e-04f, 5.649328e-03f, 2.429014e-02f, 8.021259e-02f, 2.060381e-01f, 4.157473e-01f, 6.673983e-01f, 8.732946e-01f, 9.762427e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 3.725290e-09f, 1.601875e-07f, 3.211200e-06f, 3.982335e-05f, 3.418736e-04f, 2.154175e-03f, 1.030953e-02f, 3.827076e-02f, 1.116690e-01f, 2.584654e-01f, 4.786600e-01f, 7.188724e-01f, 8.990316e-01f, 9.821821e-01f, 1.000000e+00f, 1.000000e+00f, 1.000000e+00f },
+    { 9.313226e-10f, 4.284084e-08f, 9.229407e-07f, 1.236424e-05f, 1.153359e-04f, 7.949490e-04f, 4.193014e-03f, 1.729984e-02f, 5.662031e-02f, 1.483681e-01f, 3.135141e-01f, 5.387131e-01f, 7.639122e-01f, 9.198192e-01f, 9.866365e-01f, 1.000000e+00f, 1.000000e+00f },
+    { 2.328306e-10f, 1.140870e-08f, 2.628658e-07f, 3.783265e-06f, 3.810716e-05f, 2.852392e-04f, 1.644465e-03f, 7.469720e-03f, 2.712996e-02f, 7.955725e-02f, 1.896546e-01f, 3.698138e-01f, 5.950129e-01f, 8.028890e-01f, 9.365236e-01f, 9.899774e-01f, 1.000000e+00f },
+};
+
 __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
     asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));        /* a ^ b ^ c */
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));      /* majority */
@@ -1150,8 +1172,6 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
                 base_probability *= f.factor;
                 w[k] = f.ratio;
                 const bool counted = valid && !ambiguous && j < L && f.ratio < 1.0;
-                const uint32_t code = ((o_lo >> j) & 1u) | (((o_hi >> j) & 1u) << 1);
-                plane_address[j] = ring + (static_cast< uint32_t >(j * WHITELIST_PLANES) + (counted ? code : 4u)) * 16u;
                 counted_ratio[j] = counted ? f.ratio : 2.0;
                 if(f.ratio > 1.0) { loose *= f.ratio; }
             }
@@ -1165,17 +1185,25 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
         }
         high_quality_mask &= (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
 
-        /* ---- bound[c]: no barcode with c counted mismatches has a prior adjusted product above it. The
-           counted ratios in descending order by rank (ties by position), then the running product; the
-           factor 1 + 2^-20 covers the rounding of the products on either side. */
+        /* ---- which positions to count, and bound[c]: no barcode with c counted mismatches has a prior adjusted
+           product above it. The candidate positions (ratio < 1) in descending order of their ratio, by rank (ties by
+           position). Leaving the k weakest of them out is always valid (a mismatch there multiplies by less than 1)
+           and often better: a Phred 12 position tells the counter little but loosens the bound by a factor 15, so
+           the read would pass many more barcodes to the exact path. k is chosen to minimise the chance that a
+           random barcode passes once the threshold has settled at its noise floor. The factor 1 + 2^-20 covers the
+           rounding of the products on either side. */
         double bound[WHITELIST_POSITIONS + 1];
         int counted_positions = 0;
+        const double noise_term = P.adjusted_noise_probability / base_probability;
         {
             double sorted[WHITELIST_POSITIONS];
+            int rank_of[WHITELIST_POSITIONS];
             #pragma unroll
             for(int j = 0; j < WHITELIST_POSITIONS; ++j) { sorted[j] = 0.0; }
+            int candidates = 0;
             #pragma unroll
             for(int j = 0; j < WHITELIST_POSITIONS; ++j) {
+                rank_of[j] = -1;
                 if(counted_ratio[j] < 1.0) {
                     int rank = 0;
                     #pragma unroll
@@ -1183,20 +1211,37 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
                         if(counted_ratio[i] < 1.0 && (counted_ratio[i] > counted_ratio[j] || (counted_ratio[i] == counted_ratio[j] && i < j))) { ++rank; }
                     }
                     sorted[rank] = counted_ratio[j];
-                    ++counted_positions;
+                    rank_of[j] = rank;
+                    ++candidates;
                 }
             }
-            double running = P.prior_maximum * loose * (1.0 + 9.5367431640625e-07);
+            const double ceiling = P.prior_maximum * loose * (1.0 + 9.5367431640625e-07);
+            const double floor_threshold = tolerance_per_barcode * noise_term;
+            int skipped = 0;
+            float lowest = 2.0f;
+            for(int k = 0; k <= candidates; ++k) {
+                double running = ceiling;
+                int c = 0;
+                while(c < candidates - k && running * sorted[k + c] >= floor_threshold) { running *= sorted[k + c]; ++c; }
+                const float chance = WHITELIST_PASS_PROBABILITY[candidates - k][c];
+                if(chance < lowest) { lowest = chance; skipped = k; }
+            }
+            counted_positions = candidates - skipped;
+            double running = ceiling;
             bound[0] = running;
             for(int c = 1; c <= WHITELIST_POSITIONS; ++c) {
-                running *= sorted[c - 1];           /* 0 beyond the counted positions: such counts do not occur */
+                running *= (skipped + c - 1 < WHITELIST_POSITIONS) ? sorted[skipped + c - 1] : 0.0;     /* 0 beyond the counted positions: such counts do not occur */
                 bound[c] = running;
+            }
+            #pragma unroll
+            for(int j = 0; j < WHITELIST_POSITIONS; ++j) {
+                const uint32_t code = ((o_lo >> j) & 1u) | (((o_hi >> j) & 1u) << 1);
+                plane_address[j] = ring + (static_cast< uint32_t >(j * WHITELIST_PLANES) + (rank_of[j] >= skipped ? code : 4u)) * 16u;
             }
         }
         int limit = counted_positions;
         double limit_bound = bound[limit];
         double threshold = 0.0;                     /* min(best / 2, tolerance share of the rest of sigma_p): only ever grows */
-        const double noise_term = P.adjusted_noise_probability / base_probability;
         const uint32_t valid_mask = valid ? 0xffffffffu : 0u;
         uint32_t b0, b1, b2, b3, take_all;
         auto set_limit = [&]() {
