@@ -20,6 +20,8 @@
 #include "json.hpp"
 #include "../../include/pheniqs_b200.h"
 
+#include <cstdlib>
+#include <climits>
 #include <map>
 #include <set>
 
@@ -789,7 +791,12 @@ inline Json compile_job(const Json& directive) {
 /*  Job::load_instruction_with_import (job.cpp:160-224): the document at `path` with the documents its `import`
     list names merged underneath it, depth first; an import path is relative to the importing document and a
     document is only visited once. */
-inline Json load_job_with_import(const std::string& path, std::set< std::string >& visited) {
+inline std::string canonical_path(const std::string& path) {
+    char resolved[4096];
+    return realpath(path.c_str(), resolved) != NULL ? std::string(resolved) : path;
+}
+inline Json load_job_with_import(const std::string& given, std::set< std::string >& visited) {
+    const std::string path(canonical_path(given));      /* the same document reached through another spelling is the same document */
     FILE* const file(fopen(path.c_str(), "rb"));
     if(file == NULL) { throw ConfigurationError("unable to read instruction file from " + path); }
     std::string text;
@@ -809,6 +816,7 @@ inline Json load_job_with_import(const std::string& path, std::set< std::string 
             std::string target(record.as_string());
             if(target.empty()) { continue; }
             if(target[0] != '/') { target = directory + target; }
+            target = canonical_path(target);
             if(visited.count(target)) { continue; }
             Json imported(load_job_with_import(target, visited));
             merge_json(aggregated, imported);

@@ -209,3 +209,19 @@ def test_inheritance_errors():
         compile_job({"sample": {"base": "nowhere", "transform": {"token": ["0::8"]}}, "decoder": {"a": {"noise": 0.1}}})
     with pytest.raises(ConfigurationError):
         compile_job({"decoder": {"a": {"base": "a"}}, "sample": {"base": "a", "transform": {"token": ["0::8"]}}})
+
+
+def test_load_job_resolves_imports_relative_to_the_importing_file_and_visits_each_once(tmp_path):
+    """Job::load_instruction_with_import (job.cpp:160-224): paths are relative to the importing document, the
+    importing document wins over what it imports, later imports over earlier ones, and a document that is imported
+    twice (here through a cycle) is read once."""
+    import json
+    from pheniqs_b200 import load_job
+    (tmp_path / "lib").mkdir()
+    (tmp_path / "lib" / "base.json").write_text(json.dumps({"import": ["../job.json"], "noise": 0.2, "PL": "ILLUMINA", "decoder": {"a": {"noise": 0.3}}}))
+    (tmp_path / "lib" / "more.json").write_text(json.dumps({"noise": 0.4, "PM": "novaseq"}))
+    (tmp_path / "job.json").write_text(json.dumps({"import": ["lib/base.json", "lib/more.json"], "decoder": {"b": {"base": "a"}}, "PL": "mine"}))
+    job = load_job(str(tmp_path / "job.json"))
+    assert "import" not in job
+    assert job["PL"] == "mine" and job["PM"] == "novaseq" and job["noise"] == 0.4
+    assert job["decoder"] == {"a": {"noise": 0.3}, "b": {"base": "a"}}

@@ -89,3 +89,13 @@ def test_degenerate_observations():
     quality[48:] = rng.integers(0, 42, size=(16, 10))
     batch = O.ReadBatch.from_fixed([code], [quality])
     both(compiled, batch, 1)
+
+
+def test_whitelist_config_reduced():
+    """Config 5's shape (16 nt cellular whitelist + naive UMI) on 4,000 barcodes: the restatement and the reference's own
+    classes agree bit for bit there too (the full 737,280 barcode table is covered on the GPU box against oracle/_ref)."""
+    spec = workload.load("c5", whitelist_cardinality=4000)
+    compiled = O.compile_job(spec["job"])
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 400, seed=5)
+    out = both(compiled, O.ReadBatch(code, quality, offset), len(code))
+    assert (out.index > 0).any()
