@@ -81,9 +81,6 @@ __device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbarrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(shared_address(bar)), "r"(bytes) : "memory");
 }
@@ -1349,7 +1346,6 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
             /* keep the ring full: the stage freed by the previous group receives group + stages - 1 */
             if(group + WHITELIST_STAGES - 1 < group_cardinality) { issue(group + WHITELIST_STAGES - 1); }
             mbarrier_wait(&mbarrier[consume_stage], consume_phase);
-            const int first = group * WHITELIST_CHUNK;
 
             /* ---- fast path: one 16-byte load per position covers the four blocks of the group */
             uint32_t pass[4];
