@@ -989,10 +989,10 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
    Every warp is its own pipeline: it owns 32 reads at a time (taken from a global counter, so slow reads do
    not hold a CTA back), streams the table through a private three-stage ring of TMA bulk copies (one 3.3 KB
    group per stage, completion on the warp's own mbarriers) and never meets a CTA-wide barrier. */
-constexpr int WHITELIST_STAGES = 4;
+constexpr int WHITELIST_STAGES = 3;
 constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
 constexpr int WHITELIST_WORDS = 256;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 4 x 32); expanded up to 32 at a time */
-constexpr int WHITELIST_MAX_WARPS = 13;
+constexpr int WHITELIST_MAX_WARPS = 14;
 constexpr double WHITELIST_TOLERANCE = 4.76837158203125e-07;       /* 2^-21: half of the 1e-6 the path allows, as a worst case bound */
 
 /* per-warp shared memory of pamld_whitelist_kernel */
