@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 METRIC = "reads/sec decoded (PAMLD)"
 UNIT = "reads/s"
-DEFAULT_READS = {"c1": 1 << 28, "c2": 1 << 28, "c3": 1 << 26, "c4": 1 << 26, "c5": 148 * 14 * 32 * 8}
+DEFAULT_READS = {"c1": 1 << 28, "c2": 1 << 28, "c3": 1 << 26, "c4": 1 << 26, "c5": 148 * 15 * 32 * 8}
 WORKLOAD_LABEL = {
     "c1": "C1: Illumina dual-index (i7+i5, 8 bp each) 96-sample PAMLD, noise 0.05, confidence threshold 0.95",
     "c2": "C2: same 96-sample dual-index set, MDD, distance tolerance [1,1]",

@@ -991,8 +991,8 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
    group per stage, completion on the warp's own mbarriers) and never meets a CTA-wide barrier. */
 constexpr int WHITELIST_STAGES = 3;
 constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
-constexpr int WHITELIST_WORDS = 256;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 4 x 32); expanded up to 32 at a time */
-constexpr int WHITELIST_MAX_WARPS = 14;
+constexpr int WHITELIST_WORDS = 128;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 2 x 32); expanded up to 32 at a time */
+constexpr int WHITELIST_MAX_WARPS = 15;
 constexpr double WHITELIST_TOLERANCE = 4.76837158203125e-07;       /* 2^-21: half of the 1e-6 the path allows, as a worst case bound */
 
 /* per-warp shared memory of pamld_whitelist_kernel */
@@ -1377,9 +1377,11 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
                     }
                     word_tail += static_cast< unsigned >(__popc(lanes));
                 }
+                if(u == 1 || u == 3) {          /* the word queue holds 31 + two blocks' worth */
+                    #pragma unroll 1
+                    while(word_tail - word_head >= 32u) { expand(32u); }
+                }
             }
-            #pragma unroll 1
-            while(word_tail - word_head >= 32u) { expand(32u); }
             if(limit != previous) { set_limit(); }
             __syncwarp();       /* the stage is free for the copy the next trip issues */
         }
