@@ -243,7 +243,15 @@ def main():
     stream = torch.cuda.current_stream(device)
     u64_plane, f64_plane = chain.accumulator_tensors()
 
+    # timing rule: inputs larger than L2, or L2 flushed between steps. The tile planes of a step exceed the 126 MB L2 for
+    # c1-c4 at their default sizes; where they do not (c5: a few MB of reads against a table that is MEANT to live in L2),
+    # a 256 MB write between steps evicts them (about 40 us inside a step of tens of ms).
+    input_bytes = algorithmic_bytes_per_read(chain, compiled) * n
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if input_bytes < (192 << 20) else None
+
     def step():
+        if flush is not None:
+            flush.zero_()
         flags.zero_()
         u64_plane.zero_()
         f64_plane.zero_()
@@ -317,11 +325,23 @@ def main():
                 "pair_words_per_clk_per_sm": (pairs * n / (kernel_ms_mean * 1e-3)) / (sm_mhz * 1e6 * sm_count) if sm_mhz else None,
                 "note": "the path is issue/shared-memory bound, not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the contract asks"}
 
+    # SURVEY.md §8d also asks for the integer / issue roofline: the exhaustive formulation costs 19 integer-pipe operations
+    # per (read, barcode) pair-word for PAMLD and 7 for MDD; the chip issues 4 warp instructions per clock and SM (2 on the
+    # ALU pipe + 2 on the FMA pipe, measured: profiles/r01_microbench.txt). The kernels restructure the arithmetic (separable
+    # grids, lookups, pruned bit-sliced scans), so the EQUIVALENT rate can exceed the peak: that ratio is the algorithmic gain.
+    equivalent_ops = sum((19 if info.algorithm == 0 else 7) * info.barcode_cardinality for info in chain.info if info.has_tile)
+    if sm_mhz:
+        issue_peak = sm_count * 4 * 32 * sm_mhz * 1e6
+        roofline["int"] = {"equivalent_ops_per_read": equivalent_ops, "equivalent_ops_per_s": equivalent_ops * n / (kernel_ms_mean * 1e-3),
+                           "issue_peak_lane_ops_per_s": issue_peak, "frac": equivalent_ops * n / (kernel_ms_mean * 1e-3) / issue_peak,
+                           "note": "operations of the exhaustive formulation per second over the measured issue peak; above 1 = work the kernels avoid"}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_LABEL[args.workload], "reads_per_gpu": n, "decoders": chain.n_decoders, "barcodes": [info.barcode_cardinality for info in chain.info],
-                       "l2": "inputs (%d MB per GPU) exceed L2; no flush needed" % (bytes_per_read * n >> 20), "parallelism": "reads sharded x%d, accumulators all-reduced" % world},
+                       "l2": ("inputs (%d MB per GPU) exceed L2; no flush needed" % (bytes_per_read * n >> 20)) if flush is None else
+                             ("inputs are %d MB per GPU: L2 flushed with a 256 MB write between steps (inside the timed region)" % (bytes_per_read * n >> 20)), "parallelism": "reads sharded x%d, accumulators all-reduced" % world},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clock_summary}
 
     # ---------------------------------------------------------------- end to end through the host-buffer C-ABI calls
