@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstring>
 
-int main() {
+int main(int argc, char** argv) {
     const char* job =
         "{\"sample\": {\"algorithm\": \"mdd\", \"transform\": {\"token\": [\"0::4\"]},"
         " \"codec\": {\"@b\": {\"barcode\": [\"ACGT\"]}, \"@a\": {\"barcode\": [\"TTTT\"]}}}}";
@@ -45,6 +45,18 @@ int main() {
         try { phq::compile_job("{\"sample\": {\"algorithm\": \"mdd\", \"transform\": {\"token\": [\"0::4\"]}, \"distance tolerance\": [3], \"codec\": {\"@a\": {\"barcode\": [\"ACGT\"]}, \"@b\": {\"barcode\": [\"ACGA\"]}}}}"); }
         catch(const phq::ConfigurationError& e) { rejected = e.code == 3; }
         if(!rejected) { return 6; }
+        /* a job file of the reference's own test (import + base inheritance), when one is given */
+        if(argc > 1) {
+            const std::string loaded(phq::load_job(argv[1]));
+            if(loaded.find("\"import\"") != std::string::npos || loaded.find("BDGGG_sample") == std::string::npos) { return 9; }
+            const std::string decoders(phq::compile_job(loaded));
+            if(decoders.find("\"ID\": \"BDGGG:1:AGGCAGAA\"") == std::string::npos && decoders.find("\"ID\":\"BDGGG:1:AGGCAGAA\"") == std::string::npos) { return 11; }
+            phq::BatchDecoder chain(decoders, -1);
+            if(chain.decoder_cardinality() != 3) { return 12; }
+            bool refused_tags(false);
+            try { chain.tag_record_bytes(); } catch(const phq::Error&) { refused_tags = true; }       /* needs the device tables */
+            if(!refused_tags) { return 13; }
+        }
     } catch(const phq::Error& e) {
         std::printf("error %d: %s\n", e.code, e.what());
         return 10;
