@@ -34,6 +34,19 @@ class Json {
         typedef std::pair< std::string, Json > Member;
 
         Json() : type_(Null), boolean_(false), number_(0), integral_(false) {}
+        /* the key index is a cache: never copied; moves are noexcept so that containers of values move on growth */
+        Json(const Json& o) : type_(o.type_), boolean_(o.boolean_), number_(o.number_), integral_(o.integral_), string_(o.string_), items_(o.items_), members_(o.members_) {}
+        Json(Json&& o) noexcept : type_(o.type_), boolean_(o.boolean_), number_(o.number_), integral_(o.integral_), string_(std::move(o.string_)),
+            items_(std::move(o.items_)), members_(std::move(o.members_)), index_(std::move(o.index_)) { o.type_ = Null; }
+        Json& operator=(const Json& o) { if(this != &o) { Json copy(o); *this = std::move(copy); } return *this; }
+        Json& operator=(Json&& o) noexcept {
+            if(this != &o) {
+                type_ = o.type_; boolean_ = o.boolean_; number_ = o.number_; integral_ = o.integral_;
+                string_ = std::move(o.string_); items_ = std::move(o.items_); members_ = std::move(o.members_); index_ = std::move(o.index_);
+                o.type_ = Null;
+            }
+            return *this;
+        }
         static Json boolean(bool v) { Json j; j.type_ = Bool; j.boolean_ = v; return j; }
         static Json number(double v) { Json j; j.type_ = Number; j.number_ = v; j.integral_ = false; return j; }
         static Json integer(int64_t v) { Json j; j.type_ = Number; j.number_ = static_cast< double >(v); j.integral_ = true; return j; }
@@ -84,14 +97,22 @@ class Json {
             const long at(position(key));
             if(at >= 0) { members_[static_cast< size_t >(at)].second = value; return; }
             members_.emplace_back(key, value);
-            if(index_.ready) { index_.map.emplace(key, members_.size() - 1); }
+            if(index_ != nullptr) { index_->emplace(key, members_.size() - 1); }
         }
         void erase(const std::string& key) {
             expect(Object, "object");
             index_.reset();
             members_.erase(std::remove_if(members_.begin(), members_.end(), [&](const Member& m) { return m.first == key; }), members_.end());
         }
+        void set(const std::string& key, Json&& value) {
+            expect(Object, "object");
+            const long at(position(key));
+            if(at >= 0) { members_[static_cast< size_t >(at)].second = std::move(value); return; }
+            members_.emplace_back(key, std::move(value));
+            if(index_ != nullptr) { index_->emplace(key, members_.size() - 1); }
+        }
         void push(const Json& value) { expect(Array, "array"); items_.push_back(value); }
+        void push(Json&& value) { expect(Array, "array"); items_.push_back(std::move(value)); }
 
         /* json.cpp:875-893: recursive key sort, byte order */
         void sort_keys() {
@@ -125,30 +146,21 @@ class Json {
         std::string string_;
         std::vector< Json > items_;
         std::vector< Member > members_;
-        /* key -> position, built on the first lookup of a large object (a 737 K barcode codec is one object) and
-           never copied with the value */
-        struct KeyIndex {
-            std::unordered_map< std::string, size_t > map;
-            bool ready;
-            KeyIndex() : ready(false) {}
-            KeyIndex(const KeyIndex&) : ready(false) {}
-            KeyIndex& operator=(const KeyIndex&) { reset(); return *this; }
-            void reset() { if(ready) { map.clear(); ready = false; } }
-        };
-        mutable KeyIndex index_;
+        /* key -> position, built on the first lookup of a large object (a 737 K barcode codec is one object); a cache
+           that is allocated on demand and dropped whenever positions may change */
+        mutable std::unique_ptr< std::unordered_map< std::string, size_t > > index_;
         long position(const std::string& key) const {
             if(members_.size() < 32) {
                 for(size_t i(0); i < members_.size(); ++i) { if(members_[i].first == key) { return static_cast< long >(i); } }
                 return -1;
             }
-            if(!index_.ready) {
-                index_.map.clear();
-                index_.map.reserve(members_.size() * 2);
-                for(size_t i(0); i < members_.size(); ++i) { index_.map.emplace(members_[i].first, i); }     /* first occurrence wins */
-                index_.ready = true;
+            if(index_ == nullptr) {
+                index_.reset(new std::unordered_map< std::string, size_t >());
+                index_->reserve(members_.size() * 2);
+                for(size_t i(0); i < members_.size(); ++i) { index_->emplace(members_[i].first, i); }     /* first occurrence wins */
             }
-            const auto found(index_.map.find(key));
-            return found == index_.map.end() ? -1 : static_cast< long >(found->second);
+            const auto found(index_->find(key));
+            return found == index_->end() ? -1 : static_cast< long >(found->second);
         }
 
         void expect(Type t, const char* name) const {
@@ -189,8 +201,7 @@ class Json {
                     if(peek() != '"') { throw JsonError("expected a member name at offset " + std::to_string(at)); }
                     std::string key(parse_string());
                     consume(':');
-                    Json value(parse_value());
-                    o.set(key, value);
+                    o.set(key, parse_value());
                     char c(peek());
                     ++at;
                     if(c == '}') { break; }

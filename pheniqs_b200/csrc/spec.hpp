@@ -418,26 +418,20 @@ inline Json project_json(const Json& base, const Json& ontology) {
     if(!ontology.is_null() && container.is_null()) { container = ontology; }
     return container;
 }
-/* clean_json_value (json.cpp:833-874): false, empty strings, empty containers and nulls disappear */
+/* clean_json_value (json.cpp:833-874): false, empty strings, empty containers and nulls disappear (in place) */
 inline void clean_json(Json& v) {
     if(v.is_bool()) { if(!v.as_bool()) { v = Json(); } }
     else if(v.is_string()) { if(v.as_string().empty()) { v = Json(); } }
     else if(v.is_object()) {
-        Json clean(Json::object());
-        for(auto& m : v.members()) {
-            Json child(m.second);
-            clean_json(child);
-            if(!child.is_null()) { clean.set(m.first, child); }
-        }
-        v = clean.members().empty() ? Json() : clean;
+        std::vector< Json::Member >& members(v.members());
+        for(auto& m : members) { clean_json(m.second); }
+        members.erase(std::remove_if(members.begin(), members.end(), [](const Json::Member& m) { return m.second.is_null(); }), members.end());
+        if(members.empty()) { v = Json(); }
     } else if(v.is_array()) {
-        Json clean(Json::array());
-        for(auto& e : v.items()) {
-            Json child(e);
-            clean_json(child);
-            if(!child.is_null()) { clean.push(child); }
-        }
-        v = clean.items().empty() ? Json() : clean;
+        std::vector< Json >& items(v.items());
+        for(auto& e : items) { clean_json(e); }
+        items.erase(std::remove_if(items.begin(), items.end(), [](const Json& e) { return e.is_null(); }), items.end());
+        if(items.empty()) { v = Json(); }
     }
 }
 
@@ -580,11 +574,10 @@ inline int32_t shannon_bound(const std::set< std::string >& words, int32_t lengt
     return (minimum - 1) / 2;
 }
 
-inline Json compile_decoder(const Json& directive, const char* topic, int32_t index, const Json& default_decoder, const Json& default_barcode) {
-    if(!directive.is_object()) { throw ConfigurationError("decoder element must be a dictionary"); }
+inline Json compile_decoder(Json value, const char* topic, int32_t index, const Json& default_decoder, const Json& default_barcode) {
+    if(!value.is_object()) { throw ConfigurationError("decoder element must be a dictionary"); }
     /* Transcode::compile_decoder (transcode.cpp:937-966): overlay on the default decoder (the "<topic>:decoder"
        projection valued from the job root, transcode.cpp:769-790), then clean */
-    Json value(directive);
     value.set("index", Json::integer(index));
     merge_json(default_decoder, value);
     clean_json(value);
@@ -655,7 +648,7 @@ inline Json compile_decoder(const Json& directive, const char* topic, int32_t in
     }
 
     if(value.has("codec")) {
-        Json codec(value.at("codec"));
+        Json& codec(*value.find("codec"));     /* compiled in place: a whitelist codec is hundreds of megabytes of JSON */
         if(!codec.is_object()) { throw ConfigurationError("codec element must be a dictionary"); }
         codec.sort_keys();                                                              /* transcode.cpp:350, json.cpp:875-893 */
         int32_t barcode_index(1);
@@ -698,7 +691,6 @@ inline Json compile_decoder(const Json& directive, const char* topic, int32_t in
         for(auto& record : codec.members()) {
             record.second.set("concentration", Json::number(get_double(record.second, "concentration") * factor));
         }
-        value.set("codec", codec);
 
         /* CodecMetric::compile_barcode_tolerance (metric.h:216-242). The pairwise scan is quadratic in the
            distinct words of a segment; it is what the reference does, and only MDD consumes the result. */
@@ -743,19 +735,20 @@ inline Json compile_job(const Json& directive) {
     Json out(Json::object());
     const char* name[3] = { "sample", "molecular", "cellular" };
     for(int t(0); t < 3; ++t) {
-        const Json* e(job.find(name[t]));
+        Json* e(job.find(name[t]));
         if(e == NULL || e->is_null()) { continue; }
-        /* Transcode::compile_topic (transcode.cpp:769-823): defaults are the projections valued from the job root */
+        /* Transcode::compile_topic (transcode.cpp:769-823): defaults are the projections valued from the job root. The
+           projection's keys do not include the decoders themselves, so they can be moved out of the (local) job. */
         const Json default_decoder(project_json(decoder_template(name[t]), job));
         const Json default_barcode(barcode_template(name[t]));
         try {
             if(e->is_object()) {
-                out.set(name[t], compile_decoder(*e, name[t], 0, default_decoder, default_barcode));
+                out.set(name[t], compile_decoder(std::move(*e), name[t], 0, default_decoder, default_barcode));
             } else if(e->is_array()) {
                 Json list(Json::array());
                 int32_t index(0);
-                for(const auto& d : e->items()) { list.push(compile_decoder(d, name[t], index++, default_decoder, default_barcode)); }
-                out.set(name[t], list);
+                for(auto& d : e->items()) { list.push(compile_decoder(std::move(d), name[t], index++, default_decoder, default_barcode)); }
+                out.set(name[t], std::move(list));
             } else { throw ConfigurationError("decoder element must be a dictionary or an array"); }
         } catch(ConfigurationError& error) {
             throw ConfigurationError(std::string(name[t]) + " decoder : " + (error.what() + strlen("Configuration error : ")));
