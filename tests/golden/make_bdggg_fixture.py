@@ -13,7 +13,8 @@ Writes, next to this script:
                        segment, with the order they are written in
   bdggg_report.json    valid/annotated.err (the JSON report with every accumulator and estimated prior)
   bdggg_compiled.json  the sample/molecular/cellular sections of valid/compile_annotated.out
-  bdggg_import/        BDGGG_annotated.json and the BDGGG_interleave.json it imports, as the reference's test holds them
+  bdggg_import_documents.json  the job document of the annotated test and the document it imports, keyed by the
+                       file names the import list uses (the tests write them out next to each other)
   prior_report.json / prior_estimated.json   test/api/prior input report and valid/BDGGG_annotated_estimated.json
 
 Only data is written; no reference source is copied.
@@ -72,9 +73,8 @@ def main():
     }
     json.dump(job, open(os.path.join(HERE, "bdggg_job.json"), "w"), indent=1, sort_keys=True)
     # the two job documents as the reference's test holds them (import + base inheritance; data only)
-    os.makedirs(os.path.join(HERE, "bdggg_import"), exist_ok=True)
-    json.dump(annotated, open(os.path.join(HERE, "bdggg_import", "BDGGG_annotated.json"), "w"), indent=1)
-    json.dump(interleave, open(os.path.join(HERE, "bdggg_import", "BDGGG_interleave.json"), "w"), indent=1)
+    json.dump({"BDGGG_annotated.json": annotated, "BDGGG_interleave.json": interleave},
+              open(os.path.join(HERE, "bdggg_import_documents.json"), "w"), indent=1, sort_keys=True)
 
     expected = []
     for line in open(os.path.join(T, "valid", "annotated.out")):

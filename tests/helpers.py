@@ -23,6 +23,16 @@ def bdggg():
     return batch.select(keep), decoders, expected
 
 
+def bdggg_import_documents(directory):
+    """Write the job documents of the reference's annotated test (import + base inheritance) into `directory` under the
+    file names their import list uses; returns the path of the top document."""
+    documents = json.load(open(os.path.join(GOLDEN, "bdggg_import_documents.json")))
+    for name, document in documents.items():
+        with open(os.path.join(str(directory), name), "w") as f:
+            json.dump(document, f)
+    return os.path.join(str(directory), "BDGGG_annotated.json")
+
+
 def golden(name):
     return json.load(open(os.path.join(GOLDEN, name)))
 

@@ -168,7 +168,7 @@ def test_pack_reproduces_rule_apply(short):
         DecoderChain(compiled, device=-1).pack(code, noisy, offset, quality_bits=2)
 
 
-def test_job_file_with_import_and_base_compiles_like_the_reference():
+def test_job_file_with_import_and_base_compiles_like_the_reference(tmp_path):
     """the reference's own test job (test/BDGGG/BDGGG_annotated.json, which imports
     BDGGG_interleave.json and inherits its decoders from the `decoder` repository through `base`) loaded with
     phq_load_job and compiled with phq_compile_job gives the decoder sections of the reference's own compile output
@@ -179,7 +179,7 @@ def test_job_file_with_import_and_base_compiles_like_the_reference():
     import os
     from pheniqs_b200 import compile_job, load_job
     golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    job = load_job(os.path.join(golden, "bdggg_import", "BDGGG_annotated.json"))
+    job = load_job(helpers.bdggg_import_documents(tmp_path))
     assert "import" not in job and job["flowcell id"] == "BDGGG" and "BDGGG_sample" in job["decoder"]
     compiled = compile_job(job)
     expected = json.load(open(os.path.join(golden, "bdggg_compiled.json")))
