@@ -1096,6 +1096,23 @@ int32_t tag_record_bytes(const phq_handle* h) {
     return (bytes + 15) / 16 * 16;
 }
 
+/* the longest read group ID of the sample decoder (decode_tag_id_by_index, classifier.cpp:79-98): host only */
+int32_t host_read_group_longest(const phq_handle* h) {
+    int32_t longest(0);
+    const Json* element(h->job.find("sample"));
+    if(element == NULL || !element->is_object()) { return 0; }
+    auto measure = [&](const Json* record) {
+        if(record != NULL && record->is_object()) {
+            const int32_t length(static_cast< int32_t >(get_string(*record, "ID").size()));
+            if(length > longest) { longest = length; }
+        }
+    };
+    measure(element->find("undetermined"));
+    const Json* codec(element->find("codec"));
+    if(codec != NULL && codec->is_object()) { for(const auto& record : codec->members()) { measure(&record.second); } }
+    return longest;
+}
+
 /* device tables of the tag kernel: barcode codes by index (row 0 = undetermined) and the read group IDs */
 void ensure_tags(phq_handle* h) {
     if(h->tags_ready) { return; }
@@ -1332,9 +1349,12 @@ int phq_decode_batch_raw_compact(phq_handle* handle, int64_t n_reads, int32_t n_
 }
 
 int phq_tag_record_bytes(phq_handle* handle, int32_t* bytes) {
-    return guarded(handle, [&]() {
+    return guarded_host(handle, [&]() {           /* pure host work: also answers for a host-only handle */
         if(bytes == NULL) { throw InternalError("illegal argument"); }
-        ensure_tags(handle);
+        if(!handle->tags_ready) {
+            const int32_t longest(host_read_group_longest(handle));
+            if(longest > handle->read_group_longest) { handle->read_group_longest = longest; }
+        }
         *bytes = tag_record_bytes(handle);
     });
 }
