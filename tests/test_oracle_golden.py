@@ -104,3 +104,21 @@ def test_compile_matches_reference_compile_output():
             for key, record in theirs["codec"].items():
                 assert ours["codec"][key]["index"] == record["index"]
                 assert ours["codec"][key]["concentration"] == pytest.approx(record["concentration"], abs=1.1e-15)
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_bdggg_tags_golden():
+    """The checker of the tag path (RefOracle.tags: the reference's own Read::flush + Auxiliary members, read.h:187-237)
+    reproduces every tag of test/BDGGG/valid/annotated.out, their order included, from the reference's own compile
+    output — so the GPU tag tests compare against something that is itself pinned."""
+    batch, _, expected = helpers.bdggg()
+    compiled = helpers.golden("bdggg_compiled.json")
+    tags, flags = O.RefOracle(compiled, 3).tags(batch)
+    order = ("RG", "BC", "QT", "XB", "RX", "QX", "OX", "BZ", "XM", "CB", "CR", "CY", "XC")      # Auxiliary::encode, auxiliary.cpp:320-361
+    for i, e in enumerate(expected):
+        assert [t for t in order if t in tags[i]] == e["order"], e["name"]
+        for tag in ("RG", "BC", "QT", "OX", "BZ", "CB", "CR", "CY"):
+            assert tags[i].get(tag) == e[tag], "%s %s" % (e["name"], tag)
+        for tag in ("XB", "XC"):
+            assert (None if tag not in tags[i] else "%g" % tags[i][tag]) == e[tag], "%s %s" % (e["name"], tag)
+        assert (589 if flags[i] else 77) == e["flag"], e["name"]
