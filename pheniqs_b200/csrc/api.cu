@@ -11,8 +11,11 @@
 
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cmath>
+#include <exception>
 #include <functional>
+#include <thread>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,6 +40,16 @@ struct ScratchSegment {
     int32_t length;
     ScratchSegment() : code(PHQ_MAX_NUCLEOTIDES * 4 + 64, 0), quality(PHQ_MAX_NUCLEOTIDES * 4 + 64, 0), length(0) {}
 };
+
+/* threads phq_pack spreads a batch over: PHQ_PACK_THREADS, else the hardware's, at most 16, and 1 below 32 Ki reads */
+inline int pack_workers(int64_t n_reads) {
+    const char* const value(getenv("PHQ_PACK_THREADS"));
+    int workers(value != NULL && atoi(value) > 0 ? atoi(value) : static_cast< int >(std::thread::hardware_concurrency()));
+    if(workers > 16) { workers = 16; }
+    if(value == NULL && n_reads < 32768) { workers = 1; }
+    if(static_cast< int64_t >(workers) > n_reads) { workers = n_reads > 0 ? static_cast< int >(n_reads) : 1; }
+    return workers < 1 ? 1 : workers;
+}
 
 template < class T > struct DeviceBuffer {
     T* pointer;
@@ -812,80 +825,119 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
             uint32_t* out_bases(const_cast< uint32_t* >(tile.bases));
             uint16_t* out_nmask(const_cast< uint16_t* >(tile.nmask));
             uint32_t* out_quality(const_cast< uint32_t* >(tile.quality));
-            std::vector< ScratchSegment >& scratch(h->scratch[k]);
             const int32_t words(d.word_cardinality());
             const int32_t quality_words(d.quality_word_cardinality());
             const bool stale_semantics(d.algorithm == PHQ_PAMLD);
+            const int64_t pitch(tile.pitch);
+
+            /* reads [begin, end) in order on top of `scratch`; returns whether any of them was short (an observed segment
+               shorter than the barcode segment), which is when a read's tile depends on the reads before it */
+            auto pack_range = [&](int64_t begin, int64_t end, std::vector< ScratchSegment >& scratch, bool* seen) -> bool {
+                bool any_short(false);
+                for(int64_t r(begin); r < end; ++r) {
+                    /* Observation::clear + Rule::apply (sequence.h:296-300, transform.h:142-169) */
+                    for(auto& sg : scratch) { sg.length = 0; sg.code[0] = 0; sg.quality[0] = 0; }
+                    for(const auto& t : d.transform) {
+                        const int64_t from(offset[t.input_segment_index][r]);
+                        const int32_t from_length(static_cast< int32_t >(offset[t.input_segment_index][r + 1] - from));
+                        const uint8_t* from_code(code[t.input_segment_index] + from);
+                        const uint8_t* from_quality(quality[t.input_segment_index] + from);
+                        ScratchSegment& to(scratch[t.output_segment_index]);
+                        const int32_t start(t.absolute_start(from_length));
+                        const int32_t end_of_token(t.absolute_end(from_length));
+                        const int32_t size(end_of_token - start);
+                        if(size > 0) {
+                            if(to.length + size + 1 > static_cast< int32_t >(to.code.size())) { throw SequenceError("token extracts more nucleotides than the barcode segment holds"); }
+                            if(!t.reverse_complement) {
+                                memcpy(to.code.data() + to.length, from_code + start, size);
+                                memcpy(to.quality.data() + to.length, from_quality + start, size);
+                            } else {
+                                for(int32_t i(0); i < size; ++i) {
+                                    to.code[to.length + i] = BAM_REVERSE_COMPLEMENT[from_code[end_of_token - i - 1] & 0xf];
+                                    to.quality[to.length + i] = from_quality[end_of_token - i - 1];
+                                }
+                            }
+                            to.length += size;
+                            to.code[to.length] = 0;
+                            to.quality[to.length] = 0;
+                        }
+                    }
+                    /* 2-bit planes + ambiguity mask + Phred bytes */
+                    uint32_t lo(0), hi(0), ambiguous(0);
+                    uint8_t phred[PHQ_MAX_NUCLEOTIDES];
+                    memset(phred, 0, sizeof(phred));
+                    for(int32_t sgm(0); sgm < d.segment_cardinality; ++sgm) {
+                        const ScratchSegment& from(scratch[sgm]);
+                        any_short = any_short || from.length < d.segment_length[sgm];
+                        for(int32_t i(0); i < d.segment_length[sgm]; ++i) {
+                            const int32_t j(d.segment_offset[sgm] + i);
+                            if(!stale_semantics && i >= from.length) {
+                                /* Sequence::distance_from stops at the observed length: the position is absent, marked by
+                                   PHQ_ABSENT_QUALITY and, so that kernels that never read qualities see it too, by an
+                                   ambiguous position whose base bits are both set (a real ambiguous base has them clear) */
+                                phred[j] = PHQ_ABSENT_QUALITY;
+                                lo |= 1u << j;
+                                hi |= 1u << j;
+                                ambiguous |= 1u << j;
+                                continue;
+                            }
+                            /* PAMLD reads the expected length: terminator, then stale bytes (barcode.h:150) */
+                            const uint8_t c(from.code[i]);
+                            switch(c) {
+                                case 1: break;
+                                case 2: lo |= 1u << j; break;
+                                case 4: hi |= 1u << j; break;
+                                case 8: lo |= 1u << j; hi |= 1u << j; break;
+                                default: ambiguous |= 1u << j; break;
+                            }
+                            phred[j] = from.quality[i];
+                        }
+                    }
+                    for(int32_t w(0); w < words; ++w) {
+                        out_bases[w * pitch + r] = ((lo >> (16 * w)) & 0xffffu) | (((hi >> (16 * w)) & 0xffffu) << 16);
+                        out_nmask[w * pitch + r] = static_cast< uint16_t >((ambiguous >> (16 * w)) & 0xffffu);
+                    }
+                    for(int32_t w(0); w < quality_words; ++w) {
+                        out_quality[w * pitch + r] = static_cast< uint32_t >(phred[4 * w]) | (static_cast< uint32_t >(phred[4 * w + 1]) << 8)
+                            | (static_cast< uint32_t >(phred[4 * w + 2]) << 16) | (static_cast< uint32_t >(phred[4 * w + 3]) << 24);
+                    }
+                    for(int32_t j(0); j < d.nucleotide_cardinality; ++j) { seen[phred[j]] = true; }
+                }
+                return any_short;
+            };
+
             bool seen[256];
             memset(seen, 0, sizeof(seen));
-
-            for(int64_t r(0); r < n_reads; ++r) {
-                /* Observation::clear + Rule::apply (sequence.h:296-300, transform.h:142-169) */
-                for(auto& s : scratch) { s.length = 0; s.code[0] = 0; s.quality[0] = 0; }
-                for(const auto& t : d.transform) {
-                    const int64_t from(offset[t.input_segment_index][r]);
-                    const int32_t from_length(static_cast< int32_t >(offset[t.input_segment_index][r + 1] - from));
-                    const uint8_t* from_code(code[t.input_segment_index] + from);
-                    const uint8_t* from_quality(quality[t.input_segment_index] + from);
-                    ScratchSegment& to(scratch[t.output_segment_index]);
-                    const int32_t start(t.absolute_start(from_length));
-                    const int32_t end(t.absolute_end(from_length));
-                    const int32_t size(end - start);
-                    if(size > 0) {
-                        if(to.length + size + 1 > static_cast< int32_t >(to.code.size())) { throw SequenceError("token extracts more nucleotides than the barcode segment holds"); }
-                        if(!t.reverse_complement) {
-                            memcpy(to.code.data() + to.length, from_code + start, size);
-                            memcpy(to.quality.data() + to.length, from_quality + start, size);
-                        } else {
-                            for(int32_t i(0); i < size; ++i) {
-                                to.code[to.length + i] = BAM_REVERSE_COMPLEMENT[from_code[end - i - 1] & 0xf];
-                                to.quality[to.length + i] = from_quality[end - i - 1];
-                            }
-                        }
-                        to.length += size;
-                        to.code[to.length] = 0;
-                        to.quality[to.length] = 0;
-                    }
+            /*  A read's tile only depends on the reads before it when some read is short (the stale bytes of the
+                reference's Observation, barcode.h:150). Large batches are therefore packed by several threads on
+                private Observations; if any of them meets a short read the batch is packed again in order. */
+            const int workers(pack_workers(n_reads));
+            bool in_order(workers <= 1);
+            if(!in_order) {
+                std::vector< std::vector< ScratchSegment > > private_scratch(static_cast< size_t >(workers), h->scratch[k]);
+                std::vector< std::array< bool, 256 > > private_seen(static_cast< size_t >(workers));
+                std::vector< char > met_short(static_cast< size_t >(workers), 0);
+                std::vector< std::exception_ptr > failure(static_cast< size_t >(workers));
+                std::vector< std::thread > pool;
+                for(int w(0); w < workers; ++w) {
+                    private_seen[w].fill(false);
+                    pool.emplace_back([&, w]() {
+                        try {
+                            met_short[w] = pack_range(n_reads * w / workers, n_reads * (w + 1) / workers, private_scratch[w], private_seen[w].data()) ? 1 : 0;
+                        } catch(...) { failure[w] = std::current_exception(); }
+                    });
                 }
-                /* 2-bit planes + ambiguity mask + Phred bytes */
-                uint32_t lo(0), hi(0), ambiguous(0);
-                uint8_t phred[PHQ_MAX_NUCLEOTIDES];
-                memset(phred, 0, sizeof(phred));
-                for(int32_t s(0); s < d.segment_cardinality; ++s) {
-                    const ScratchSegment& from(scratch[s]);
-                    for(int32_t i(0); i < d.segment_length[s]; ++i) {
-                        const int32_t j(d.segment_offset[s] + i);
-                        if(!stale_semantics && i >= from.length) {
-                            /* Sequence::distance_from stops at the observed length: the position is absent, marked by
-                               PHQ_ABSENT_QUALITY and, so that kernels that never read qualities see it too, by an
-                               ambiguous position whose base bits are both set (a real ambiguous base has them clear) */
-                            phred[j] = PHQ_ABSENT_QUALITY;
-                            lo |= 1u << j;
-                            hi |= 1u << j;
-                            ambiguous |= 1u << j;
-                            continue;
-                        }
-                        /* PAMLD reads the expected length: terminator, then stale bytes (barcode.h:150) */
-                        const uint8_t c(from.code[i]);
-                        switch(c) {
-                            case 1: break;
-                            case 2: lo |= 1u << j; break;
-                            case 4: hi |= 1u << j; break;
-                            case 8: lo |= 1u << j; hi |= 1u << j; break;
-                            default: ambiguous |= 1u << j; break;
-                        }
-                        phred[j] = from.quality[i];
-                    }
+                for(auto& t : pool) { t.join(); }
+                for(int w(0); w < workers; ++w) { if(failure[w]) { std::rethrow_exception(failure[w]); } }
+                for(int w(0); w < workers; ++w) { in_order = in_order || met_short[w] != 0; }
+                if(!in_order) {
+                    for(int w(0); w < workers; ++w) { for(int v(0); v < 256; ++v) { seen[v] = seen[v] || private_seen[w][v]; } }
+                    h->scratch[k] = private_scratch[static_cast< size_t >(workers) - 1];       /* full length reads: the last one's Observation */
                 }
-                for(int32_t w(0); w < words; ++w) {
-                    out_bases[w * tile.pitch + r] = ((lo >> (16 * w)) & 0xffffu) | (((hi >> (16 * w)) & 0xffffu) << 16);
-                    out_nmask[w * tile.pitch + r] = static_cast< uint16_t >((ambiguous >> (16 * w)) & 0xffffu);
-                }
-                for(int32_t w(0); w < quality_words; ++w) {
-                    out_quality[w * tile.pitch + r] = static_cast< uint32_t >(phred[4 * w]) | (static_cast< uint32_t >(phred[4 * w + 1]) << 8)
-                        | (static_cast< uint32_t >(phred[4 * w + 2]) << 16) | (static_cast< uint32_t >(phred[4 * w + 3]) << 24);
-                }
-                for(int32_t j(0); j < d.nucleotide_cardinality; ++j) { seen[phred[j]] = true; }
+            }
+            if(in_order) {
+                memset(seen, 0, sizeof(seen));
+                pack_range(0, n_reads, h->scratch[k], seen);
             }
             /* quality form: Phred bytes as written above, or indices into a codebook of the distinct values */
             int32_t wanted(tile.quality_bits);
@@ -905,14 +957,22 @@ int phq_pack(phq_handle* handle, int64_t n_reads, int32_t n_input_segments,
                 memcpy(tile.quality_codebook, codebook, static_cast< size_t >(distinct));
                 const int32_t per_word(32 / wanted);
                 const int32_t packed_words((d.nucleotide_cardinality * wanted + 31) / 32);
-                for(int64_t r(0); r < n_reads; ++r) {
-                    uint32_t packed[PHQ_MAX_NUCLEOTIDES / 4];
-                    memset(packed, 0, sizeof(packed));
-                    for(int32_t j(0); j < d.nucleotide_cardinality; ++j) {
-                        const uint8_t q(static_cast< uint8_t >((out_quality[(j >> 2) * tile.pitch + r] >> (8 * (j & 3))) & 0xffu));
-                        packed[j / per_word] |= static_cast< uint32_t >(index_of[q]) << (wanted * (j % per_word));
+                auto encode_range = [&](int64_t begin, int64_t end) {
+                    for(int64_t r(begin); r < end; ++r) {
+                        uint32_t packed[PHQ_MAX_NUCLEOTIDES / 4];
+                        memset(packed, 0, sizeof(packed));
+                        for(int32_t j(0); j < d.nucleotide_cardinality; ++j) {
+                            const uint8_t q(static_cast< uint8_t >((out_quality[(j >> 2) * tile.pitch + r] >> (8 * (j & 3))) & 0xffu));
+                            packed[j / per_word] |= static_cast< uint32_t >(index_of[q]) << (wanted * (j % per_word));
+                        }
+                        for(int32_t w(0); w < packed_words; ++w) { out_quality[w * tile.pitch + r] = packed[w]; }
                     }
-                    for(int32_t w(0); w < packed_words; ++w) { out_quality[w * tile.pitch + r] = packed[w]; }
+                };
+                if(workers <= 1) { encode_range(0, n_reads); }
+                else {
+                    std::vector< std::thread > pool;
+                    for(int w(0); w < workers; ++w) { pool.emplace_back(encode_range, n_reads * w / workers, n_reads * (w + 1) / workers); }
+                    for(auto& t : pool) { t.join(); }
                 }
             }
             tile.quality_bits = wanted;

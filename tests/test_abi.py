@@ -225,3 +225,34 @@ def test_load_job_resolves_imports_relative_to_the_importing_file_and_visits_eac
     assert "import" not in job
     assert job["PL"] == "mine" and job["PM"] == "novaseq" and job["noise"] == 0.4
     assert job["decoder"] == {"a": {"noise": 0.3}, "b": {"base": "a"}}
+
+
+@pytest.mark.parametrize("short", [0.0, 0.01])
+def test_threaded_pack_equals_the_sequential_one(short, monkeypatch):
+    """phq_pack spreads large batches over threads on private Observations and falls back to the in-order pass when a
+    short read makes tiles depend on earlier reads: either way the planes, the quality form and the state left behind
+    are those of PHQ_PACK_THREADS=1."""
+    rng = np.random.default_rng(3)
+    job = {"sample": helpers.random_job(rng, "pamld", (8, 8), 24, reverse=True),
+           "cellular": [helpers.random_job(rng, "mdd", (9,), 12, minimum_distance=3)]}
+    job["cellular"][0]["transform"]["token"] = ["1:1:10"]
+    compiled = compile_job(job)
+    n = 70000
+    code, quality, offset, _ = workload.synthesize(compiled, [0], n, seed=8, short_fraction=short)
+    tail = [c[-400:] for c in code], [q[-400:] for q in quality]
+
+    def run(threads):
+        monkeypatch.setenv("PHQ_PACK_THREADS", str(threads))
+        chain = DecoderChain(compiled, device=-1)
+        first = chain.pack(code, quality, offset, quality_bits=-1)
+        # a second, ragged batch packed by the same handle shows the state the first one left behind
+        more_code, more_quality, more_offset, _ = workload.synthesize(compiled, [0], 500, seed=9, short_fraction=0.5)
+        second = chain.pack(more_code, more_quality, more_offset)
+        return first, second
+    a, b = run(1), run(5)
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        if x is None:
+            assert y is None
+            continue
+        assert x.quality_bits == y.quality_bits and bytes(x.quality_codebook) == bytes(y.quality_codebook)
+        assert np.array_equal(x.bases, y.bases) and np.array_equal(x.nmask, y.nmask) and np.array_equal(x.quality, y.quality)
