@@ -353,7 +353,8 @@ def main():
     #   e2e_full  phq_decode_batch with Phred bytes in and 16-byte {index, distance, f64 confidence} + qcfail byte out
     if not args.no_e2e:
         from pheniqs_b200 import COMPACT_DTYPE, RESULT_DTYPE
-        m = args.e2e_reads or min(n, 1 << 26)
+        # per rank; smaller with many ranks on one host (pinned staging is ~170 B per read and rank, and the ranks share the host's memory system)
+        m = args.e2e_reads or min(n, (1 << 26) // max(1, world // 2))
         host_tiles = chain.allocate_tiles(m, pinned=True)
         for k, t in enumerate(tiles):
             if t is None:
