@@ -965,16 +965,17 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
    mismatches at confidently called positions has p_b <= prior_max * (product of the c largest mismatch
    ratios of the read). The kernel therefore splits the scan:
 
-     fast path   32 barcodes per step and lane, bit sliced. The table holds, per block of 32 barcodes,
-                 position and base, the word of barcodes that have that base there (equality planes). A lane
-                 loads the 16 planes its read selects (5 distinct addresses per request: conflict free), adds
-                 them with a carry-save adder tree of 26 LOP3 (vertical counters) whose carry-in bits hold the
-                 lane's current limit, and the carry out of the tree is the word of barcodes with at most
-                 `limit` counted mismatches. About 50 instructions per 32 x 32 pairs.
-     exact path  the surviving (read, barcode) pairs of a group of 128 barcodes are pooled over the warp and
-                 evaluated one per lane exactly like pamld_kernel does (mismatch mask, subset products, prior),
-                 then every read folds its own candidates in, in index order (first-maximum selection, tie
-                 detection). Pooling makes the cost follow the number of candidates, not the worst lane.
+     fast path   128 barcodes per step and lane, bit sliced. The table holds, per group of 128 barcodes,
+                 position and base, the four words of barcodes that have that base there (equality planes). A
+                 lane loads the 16 planes its read selects (one LDS.128 each; 5 distinct addresses per request:
+                 conflict free), adds the 16 words of each block with a carry-save adder tree of 26 LOP3 (vertical
+                 counters) whose carry-in bits hold the lane's current limit, and the carry out of the tree is the
+                 word of barcodes with at most `limit` counted mismatches. 170 instructions per 32 x 128 pairs.
+     exact path  the surviving (read, barcode) pairs are pooled over the warp in two steps without divergent
+                 loops (non-empty pass words by ballot; 32 words at a time expanded into candidate keys) and
+                 evaluated 32 at a time, one per lane, exactly like pamld_kernel does (mismatch mask, subset
+                 products, prior); then every read folds its own candidates in, in barcode order (first-maximum
+                 selection, tie detection). Pooling makes the cost follow the number of candidates.
 
    `limit` is the largest count c whose bound can still matter: bound[c] >= min(best / 2,
    tolerance * (noise term + rest) / N). Everything below best / 2 cannot be the maximum or a tie; the N
@@ -987,8 +988,10 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
    select the all-ones plane, and ratios above 1 are folded into the bound.
 
    Every warp is its own pipeline: it owns 32 reads at a time (taken from a global counter, so slow reads do
-   not hold a CTA back), streams the table through a private three-stage ring of TMA bulk copies (one 3.3 KB
-   group per stage, completion on the warp's own mbarriers) and never meets a CTA-wide barrier. */
+   not hold a CTA back), streams the planes through a private three-stage ring of TMA bulk copies (one 1,280 byte
+   group per stage, completion on the warp's own mbarriers) and never meets a CTA-wide barrier. Which positions a
+   read counts is its own choice (see the per-read set-up): leaving its weakest positions out is always valid and
+   often sends fewer barcodes to the exact path. */
 constexpr int WHITELIST_STAGES = 3;
 constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold back (a power of two); evaluated 32 at a time */
 constexpr int WHITELIST_WORDS = 128;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 2 x 32); expanded up to 32 at a time */
