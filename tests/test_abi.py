@@ -108,6 +108,14 @@ def test_no_silent_fallback_without_a_gpu():
     with pytest.raises(PheniqsError) as error:
         host_only.decode(tiles, 4)
     assert "no CPU classification path" in str(error.value)
+    # the feed-bytes and tag entry points refuse the same way; the record size is host arithmetic and still answers
+    sequence = np.frombuffer(b"ACGTACGT" * 4, dtype=np.uint8)
+    segments = [(sequence, sequence, None, 8), (sequence, sequence, None, 8)]
+    for call in (lambda: host_only.decode_raw(segments, 4), lambda: host_only.decode_raw_tags(segments, 4)):
+        with pytest.raises(PheniqsError) as error:
+            call()
+        assert "no CPU classification path" in str(error.value)
+    assert host_only.tag_record_bytes() % 16 == 0 and host_only.tag_record_bytes() >= 3 + 16 + 1
 
 
 @pytest.mark.parametrize("short", [0.0, 0.3])
