@@ -523,6 +523,9 @@ void destroy(phq_handle* h) {
             for(auto& b : s.nmask) { b.release(); }
             for(auto& b : s.quality) { b.release(); }
             for(auto& b : s.results) { b.release(); }
+            for(auto& b : s.raw_sequence) { b.release(); }
+            for(auto& b : s.raw_quality) { b.release(); }
+            for(auto& b : s.raw_offset) { b.release(); }
             s.qcfail.release();
             s.aux.release();
             s.aux_length.release();
