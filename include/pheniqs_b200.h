@@ -219,6 +219,16 @@ int phq_decode_batch_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_se
 int phq_decode_batch_raw_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
                                  int32_t phred_offset, const uint8_t* qcfail_in, phq_compact_result* const* compact_results);
 
+/* The same from the form the reference itself keeps a decoded read in: `sequence` holds one BAM 4-bit code per base
+   (Sequence::code, sequence.h:264-300: A=1 C=2 G=4 T=8 N=15, what FastqRecord decoding and bam_seqi produce) and
+   `quality` one Phred value per base with the offset already removed (ObservedSequence::quality). A host whose feed
+   has decoded its input (HTS input, hts.h; or FASTQ through fastq.h:55-78) hands its Segment buffers over unchanged
+   and skips phq_pack: token slicing, reverse complement and the tile packing happen on the device. */
+int phq_decode_batch_bam(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                         const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out);
+int phq_decode_batch_bam_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                                 const uint8_t* qcfail_in, phq_compact_result* const* compact_results);
+
 /* ------------------------------------------------------------------ tags out
 
    What Read::flush (read.h:187-237) assembles from the decoders' verdicts and Auxiliary::encode
@@ -244,6 +254,11 @@ int phq_decode_batch_raw_tags(phq_handle* handle, int64_t n_reads, int32_t n_inp
                               const uint8_t* qcfail_in, uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out,
                               phq_result* const* results);
 
+/* phq_decode_batch_raw_tags over BAM code / Phred byte segments (see phq_decode_batch_bam) */
+int phq_decode_batch_bam_tags(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                              const uint8_t* qcfail_in, uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out,
+                              phq_result* const* results);
+
 int phq_host_alloc(void** pointer, size_t bytes);       /* pinned host memory */
 void phq_host_free(void* pointer);
 
@@ -262,6 +277,26 @@ int phq_totals(phq_handle* handle, uint64_t* count, uint64_t* pf_count);
     selector.cpp:68-77) — is one in-place all-reduce(sum) per plane. */
 int phq_accumulator_buffer(phq_handle* handle, void** device_pointer, int64_t* n_u64, int64_t* n_f64);
 int phq_reset_accumulators(phq_handle* handle);
+
+/* ------------------------------------------------------------------ the collective
+
+   Classifier::collect across the GPUs of a job (classifier.h:87-93, selector.cpp:68-77, 185-196; the serial loop over
+   threads of transcode.cpp:162-179): ONE in-place ncclAllReduce(sum) per plane of the handle's accumulator buffer
+   (u64 counters as ncclUint64, f64 sums as ncclFloat64, grouped into one NCCL launch), asynchronous on `stream`
+   (a cudaStream_t, NULL = default stream). `nccl_comm` is the host's own ncclComm_t with one rank per handle; the
+   library finds NCCL at run time (the libnccl.so.2 already loaded into the process, else the system one), so hosts
+   that never collect do not need it. The collective waits for the last phq_decode_batch_device of this handle
+   whatever stream that ran on. Afterwards every rank holds the sums of the whole job: phq_accumulators,
+   phq_estimate_priors and phq_report answer for the job. A handle whose tables were collected refuses to decode or
+   collect again (PHQ_INTERNAL_ERROR) until phq_reset_accumulators: the sums would be counted once per rank. */
+int phq_collect(phq_handle* handle, void* nccl_comm, void* stream);
+/* Convenience for hosts without a communicator of their own: ncclGetUniqueId on one rank (the 128 bytes travel to the
+   other ranks by whatever channel the host has), ncclCommInitRank on every rank (call after cudaSetDevice-equivalent
+   `device`), ncclCommDestroy. */
+#define PHQ_COMM_ID_BYTES 128
+int phq_comm_unique_id(uint8_t* id /* [PHQ_COMM_ID_BYTES] */);
+int phq_comm_create(const uint8_t* id, int rank, int world_size, int device, void** nccl_comm);
+int phq_comm_destroy(void* nccl_comm);
 
 /*  Classifier::finalize prior estimation (classifier.h:94-124 with pamld.h:40-48,
     decoder.h:77-83, selector.cpp:78-101) from the current accumulators of decoder k. */

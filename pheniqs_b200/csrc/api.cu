@@ -10,6 +10,8 @@
 #include "report.hpp"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>               /* types only: the entry points are resolved at run time (NcclLibrary) */
 
 #include <array>
 #include <cmath>
@@ -124,11 +126,12 @@ struct phq_handle {
     bool timing_valid;
     uint64_t kernel_launches;
     long long sub_batch_reads;              /* reads per in-flight sub-batch of the host-buffer calls */
+    bool collected;                         /* the tables hold the sums of all ranks (phq_collect): no decode / collect until reset */
     std::string error;
 
     phq_handle() : device(0), device_read_group_text(NULL), device_read_group_offset(NULL), read_group_longest(0), tags_ready(false),
         device_phred(NULL), device_accumulators(NULL), n_u64(0), n_f64(0), slots_ready(false),
-        timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0), sub_batch_reads(SUB_BATCH_READS) {
+        timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0), sub_batch_reads(SUB_BATCH_READS), collected(false) {
         /* PHQ_SUB_BATCH_READS: smaller sub-batches (tests exercise the boundaries with small inputs) */
         const char* const value(getenv("PHQ_SUB_BATCH_READS"));
         if(value != NULL && atoll(value) > 0) { sub_batch_reads = atoll(value); }
@@ -638,6 +641,19 @@ template < class F > int guarded(phq_handle* h, F body) {
     }
 }
 
+/* a handle whose accumulators hold the sums of all ranks must be reset before it accumulates again (phq_collect) */
+void refuse_collected(const phq_handle* h) {
+    if(h->collected) { throw InternalError("the accumulators of this handle were collected across ranks; phq_reset_accumulators before the next pass"); }
+}
+/* phq_compact_result carries the barcode index in 24 bits */
+void require_compact_range(const phq_handle* h) {
+    for(const auto& d : h->chain) {
+        if(d.tiled() && d.barcode_cardinality >= 0xffffff) {
+            throw ConfigurationError("a decoder with " + std::to_string(d.barcode_cardinality) + " barcodes does not fit the 24 bit index of phq_compact_result; use the phq_result forms");
+        }
+    }
+}
+
 /* for entry points that are pure host work and therefore also serve host-only handles */
 template < class F > int guarded_host(phq_handle* h, F body) {
     try {
@@ -698,6 +714,12 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         *handle = NULL;
         const Json job(Json::parse(compiled_job_json));
         std::vector< DecoderSpec > chain(parse_compiled_job(job));
+        for(const auto& d : chain) {
+            /* candidate keys of the whitelist scan (owner lane << 27 | barcode) and of the tie pass (slot << 28 | barcode) */
+            if(d.algorithm == PHQ_PAMLD && d.barcode_cardinality >= (1 << 27)) {
+                throw ConfigurationError("a PAMLD codec holds at most 2^27 - 1 barcodes on this path, not " + std::to_string(d.barcode_cardinality));
+            }
+        }
 
         if(device < 0) {
             /* host-only handle: configuration, phq_pack and phq_decoder_describe work; anything that
@@ -990,6 +1012,8 @@ static int decode_device(phq_handle* handle, int64_t n_reads, const phq_tile* de
     return guarded(handle, [&]() {
         if(n_reads < 0 || n_reads > 0x7fffffffll) { throw OverflowError("a batch holds at most 2^31 - 1 reads"); }
         if(device_qcfail == NULL) { throw InternalError("device_qcfail is required"); }
+        refuse_collected(handle);
+        if(device_compact != NULL) { require_compact_range(handle); }
         cudaStream_t s(static_cast< cudaStream_t >(stream));
         PHQ_CUDA(cudaEventRecord(handle->timing_start, s));
         launch_chain(handle, n_reads, device_tiles, device_qcfail, device_results, device_compact, handle->tie_list, s);
@@ -1012,6 +1036,8 @@ static int decode_host(phq_handle* handle, int64_t n_reads, const phq_tile* tile
     return guarded(handle, [&]() {
         phq_handle* h(handle);
         if(n_reads < 0) { throw InternalError("illegal read count"); }
+        refuse_collected(h);
+        if(compact != NULL) { require_compact_range(h); }
         ensure_slots(h);
         const size_t n_decoders(h->chain.size());
         const long long sub(n_reads < h->sub_batch_reads ? (n_reads > 0 ? n_reads : 1) : h->sub_batch_reads);
@@ -1090,6 +1116,7 @@ struct RawReader {
     const DecoderSpec& d;
     const phq_raw_segment* segments;
     int32_t phred_offset;
+    bool bam_input;
     int64_t begin(int32_t i, int64_t r) const { return segments[i].offset != NULL ? segments[i].offset[r] : r * segments[i].length; }
     int32_t length(int32_t i, int64_t r) const { return segments[i].offset != NULL ? static_cast< int32_t >(segments[i].offset[r + 1] - segments[i].offset[r]) : static_cast< int32_t >(segments[i].length); }
     int32_t observed_length(int64_t r, int32_t s) const {
@@ -1112,7 +1139,7 @@ struct RawReader {
             if(size <= 0) { continue; }
             if(i < at + size) {
                 const int64_t source(begin(t.input_segment_index, r) + (t.reverse_complement ? (end - (i - at) - 1) : (start + (i - at))));
-                code = ascii_to_bam(segments[t.input_segment_index].sequence[source]);
+                code = bam_input ? static_cast< uint8_t >(segments[t.input_segment_index].sequence[source] & 0xf) : ascii_to_bam(segments[t.input_segment_index].sequence[source]);
                 if(t.reverse_complement) { code = BAM_REVERSE_COMPLEMENT[code & 0xf]; }
                 quality = static_cast< uint8_t >(segments[t.input_segment_index].quality[source] - phred_offset);
                 return;
@@ -1215,7 +1242,7 @@ void ensure_tags(phq_handle* h) {
 
 int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments, int32_t phred_offset,
                const uint8_t* qcfail_in, phq_result* const* results, phq_compact_result* const* compact, uint8_t* qcfail_out,
-               uint8_t* aux = NULL, int32_t* aux_length = NULL, int32_t aux_stride = 0) {
+               uint8_t* aux = NULL, int32_t* aux_length = NULL, int32_t aux_stride = 0, bool bam_input = false) {
     return guarded(handle, [&]() {
         phq_handle* h(handle);
         const bool tags(aux != NULL);
@@ -1227,6 +1254,8 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
         }
         if(n_reads < 0 || n_input_segments < 0 || (n_input_segments > 0 && segments == NULL)) { throw InternalError("illegal argument"); }
         if(n_input_segments > PACK_MAX_INPUT_SEGMENTS) { throw ConfigurationError("more than " + std::to_string(PACK_MAX_INPUT_SEGMENTS) + " input segments are not supported on this path"); }
+        refuse_collected(h);
+        if(compact != NULL) { require_compact_range(h); }
         ensure_slots(h);
         const size_t n_decoders(h->chain.size());
         std::vector< bool > used(static_cast< size_t >(n_input_segments), false);
@@ -1305,6 +1334,7 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
                     plan.nucleotide_cardinality = d.nucleotide_cardinality;
                     plan.stale_semantics = d.algorithm == PHQ_PAMLD ? 1 : 0;
                     plan.phred_offset = phred_offset;
+                    plan.bam_input = bam_input ? 1 : 0;
                     for(int32_t i(0); i <= d.segment_cardinality; ++i) { plan.segment_offset[i] = d.segment_offset[i]; }
                     for(size_t i(0); i < d.transform.size(); ++i) {
                         const TransformSpec& t(d.transform[i]);
@@ -1316,7 +1346,7 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
                     /* the kernel indexes reads from 0: move the views to this sub-batch */
                     for(int32_t i(0); i < n_input_segments; ++i) { if(plan.input[i].offset == NULL) { plan.input[i].first = begin; } }
                     if(plan.stale_semantics) {
-                        const RawReader reader{ d, segments, phred_offset };
+                        const RawReader reader{ d, segments, phred_offset, bam_input };
                         reader.state_after(begin - 1, h->scratch[k], plan.carry_code, plan.carry_quality);
                     }
                     PHQ_CUDA(launch_pack(plan, count, s.bases[k].pointer, s.nmask[k].pointer, s.quality[k].pointer, sub, h->geometry.multiprocessor_count, s.stream));
@@ -1340,6 +1370,7 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
                 memset(&plan, 0, sizeof(plan));
                 plan.decoder_cardinality = static_cast< int32_t >(n_decoders);
                 plan.phred_offset = phred_offset;
+                plan.bam_input = bam_input ? 1 : 0;
                 plan.stride = aux_stride;
                 plan.read_group_text = h->device_read_group_text;
                 plan.read_group_offset = h->device_read_group_offset;
@@ -1387,7 +1418,7 @@ int decode_raw(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, co
             const DecoderSpec& d(h->chain[k]);
             if(!d.tiled() || d.algorithm != PHQ_PAMLD) { continue; }
             uint8_t code[PHQ_MAX_NUCLEOTIDES], quality[PHQ_MAX_NUCLEOTIDES];
-            const RawReader reader{ d, segments, phred_offset };
+            const RawReader reader{ d, segments, phred_offset, bam_input };
             reader.state_after(n_reads - 1, h->scratch[k], code, quality);
             for(int32_t sgm(0); sgm < d.segment_cardinality; ++sgm) {
                 for(int32_t i(0); i < d.segment_length[sgm]; ++i) {
@@ -1425,6 +1456,21 @@ int phq_decode_batch_raw_tags(phq_handle* handle, int64_t n_reads, int32_t n_inp
                               const uint8_t* qcfail_in, uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out, phq_result* const* results) {
     if(aux == NULL) { return PHQ_INTERNAL_ERROR; }
     return decode_raw(handle, n_reads, n_input_segments, segments, phred_offset, qcfail_in, results, NULL, qcfail_out, aux, aux_length, aux_stride);
+}
+
+/* the same three calls over the reference's own in-memory form of a segment (sequence.h:264-300): BAM codes, Phred bytes */
+int phq_decode_batch_bam(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                         const uint8_t* qcfail_in, phq_result* const* results, uint8_t* qcfail_out) {
+    return decode_raw(handle, n_reads, n_input_segments, segments, 0, qcfail_in, results, NULL, qcfail_out, NULL, NULL, 0, true);
+}
+int phq_decode_batch_bam_compact(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                                 const uint8_t* qcfail_in, phq_compact_result* const* compact_results) {
+    return decode_raw(handle, n_reads, n_input_segments, segments, 0, qcfail_in, NULL, compact_results, NULL, NULL, NULL, 0, true);
+}
+int phq_decode_batch_bam_tags(phq_handle* handle, int64_t n_reads, int32_t n_input_segments, const phq_raw_segment* segments,
+                              const uint8_t* qcfail_in, uint8_t* aux, int32_t aux_stride, int32_t* aux_length, uint8_t* qcfail_out, phq_result* const* results) {
+    if(aux == NULL) { return PHQ_INTERNAL_ERROR; }
+    return decode_raw(handle, n_reads, n_input_segments, segments, 0, qcfail_in, results, NULL, qcfail_out, aux, aux_length, aux_stride, true);
 }
 
 int phq_host_alloc(void** pointer, size_t bytes) {
@@ -1470,6 +1516,7 @@ int phq_reset_accumulators(phq_handle* handle) {
     return guarded(handle, [&]() {
         PHQ_CUDA(cudaDeviceSynchronize());
         PHQ_CUDA(cudaMemset(handle->device_accumulators, 0, static_cast< size_t >(handle->n_u64 + handle->n_f64) * 8));
+        handle->collected = false;
     });
 }
 
@@ -1527,6 +1574,107 @@ int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* 
         upload_grid(handle, static_cast< size_t >(decoder));
         upload_whitelist(handle, static_cast< size_t >(decoder));
         refresh_params(handle, static_cast< size_t >(decoder));
+    });
+}
+
+/* ------------------------------------------------------------------ the collective (classifier.h:87-93 across GPUs) */
+extern "C++" {
+namespace {
+
+/*  NCCL resolved at run time: dlopen("libnccl.so.2") returns the copy already mapped into the process when there is
+    one (a PyTorch host brings its own), else the system library. A host that never collects never needs it. */
+struct NcclLibrary {
+    void* library;
+    ncclResult_t (*get_unique_id)(ncclUniqueId*);
+    ncclResult_t (*comm_init_rank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*comm_destroy)(ncclComm_t);
+    ncclResult_t (*comm_count)(const ncclComm_t, int*);
+    ncclResult_t (*all_reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*group_start)();
+    ncclResult_t (*group_end)();
+    const char* (*get_error_string)(ncclResult_t);
+    NcclLibrary() : library(NULL) {
+        const char* const candidates[] = { "libnccl.so.2", "libnccl.so" };
+        for(const char* name : candidates) {
+            library = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if(library != NULL) { break; }
+        }
+        if(library == NULL) { throw InternalError(std::string("NCCL is not available : ") + dlerror()); }
+        resolve(get_unique_id, "ncclGetUniqueId");
+        resolve(comm_init_rank, "ncclCommInitRank");
+        resolve(comm_destroy, "ncclCommDestroy");
+        resolve(comm_count, "ncclCommCount");
+        resolve(all_reduce, "ncclAllReduce");
+        resolve(group_start, "ncclGroupStart");
+        resolve(group_end, "ncclGroupEnd");
+        resolve(get_error_string, "ncclGetErrorString");
+    }
+    template < class F > void resolve(F& target, const char* name) {
+        target = reinterpret_cast< F >(dlsym(library, name));
+        if(target == NULL) { throw InternalError(std::string("NCCL symbol missing : ") + name); }
+    }
+    void check(ncclResult_t status, const char* what) const {
+        if(status != ncclSuccess) { throw InternalError(std::string("Internal error : NCCL ") + what + " : " + get_error_string(status)); }
+    }
+};
+const NcclLibrary& nccl() {
+    static const NcclLibrary instance;
+    return instance;
+}
+
+template < class F > int guarded_global(F body) {
+    try { body(); return PHQ_OK; }
+    catch(const phq::Error& e) { global_error = e.what(); return e.code; }
+    catch(const std::exception& e) { global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
+}
+
+}   /* namespace */
+}   /* extern "C++" */
+
+int phq_comm_unique_id(uint8_t* id) {
+    return guarded_global([&]() {
+        if(id == NULL) { throw InternalError("null argument"); }
+        static_assert(sizeof(ncclUniqueId) == PHQ_COMM_ID_BYTES, "PHQ_COMM_ID_BYTES is NCCL_UNIQUE_ID_BYTES");
+        ncclUniqueId value;
+        nccl().check(nccl().get_unique_id(&value), "ncclGetUniqueId");
+        memcpy(id, &value, sizeof(value));
+    });
+}
+
+int phq_comm_create(const uint8_t* id, int rank, int world_size, int device, void** nccl_comm) {
+    return guarded_global([&]() {
+        if(id == NULL || nccl_comm == NULL || rank < 0 || rank >= world_size) { throw InternalError("illegal argument"); }
+        PHQ_CUDA(cudaSetDevice(device));
+        ncclUniqueId value;
+        memcpy(&value, id, sizeof(value));
+        ncclComm_t comm(NULL);
+        nccl().check(nccl().comm_init_rank(&comm, world_size, value, rank), "ncclCommInitRank");
+        *nccl_comm = comm;
+    });
+}
+
+int phq_comm_destroy(void* nccl_comm) {
+    return guarded_global([&]() {
+        if(nccl_comm != NULL) { nccl().check(nccl().comm_destroy(static_cast< ncclComm_t >(nccl_comm)), "ncclCommDestroy"); }
+    });
+}
+
+int phq_collect(phq_handle* handle, void* nccl_comm, void* stream) {
+    return guarded(handle, [&]() {
+        if(nccl_comm == NULL) { throw InternalError("null communicator"); }
+        refuse_collected(handle);
+        const NcclLibrary& library(nccl());
+        ncclComm_t comm(static_cast< ncclComm_t >(nccl_comm));
+        cudaStream_t s(static_cast< cudaStream_t >(stream));
+        int world(0);
+        library.check(library.comm_count(comm, &world), "ncclCommCount");
+        /* behind the last device batch of this handle, whatever stream it was launched on */
+        if(handle->timing_valid && handle->timing_stream != s) { PHQ_CUDA(cudaStreamWaitEvent(s, handle->timing_stop, 0)); }
+        library.check(library.group_start(), "ncclGroupStart");
+        library.check(library.all_reduce(handle->u64_plane(), handle->u64_plane(), static_cast< size_t >(handle->n_u64), ncclUint64, ncclSum, comm, s), "ncclAllReduce (u64 plane)");
+        library.check(library.all_reduce(handle->f64_plane(), handle->f64_plane(), static_cast< size_t >(handle->n_f64), ncclFloat64, ncclSum, comm, s), "ncclAllReduce (f64 plane)");
+        library.check(library.group_end(), "ncclGroupEnd");
+        handle->collected = world > 1;
     });
 }
 

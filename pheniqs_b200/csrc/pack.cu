@@ -44,10 +44,11 @@ struct TokenView {
     int token_cardinality;
     const RawSegmentView* input;
     int phred_offset;
+    int bam_input;
 };
 __device__ __forceinline__ TokenView view_of(const PackPlan& plan) {
     TokenView v;
-    v.token = plan.token; v.token_cardinality = plan.token_cardinality; v.input = plan.input; v.phred_offset = plan.phred_offset;
+    v.token = plan.token; v.token_cardinality = plan.token_cardinality; v.input = plan.input; v.phred_offset = plan.phred_offset; v.bam_input = plan.bam_input;
     return v;
 }
 
@@ -81,7 +82,8 @@ __device__ __forceinline__ Base fetch(const TokenView& plan, const uint8_t* tabl
             const int within = i - at;
             const long long source = read_begin(v, r) + (t.reverse_complement ? (end - within - 1) : (start + within));
             const uint32_t letter = v.sequence[source];
-            uint32_t code = (letter >= 0x30u && letter < 0x80u) ? table[letter - 0x30u] : 15u;
+            /* FASTQ text through AsciiToAmbiguousBam (iupac.h:153-171), or the BAM code a decoded feed already holds */
+            uint32_t code = plan.bam_input ? (letter & 0xfu) : ((letter >= 0x30u && letter < 0x80u) ? table[letter - 0x30u] : 15u);
             if(t.reverse_complement) { code = table[80 + code]; }
             b.code = code;
             b.quality = (static_cast< uint32_t >(v.quality[source]) - static_cast< uint32_t >(plan.phred_offset)) & 0xffu;     /* char arithmetic, fastq.h:73 */
@@ -190,7 +192,7 @@ __device__ __forceinline__ void put_string(TagWriter& w, const TagPlan& plan, co
         const bool corrected = content == TAG_CORRECTED_SEQUENCE || content == TAG_CORRECTED_QUALITY;
         if(corrected && d.results == nullptr) { continue; }
         TokenView view;
-        view.token = d.token; view.token_cardinality = d.token_cardinality; view.input = plan.input; view.phred_offset = plan.phred_offset;
+        view.token = d.token; view.token_cardinality = d.token_cardinality; view.input = plan.input; view.phred_offset = plan.phred_offset; view.bam_input = plan.bam_input;
         const uint8_t* barcode = nullptr;
         if(corrected) { barcode = d.barcode_code + static_cast< long long >(d.results[r].index) * d.nucleotide_cardinality; }
         for(int s = 0; s < d.segment_cardinality; ++s) {

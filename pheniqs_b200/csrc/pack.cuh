@@ -42,6 +42,7 @@ struct PackPlan {
     int32_t nucleotide_cardinality;
     int32_t stale_semantics;        /* PAMLD: expected length is read, terminator then bytes of earlier reads (barcode.h:150) */
     int32_t phred_offset;
+    int32_t bam_input;              /* the segments hold the reference's in-memory form (one BAM 4-bit code and one Phred byte per base, sequence.h:264-300) instead of FASTQ text */
     int32_t segment_offset[PHQ_MAX_SEGMENTS + 1];
     PackToken token[PACK_MAX_TOKENS];
     /* the Observation as the reads before this launch left it, by concatenated position: BAM code and Phred byte */
@@ -75,6 +76,7 @@ struct TagDecoder {
 struct TagPlan {
     int32_t decoder_cardinality;
     int32_t phred_offset;
+    int32_t bam_input;              /* as PackPlan */
     int32_t stride;                 /* bytes per record in `aux` (multiple of 4) */
     const uint8_t* read_group_text; /* device: read group IDs of the sample decoder, row i at [offset[i], offset[i + 1]) */
     const int32_t* read_group_offset;

@@ -241,35 +241,45 @@ class DecoderChain:
         check(self.lib.phq_decode_batch_compact(self.handle, n_reads, self._tile_array(tiles), None if qin is None else qin.ctypes.data, pointers), self.handle)
         return results
 
-    def decode_raw(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, compact: bool = False, results=None, qcfail_out=None):
-        """phq_decode_batch_raw[_compact]: the bytes of the FASTQ records in, packing on the device.
-
-        segments[i] = (sequence uint8 [bytes], quality uint8 [bytes], offset int64 [n_reads + 1] or None, length) or None
-        for an input segment no token refers to."""
+    def _raw_segment_array(self, segments):
         array = (RawSegment * max(len(segments), 1))()
         keep = []
         for i, g in enumerate(segments):
             if g is None:
                 continue
-            sequence, quality, offset, length = g
+            sequence, quality, offset, length = g[:4]
             sequence = np.ascontiguousarray(sequence, dtype=np.uint8)
             quality = np.ascontiguousarray(quality, dtype=np.uint8)
             offset = None if offset is None else np.ascontiguousarray(offset, dtype=np.int64)
             keep.append((sequence, quality, offset))
             array[i] = RawSegment(sequence.ctypes.data, quality.ctypes.data, None if offset is None else offset.ctypes.data, int(length))
+        return array, keep
+
+    def decode_raw(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, compact: bool = False, results=None, qcfail_out=None, bam: bool = False):
+        """phq_decode_batch_raw[_compact]: the bytes of the FASTQ records in, packing on the device; with bam=True
+        phq_decode_batch_bam[_compact]: the reference's own decoded form in (one BAM code and one Phred byte per base).
+
+        segments[i] = (sequence uint8 [bytes], quality uint8 [bytes], offset int64 [n_reads + 1] or None, length) or None
+        for an input segment no token refers to."""
+        array, keep = self._raw_segment_array(segments)
         if results is None:
             dtype = COMPACT_DTYPE if compact else RESULT_DTYPE
             results = [np.zeros(n_reads, dtype=dtype) if (info.has_tile or not compact) else None for info in self.info]
         pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
         qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
+        qin_pointer = None if qin is None else qin.ctypes.data
         if compact:
-            check(self.lib.phq_decode_batch_raw_compact(self.handle, n_reads, len(segments), array, phred_offset,
-                                                        None if qin is None else qin.ctypes.data, pointers), self.handle)
+            if bam:
+                check(self.lib.phq_decode_batch_bam_compact(self.handle, n_reads, len(segments), array, qin_pointer, pointers), self.handle)
+            else:
+                check(self.lib.phq_decode_batch_raw_compact(self.handle, n_reads, len(segments), array, phred_offset, qin_pointer, pointers), self.handle)
             return results
         if qcfail_out is None:
             qcfail_out = np.zeros(n_reads, dtype=np.uint8)
-        check(self.lib.phq_decode_batch_raw(self.handle, n_reads, len(segments), array, phred_offset,
-                                            None if qin is None else qin.ctypes.data, pointers, qcfail_out.ctypes.data), self.handle)
+        if bam:
+            check(self.lib.phq_decode_batch_bam(self.handle, n_reads, len(segments), array, qin_pointer, pointers, qcfail_out.ctypes.data), self.handle)
+        else:
+            check(self.lib.phq_decode_batch_raw(self.handle, n_reads, len(segments), array, phred_offset, qin_pointer, pointers, qcfail_out.ctypes.data), self.handle)
         return results, qcfail_out
 
     def tag_record_bytes(self) -> int:
@@ -279,20 +289,11 @@ class DecoderChain:
         return value.value
 
     def decode_raw_tags(self, segments, n_reads: int, phred_offset: int = 33, qcfail_in=None, stride: int = 0, want_results: bool = False,
-                        aux=None, aux_length=None, qcfail_out=None):
-        """phq_decode_batch_raw_tags: FASTQ bytes in, the BAM auxiliary block of every read out.
+                        aux=None, aux_length=None, qcfail_out=None, bam: bool = False):
+        """phq_decode_batch_raw_tags (bam=True: phq_decode_batch_bam_tags): feed bytes in, the BAM auxiliary block of every
+        read out.
         Returns (aux uint8 [n_reads, stride], aux_length int32 [n_reads], qcfail uint8 [n_reads][, results])."""
-        array = (RawSegment * max(len(segments), 1))()
-        keep = []
-        for i, g in enumerate(segments):
-            if g is None:
-                continue
-            sequence, quality, offset, length = g
-            sequence = np.ascontiguousarray(sequence, dtype=np.uint8)
-            quality = np.ascontiguousarray(quality, dtype=np.uint8)
-            offset = None if offset is None else np.ascontiguousarray(offset, dtype=np.int64)
-            keep.append((sequence, quality, offset))
-            array[i] = RawSegment(sequence.ctypes.data, quality.ctypes.data, None if offset is None else offset.ctypes.data, int(length))
+        array, keep = self._raw_segment_array(segments)
         stride = stride or self.tag_record_bytes()
         aux = np.zeros((max(n_reads, 1), stride), dtype=np.uint8) if aux is None else aux
         aux_length = np.zeros(max(n_reads, 1), dtype=np.int32) if aux_length is None else aux_length
@@ -300,8 +301,13 @@ class DecoderChain:
         results = [np.zeros(n_reads, dtype=RESULT_DTYPE) if (want_results and info.has_tile) else None for info in self.info]
         pointers = (C.c_void_p * self.n_decoders)(*[None if r is None else r.ctypes.data for r in results])
         qin = None if qcfail_in is None else np.ascontiguousarray(qcfail_in, dtype=np.uint8)
-        check(self.lib.phq_decode_batch_raw_tags(self.handle, n_reads, len(segments), array, phred_offset, None if qin is None else qin.ctypes.data,
-                                                 aux.ctypes.data, stride, aux_length.ctypes.data, qcfail_out.ctypes.data, pointers), self.handle)
+        qin_pointer = None if qin is None else qin.ctypes.data
+        if bam:
+            check(self.lib.phq_decode_batch_bam_tags(self.handle, n_reads, len(segments), array, qin_pointer,
+                                                     aux.ctypes.data, stride, aux_length.ctypes.data, qcfail_out.ctypes.data, pointers), self.handle)
+        else:
+            check(self.lib.phq_decode_batch_raw_tags(self.handle, n_reads, len(segments), array, phred_offset, qin_pointer,
+                                                     aux.ctypes.data, stride, aux_length.ctypes.data, qcfail_out.ctypes.data, pointers), self.handle)
         out = (aux[:n_reads], aux_length[:n_reads], qcfail_out[:n_reads])
         return out + (results,) if want_results else out
 
@@ -373,15 +379,33 @@ class DecoderChain:
         f = torch.as_tensor(_Raw(pointer.value + 8 * n_u64.value, n_f64.value, "<f8"), device=device)
         return u, f
 
-    def collect(self, group=None):
-        """Classifier::collect across ranks (classifier.h:87-93): one all-reduce(sum) per plane, in place."""
+    def communicator(self, group=None):
+        """The ncclComm_t phq_collect reduces over: one rank per process of `group`, created once per (group, device)
+        from an id that rank 0 draws (phq_comm_unique_id) and torch.distributed carries to the other ranks."""
+        import torch.distributed as dist
+        key = (id(group), self.device)
+        if key not in _COMMUNICATORS:
+            ident = (C.c_uint8 * 128)()
+            if dist.get_rank(group) == 0:
+                check(self.lib.phq_comm_unique_id(ident))
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = (C.c_uint8 * 128)(*box[0])
+            comm = C.c_void_p()
+            check(self.lib.phq_comm_create(ident, dist.get_rank(group), dist.get_world_size(group), self.device, C.byref(comm)))
+            _COMMUNICATORS[key] = comm
+        return _COMMUNICATORS[key]
+
+    def collect(self, group=None, stream=None):
+        """Classifier::collect across ranks (classifier.h:87-93): phq_collect, one grouped in-place ncclAllReduce(sum)
+        over the two accumulator planes, asynchronous on `stream` (default: torch's current stream). Afterwards the
+        handle answers for the whole job and refuses to accumulate again until reset()."""
         import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
-        u, f = self.accumulator_tensors()
-        torch.cuda.current_stream(u.device).synchronize()
-        all_reduce_accumulators(u, f, group)
+        stream = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", self.device))
+        check(self.lib.phq_collect(self.handle, self.communicator(group), C.c_void_p(stream.cuda_stream)), self.handle)
 
     def report(self, incoming=(0, 0), precision: int = 15, text: bool = False):
         """The decoder sections of the job report (phq_report) from this handle's device accumulators."""
@@ -433,9 +457,13 @@ class DecoderChain:
         return {"kernel_launches": a.value, "exact_path_reads": b.value, "threshold_band_reads": c.value}
 
 
+_COMMUNICATORS = {}
+
+
 def all_reduce_accumulators(u64_plane, f64_plane, group=None):
-    """Sum the accumulator planes of all ranks in place. u64 counters travel as int64 bit patterns
-    (two's complement addition is the same operation); works for NCCL (device tensors) and gloo (CPU)."""
+    """Sum accumulator planes held as torch tensors in place over torch.distributed: what phq_collect does inside the
+    library, for hosts that keep their tables elsewhere (the gloo test reduces CPU tables with it). u64 counters
+    travel as int64 bit patterns (two's complement addition is the same operation)."""
     import torch.distributed as dist
     dist.all_reduce(u64_plane, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(f64_plane, op=dist.ReduceOp.SUM, group=group)

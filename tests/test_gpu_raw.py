@@ -1,6 +1,10 @@
 """Feed bytes in: phq_decode_batch_raw packs on the device what phq_pack packs on the host.
 Parity bar: every tile bit — hence every result, flag and accumulator — identical to the host packed path, including
-the state short tokens leave behind across sub-batches and across calls."""
+the state short tokens leave behind across sub-batches and across calls.
+
+Anchoring: the first three tests compare the device packer with the host packer (product against product); the host
+packer is pinned on the oracle's Rule::apply on the CPU (tests/test_abi.py) and the raw path on oracle/_ref in
+tests/test_gpu_tags.py. test_bam_segments_equal_the_oracle compares the BAM-code form with the oracle directly."""
 import copy
 import os
 
@@ -8,6 +12,7 @@ import numpy as np
 import pytest
 
 import helpers
+from oracle import oracle as O
 from pheniqs_b200 import DecoderChain, compile_job, workload
 
 pytestmark = pytest.mark.gpu
@@ -121,3 +126,42 @@ def test_fixed_length_segments_and_compact_records():
     assert np.array_equal(results[0]["packed"], expected[0]["packed"])
     assert np.array_equal(results[0]["error_probability"].view(np.uint32), expected[0]["error_probability"].view(np.uint32))
     assert "pack" not in os.environ.get("PHQ_DISABLE", "")
+
+
+@pytest.mark.parametrize("short", [0.0, 0.25])
+@pytest.mark.parametrize("sub_batch", [0, 555])
+def test_bam_segments_equal_the_oracle(short, sub_batch, monkeypatch):
+    """phq_decode_batch_bam: the reference's own in-memory form of a segment (Sequence::code BAM bytes and Phred bytes,
+    sequence.h:264-300) goes to the device unchanged; token slicing, reverse complement, knit and packing happen there.
+    Checked against the oracle (the reference's classes when oracle/_ref is built) on the very same arrays."""
+    if sub_batch:
+        monkeypatch.setenv("PHQ_SUB_BATCH_READS", str(sub_batch))
+    rng = np.random.default_rng(131 + sub_batch)
+    for label, job, spelled in jobs(rng):
+        n = 8000
+        code, quality, offset, _ = workload.synthesize(compile_job(job), [0, 0], n, seed=23, short_fraction=short)
+        compiled = compile_job(spelled)
+        qcfail = (rng.random(n) < 0.1).astype(np.uint8)
+        chain = DecoderChain(compiled, device=0)
+        segments = [(code[i], quality[i], offset[i], 0) for i in range(len(code))]
+        results, flags = chain.decode_raw(segments, n, 0, qcfail, bam=True)
+        checker = O.best_oracle(compiled, len(code))
+        expected = checker.decode(O.ReadBatch(code, quality, offset, qcfail))
+        assert np.array_equal(flags, expected.qcfail), label
+        for k, info in enumerate(chain.info):
+            if info.algorithm == 0:
+                helpers.compare_pamld(results[k], expected.index[:, k], expected.distance[:, k], expected.confidence[:, k], "%s decoder %d" % (label, k))
+            elif info.has_tile:
+                assert np.array_equal(results[k]["index"], expected.index[:, k]), (label, k)
+                assert np.array_equal(results[k]["distance"], expected.distance[:, k]), (label, k)
+            u, f = chain.accumulators(k)
+            eu, ef = checker.accumulators(k)
+            assert np.array_equal(u, eu), (label, k)
+            assert np.allclose(f, ef, rtol=1e-9, atol=0), (label, k)
+        assert chain.totals() == checker.totals()
+        # and the compact records of the same call family
+        again = DecoderChain(compiled, device=0)
+        compact = again.decode_raw(segments, n, 0, qcfail, compact=True, bam=True)
+        for k, info in enumerate(again.info):
+            if info.has_tile:
+                assert np.array_equal(compact[k]["packed"] & 0xffffff, results[k]["index"].astype(np.uint32)), (label, k)

@@ -94,6 +94,12 @@ def test_tags_equal_the_reference(short, sub_batch, monkeypatch):
         assert np.array_equal(flags, expected_flags), label
         for r in range(n):
             compare(parse_auxiliary(aux[r, :length[r]]), expected[r], "%s, read %d" % (label, r))
+        # the same block from the reference's decoded form of the segments (phq_decode_batch_bam_tags)
+        if not sub_batch:
+            decoded = DecoderChain(compiled, device=0)
+            aux2, length2, flags2 = decoded.decode_raw_tags([(c, q, o, 0) for c, q, o in zip(code, quality, offset)], n, 0, qcfail, bam=True)
+            assert np.array_equal(aux2, aux) and np.array_equal(length2, length) and np.array_equal(flags2, flags), label
+            decoded.close()
         # the tag path leaves the accumulators as any other decode call does
         for k, info in enumerate(chain.info):
             u, _ = chain.accumulators(k)
