@@ -277,6 +277,9 @@ int phq_totals(phq_handle* handle, uint64_t* count, uint64_t* pf_count);
     selector.cpp:68-77) — is one in-place all-reduce(sum) per plane. */
 int phq_accumulator_buffer(phq_handle* handle, void** device_pointer, int64_t* n_u64, int64_t* n_f64);
 int phq_reset_accumulators(phq_handle* handle);
+/* the same without synchronising the device: the tables are cleared in `stream` order (a cudaStream_t, NULL = default
+   stream), for hosts that keep decode -> collect -> reset on one stream */
+int phq_reset_accumulators_async(phq_handle* handle, void* stream);
 
 /* ------------------------------------------------------------------ the collective
 

@@ -71,7 +71,7 @@ EXPORTS = (
     "phq_decode_batch_device", "phq_decode_batch_device_compact", "phq_decode_batch_raw", "phq_decode_batch_raw_compact",
     "phq_decode_batch_raw_tags", "phq_tag_record_bytes", "phq_decode_batch_bam", "phq_decode_batch_bam_compact", "phq_decode_batch_bam_tags",
     "phq_host_alloc", "phq_host_free", "phq_accumulators", "phq_totals", "phq_accumulator_buffer",
-    "phq_reset_accumulators", "phq_collect", "phq_comm_unique_id", "phq_comm_create", "phq_comm_destroy", "phq_estimate_priors", "phq_set_priors", "phq_report", "phq_encode_report", "phq_adjust_job",
+    "phq_reset_accumulators", "phq_reset_accumulators_async", "phq_collect", "phq_comm_unique_id", "phq_comm_create", "phq_comm_destroy", "phq_estimate_priors", "phq_set_priors", "phq_report", "phq_encode_report", "phq_adjust_job",
     "phq_statistics", "phq_kernel_description",
     "phq_last_kernel_milliseconds",
 )
@@ -120,6 +120,7 @@ def library() -> C.CDLL:
     lib.phq_totals.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.phq_accumulator_buffer.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_int64), P(C.c_int64)]
     lib.phq_reset_accumulators.argtypes = [C.c_void_p]
+    lib.phq_reset_accumulators_async.argtypes = [C.c_void_p, C.c_void_p]
     lib.phq_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.phq_comm_unique_id.argtypes = [C.c_void_p]
     lib.phq_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, P(C.c_void_p)]

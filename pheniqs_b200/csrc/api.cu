@@ -108,6 +108,9 @@ struct phq_handle {
     std::vector< unsigned char* > device_whitelist;    /* chunked whitelist blobs (kernels.cuh), NULL where not applicable */
     std::vector< int32_t > whitelist_chunks;
     std::vector< double > prior_maximum;
+    std::vector< FastEntry* > device_fast;     /* f32 form of the barcode tables for the prefilter scans, NULL where not applicable */
+    float* device_phred32;                      /* f32 mismatch ratios */
+    bool fast_enabled;                          /* PHQ_DISABLE_FAST=1 keeps every PAMLD decoder on the exact scans */
     std::vector< void* > device_grid;          /* combinatorial codec blobs (kernels.cuh), NULL where not applicable */
     std::vector< int32_t > grid_shape;         /* per decoder: grid_a, grid_b, grid_entries, grid_split, grid_dense, grid_uniform */
     double* device_phred;
@@ -129,12 +132,14 @@ struct phq_handle {
     bool collected;                         /* the tables hold the sums of all ranks (phq_collect): no decode / collect until reset */
     std::string error;
 
-    phq_handle() : device(0), device_read_group_text(NULL), device_read_group_offset(NULL), read_group_longest(0), tags_ready(false),
+    phq_handle() : device(0), device_phred32(NULL), fast_enabled(true), device_read_group_text(NULL), device_read_group_offset(NULL), read_group_longest(0), tags_ready(false),
         device_phred(NULL), device_accumulators(NULL), n_u64(0), n_f64(0), slots_ready(false),
         timing_start(NULL), timing_stop(NULL), timing_stream(NULL), timing_valid(false), kernel_launches(0), sub_batch_reads(SUB_BATCH_READS), collected(false) {
         /* PHQ_SUB_BATCH_READS: smaller sub-batches (tests exercise the boundaries with small inputs) */
         const char* const value(getenv("PHQ_SUB_BATCH_READS"));
         if(value != NULL && atoll(value) > 0) { sub_batch_reads = atoll(value); }
+        const char* const disable(getenv("PHQ_DISABLE_FAST"));
+        if(disable != NULL && atoi(disable) > 0) { fast_enabled = false; }
     }
 
     unsigned long long* u64_plane() const { return reinterpret_cast< unsigned long long* >(device_accumulators); }
@@ -181,6 +186,28 @@ void upload_barcodes(phq_handle* h, size_t k) {
         table[b] = e;
     }
     PHQ_CUDA(cudaMemcpy(h->device_barcodes[k], table.data(), table.size() * sizeof(BarcodeEntry), cudaMemcpyHostToDevice));
+}
+
+/* the barcode table in the form the f32 prefilter scans read (pamld_fast_kernel) */
+void upload_fast(phq_handle* h, size_t k) {
+    const DecoderSpec& d(h->chain[k]);
+    if(h->device_fast[k] != NULL) { cudaFree(h->device_fast[k]); h->device_fast[k] = NULL; }
+    if(d.algorithm != PHQ_PAMLD || !h->fast_enabled) { return; }
+    std::vector< FastEntry > table(static_cast< size_t >(d.barcode_cardinality));
+    for(int32_t b(0); b < d.barcode_cardinality; ++b) {
+        FastEntry e;
+        e.lo = 0; e.hi = 0; e.pad = 0;
+        for(int32_t j(0); j < d.nucleotide_cardinality; ++j) {
+            const uint8_t code(d.barcode[static_cast< size_t >(b) * d.nucleotide_cardinality + j]);
+            const uint32_t two(code == 1 ? 0u : code == 2 ? 1u : code == 4 ? 2u : 3u);
+            e.lo |= (two & 1u) << j;
+            e.hi |= (two >> 1) << j;
+        }
+        e.prior = static_cast< float >(d.concentration[b]);
+        table[b] = e;
+    }
+    PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_fast[k]), (table.size() ? table.size() : 1) * sizeof(FastEntry)));
+    PHQ_CUDA(cudaMemcpy(h->device_fast[k], table.data(), table.size() * sizeof(FastEntry), cudaMemcpyHostToDevice));
 }
 
 /*  Combinatorial codecs (C1: 12 distinct i7 words x 8 distinct i5 words = 96 barcodes): group the barcodes
@@ -505,6 +532,10 @@ void refresh_params(phq_handle* h, size_t k) {
     p.grid_split = h->grid_shape[k * 6 + 3];
     p.grid_dense = h->grid_shape[k * 6 + 4];
     p.grid_uniform = h->grid_shape[k * 6 + 5];
+    /* the prefilter scan exists for the generic scan and for the separable form of the combinatorial one */
+    const bool prefilter(h->device_fast[k] != NULL && p.whitelist == NULL && (p.grid == NULL || p.grid_uniform != 0));
+    p.fast_barcodes = prefilter ? h->device_fast[k] : NULL;
+    p.phred32 = h->device_phred32;
 }
 
 void destroy(phq_handle* h) {
@@ -513,6 +544,8 @@ void destroy(phq_handle* h) {
     cudaSetDevice(h->device);
     for(auto* p : h->device_barcodes) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_grid) { if(p != NULL) { cudaFree(p); } }
+    for(auto* p : h->device_fast) { if(p != NULL) { cudaFree(p); } }
+    if(h->device_phred32 != NULL) { cudaFree(h->device_phred32); }
     for(auto* p : h->device_whitelist) { if(p != NULL) { cudaFree(p); } }
     for(auto* p : h->device_barcode_code) { if(p != NULL) { cudaFree(p); } }
     if(h->device_read_group_text != NULL) { cudaFree(h->device_read_group_text); }
@@ -552,13 +585,15 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
     bool needs_queue(false);
     for(size_t k(0); k < n_decoders; ++k) { needs_queue = needs_queue || h->chain[k].algorithm == PHQ_PAMLD || h->params[k].mdd_tables != NULL; }
     const long long queue_reads(n_reads < PAMLD_LAUNCH_READS ? n_reads : PAMLD_LAUNCH_READS);
-    if(needs_queue) { tie_list.reserve(16 + static_cast< size_t >(queue_reads) * sizeof(TieRecord)); }
+    /* [16 bytes: counters][tie records][hard list of the prefilter scans: one int per read] */
+    if(needs_queue) { tie_list.reserve(16 + static_cast< size_t >(queue_reads) * (sizeof(TieRecord) + sizeof(int))); }
     for(size_t k(0); k < n_decoders; ++k) {
         DecoderParams p(h->params[k]);
         p.totals = (k + 1 == n_decoders) ? h->totals() : NULL;
         if(tie_list.pointer != NULL) {
             p.tie_count = reinterpret_cast< unsigned* >(tie_list.pointer);
             p.tie_record = reinterpret_cast< TieRecord* >(tie_list.pointer + 16);
+            p.hard_list = reinterpret_cast< int* >(tie_list.pointer + 16 + static_cast< size_t >(queue_reads) * sizeof(TieRecord));
         }
         TileArguments a;
         memset(&a, 0, sizeof(a));
@@ -593,7 +628,7 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
                 part.compact = a.compact != NULL ? a.compact + begin : NULL;
                 if(h->chain[k].algorithm == PHQ_PAMLD) {
                     status = launch_pamld(p, part, h->geometry, stream);
-                    h->kernel_launches += PAMLD_KERNEL_LAUNCHES;
+                    h->kernel_launches += pamld_launches(p);
                 } else {
                     status = launch_mdd(p, part, h->geometry, stream);
                     h->kernel_launches += p.mdd_tables != NULL ? 2 * MDD_KERNEL_LAUNCHES : MDD_KERNEL_LAUNCHES;
@@ -754,6 +789,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         h->params.resize(n);
         h->device_barcodes.assign(n, NULL);
         h->device_grid.assign(n, NULL);
+        h->device_fast.assign(n, NULL);
         h->device_whitelist.assign(n, NULL);
         h->whitelist_chunks.assign(n, 0);
         h->prior_maximum.assign(n, 0.0);
@@ -781,6 +817,12 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
         assemble_phred(phred, uniform_quality, base);
         PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_phred), phred.size() * sizeof(double)));
         PHQ_CUDA(cudaMemcpy(h->device_phred, phred.data(), phred.size() * sizeof(double), cudaMemcpyHostToDevice));
+        {
+            float ratio32[128];
+            for(int q(0); q < 128; ++q) { ratio32[q] = static_cast< float >(phred[PHRED_MISMATCH_RATIO + q]); }
+            PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_phred32), sizeof(ratio32)));
+            PHQ_CUDA(cudaMemcpy(h->device_phred32, ratio32, sizeof(ratio32), cudaMemcpyHostToDevice));
+        }
 
         for(size_t k(0); k < n; ++k) {
             if(chain[k].tiled()) {
@@ -789,6 +831,7 @@ int phq_create(const char* compiled_job_json, int device, phq_handle** handle) {
                 PHQ_CUDA(cudaMalloc(reinterpret_cast< void** >(&h->device_barcodes[k]), padded * sizeof(BarcodeEntry)));
                 PHQ_CUDA(cudaMemset(h->device_barcodes[k], 0, padded * sizeof(BarcodeEntry)));
                 upload_barcodes(h, k);
+                upload_fast(h, k);
                 upload_grid(h, k);
                 upload_whitelist(h, k);
                 upload_mdd_tables(h, k);
@@ -1520,6 +1563,13 @@ int phq_reset_accumulators(phq_handle* handle) {
     });
 }
 
+int phq_reset_accumulators_async(phq_handle* handle, void* stream) {
+    return guarded(handle, [&]() {
+        PHQ_CUDA(cudaMemsetAsync(handle->device_accumulators, 0, static_cast< size_t >(handle->n_u64 + handle->n_f64) * 8, static_cast< cudaStream_t >(stream)));
+        handle->collected = false;
+    });
+}
+
 int phq_estimate_priors(phq_handle* handle, int decoder, double* estimated_noise, double* estimated_concentration) {
     return guarded(handle, [&]() {
         if(decoder < 0 || decoder >= static_cast< int >(handle->chain.size())) { throw InternalError("decoder index out of range"); }
@@ -1571,6 +1621,7 @@ int phq_set_priors(phq_handle* handle, int decoder, double noise, const double* 
         }
         PHQ_CUDA(cudaDeviceSynchronize());
         upload_barcodes(handle, static_cast< size_t >(decoder));
+        upload_fast(handle, static_cast< size_t >(decoder));
         upload_grid(handle, static_cast< size_t >(decoder));
         upload_whitelist(handle, static_cast< size_t >(decoder));
         refresh_params(handle, static_cast< size_t >(decoder));

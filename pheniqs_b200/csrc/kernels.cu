@@ -45,11 +45,11 @@ struct SharedPlan {
     int stage_capacity;         /* entries per stage buffer */
     int stage_buffers;          /* 1 when the whole table fits one chunk, else 2 */
     int accumulator_rows;       /* N + 1 when accumulators are staged in shared memory, else 0 */
-    unsigned off_stage, off_phred, off_acc_f64, off_acc_u32, off_misc, off_mbarrier, off_tables;
+    unsigned off_stage, off_phred, off_ratio32, off_acc_f64, off_acc_u32, off_misc, off_mbarrier, off_tables;
     unsigned fixed_bytes;       /* everything except the per-warp tables */
 };
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
-__host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool phred_tables, int blob_entries = 0) {
+__host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool phred_tables, int blob_entries = 0, bool ratio32 = false) {
     SharedPlan p;
     p.stage_capacity = barcode_cardinality < STAGE_ENTRIES ? barcode_cardinality : STAGE_ENTRIES;
     p.stage_buffers = barcode_cardinality <= STAGE_ENTRIES ? 1 : 2;
@@ -61,6 +61,7 @@ __host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool ph
     unsigned at = 0;
     p.off_stage = at;       at += align_up(unsigned(p.stage_capacity) * unsigned(p.stage_buffers) * 16u, 128u);
     p.off_phred = at;       at += phred_tables ? 256u * 8u : 0u;
+    p.off_ratio32 = at;     at += ratio32 ? 128u * 4u : 0u;      /* f32 mismatch ratios of the prefilter scans */
     p.off_acc_f64 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_F64_COLUMNS * 8u, 16u);
     p.off_acc_u32 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_U64_COLUMNS * 4u, 16u);
     p.off_misc = at;        at += 16u;          /* totals count, pf_count; diagnostics exact, band */
@@ -189,9 +190,9 @@ struct BlockState {
     Accumulator accumulator;
 };
 
-__device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const DecoderParams& P, bool phred_tables, int blob_entries = 0) {
+__device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const DecoderParams& P, bool phred_tables, int blob_entries = 0, bool ratio32 = false) {
     BlockState s;
-    s.plan = make_plan(P.barcode_cardinality, phred_tables, blob_entries);
+    s.plan = make_plan(P.barcode_cardinality, phred_tables, blob_entries, ratio32);
     s.stage = reinterpret_cast< BarcodeEntry* >(smem + s.plan.off_stage);
     s.phred = reinterpret_cast< double* >(smem + s.plan.off_phred);
     s.misc = reinterpret_cast< uint32_t* >(smem + s.plan.off_misc);
@@ -204,6 +205,10 @@ __device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const 
     const int tid = threadIdx.x;
     if(phred_tables) {
         for(int i = tid; i < 256; i += blockDim.x) { s.phred[i] = P.phred[i]; }
+    }
+    if(ratio32) {
+        float* const ratio = reinterpret_cast< float* >(smem + s.plan.off_ratio32);
+        for(int i = tid; i < 128; i += blockDim.x) { ratio[i] = P.phred32[i]; }
     }
     for(int i = tid; i < s.plan.accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) { s.accumulator.shared_u32[i] = 0; }
     for(int i = tid; i < s.plan.accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) { s.accumulator.shared_f64[i] = 0.0; }
@@ -247,8 +252,10 @@ __device__ __forceinline__ void block_epilogue(const BlockState& s, const Decode
 struct BarcodeStream {
     const BlockState& s;
     const DecoderParams& P;
+    const BarcodeEntry* source;         /* 16-byte entries: the barcode table, or its f32 form (FastEntry) */
     int chunk_cardinality;
-    __device__ __forceinline__ BarcodeStream(const BlockState& s, const DecoderParams& P) : s(s), P(P) {
+    __device__ __forceinline__ BarcodeStream(const BlockState& s, const DecoderParams& P, const void* table = nullptr) : s(s), P(P) {
+        source = table != nullptr ? static_cast< const BarcodeEntry* >(table) : P.barcodes;
         chunk_cardinality = (P.barcode_cardinality + s.plan.stage_capacity - 1) / s.plan.stage_capacity;
     }
     __device__ __forceinline__ int count(int chunk) const {
@@ -262,7 +269,7 @@ struct BarcodeStream {
         const uint32_t bytes = static_cast< uint32_t >(count(chunk)) * 16u;
         mbarrier_expect_tx(&s.mbarrier[buffer], bytes);
         tma_bulk_load(s.stage + static_cast< size_t >(buffer) * s.plan.stage_capacity,
-                      P.barcodes + static_cast< size_t >(chunk) * s.plan.stage_capacity, bytes, &s.mbarrier[buffer]);
+                      source + static_cast< size_t >(chunk) * s.plan.stage_capacity, bytes, &s.mbarrier[buffer]);
     }
     __device__ __forceinline__ const BarcodeEntry* wait(unsigned iteration) const {
         const int buffer = (s.plan.stage_buffers == 1) ? 0 : (iteration & 1u);
@@ -396,6 +403,16 @@ __device__ __forceinline__ ObservedRead< G > fetch_read(const TileArguments& A, 
     }
     return o;
 }
+/*  The scans work on reads 0 .. n_reads of the launch or, when the launch carries an index list (the reads an earlier
+    kernel left to this one), on reads index_list[0 .. *index_count). Item -> read, or n_reads (which fetch_read
+    answers with an empty observation) past the end. */
+__device__ __forceinline__ long long item_cardinality_of(const TileArguments& A) {
+    return A.index_list != nullptr ? static_cast< long long >(*A.index_count) : A.n_reads;
+}
+__device__ __forceinline__ long long read_of_item(const TileArguments& A, long long item, long long item_cardinality) {
+    if(item >= item_cardinality) { return A.n_reads; }
+    return A.index_list != nullptr ? static_cast< long long >(A.index_list[item]) : item;
+}
 /* the four Phred bytes of quality word g from the raw words (see quality_word) */
 template < int G >
 __device__ __forceinline__ uint32_t decode_quality(const TileArguments& A, const uint32_t (&raw)[G], int g) {
@@ -425,17 +442,12 @@ struct Verdict {
     double confidence;
     uint32_t qcfail;
 };
-__device__ __forceinline__ Verdict pamld_decide(const DecoderParams& P, const Accumulator& accumulator, uint32_t* band_counter,
-                                                int best_index, uint32_t m, double t, double prior, double others,
-                                                double base_probability, bool uniform, uint32_t high_quality_mask, uint32_t qcfail) {
-    /* when every position scores UNIFORM_BASE_QUALITY all barcodes share sigma = L x U and the
-       reference's P(r|b) is the host libm constant */
-    if(uniform) { base_probability = P.uniform_observation_probability; }
-    const double conditional_probability = base_probability * t;
-    const double p = t * prior;
-    const double sigma_p = p + (others + P.adjusted_noise_probability / base_probability);
+/* the branches of pamld.cpp:96-122 and the accumulator updates, once P(r|b) and the confidence of the winner are known */
+__device__ __forceinline__ Verdict pamld_apply(const DecoderParams& P, const Accumulator& accumulator, uint32_t* band_counter,
+                                               int best_index, uint32_t m, double conditional_probability, double confidence,
+                                               bool uniform, uint32_t high_quality_mask, uint32_t qcfail) {
     Verdict v;
-    v.confidence = p / sigma_p;
+    v.confidence = confidence;
     v.distance = __popc(m);
     v.decoded = best_index + 1;
     v.qcfail = qcfail;
@@ -466,6 +478,17 @@ __device__ __forceinline__ Verdict pamld_decide(const DecoderParams& P, const Ac
     }
     accumulator.add_pair(v.decoded, ACC_COUNT, ACC_PF_COUNT, 1u, !v.qcfail);
     return v;
+}
+__device__ __forceinline__ Verdict pamld_decide(const DecoderParams& P, const Accumulator& accumulator, uint32_t* band_counter,
+                                                int best_index, uint32_t m, double t, double prior, double others,
+                                                double base_probability, bool uniform, uint32_t high_quality_mask, uint32_t qcfail) {
+    /* when every position scores UNIFORM_BASE_QUALITY all barcodes share sigma = L x U and the
+       reference's P(r|b) is the host libm constant */
+    if(uniform) { base_probability = P.uniform_observation_probability; }
+    const double conditional_probability = base_probability * t;
+    const double p = t * prior;
+    const double sigma_p = p + (others + P.adjusted_noise_probability / base_probability);
+    return pamld_apply(P, accumulator, band_counter, best_index, m, conditional_probability, p / sigma_p, uniform, high_quality_mask, qcfail);
 }
 
 /* per-position factors of an observation: what one base contributes to P0 and to a mismatch product */
@@ -507,7 +530,8 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
     const int L = P.nucleotide_cardinality;
 
-    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    const long long items = item_cardinality_of(A);
+    const long long tile_cardinality = (items + blockDim.x - 1) / blockDim.x;
     const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * stream.chunk_cardinality;
     unsigned iteration = 0;
@@ -516,14 +540,16 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     const BarcodeEntry* resident_stage = nullptr;
     if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
 
-    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
+    long long upcoming_read = read_of_item(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid, items);
+    ObservedRead< G > upcoming = fetch_read< G >(A, upcoming_read);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
-        const long long r = tile * blockDim.x + tid;
+        const long long r = upcoming_read;
         const bool valid = r < A.n_reads;
 
         /* ---- this lane's read (requested one tile ago); request the next one */
         const ObservedRead< G > observed = upcoming;
-        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        upcoming_read = read_of_item(A, (tile + gridDim.x) * blockDim.x + tid, items);
+        upcoming = fetch_read< G >(A, upcoming_read);
         const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
         uint32_t qcfail = observed.qcfail;
         uint32_t quality[G];
@@ -758,15 +784,18 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
     const uint32_t suffix_base = shared_address(suffix);
     const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
 
-    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
-    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
+    const long long items = item_cardinality_of(A);
+    const long long tile_cardinality = (items + blockDim.x - 1) / blockDim.x;
+    long long upcoming_read = read_of_item(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid, items);
+    ObservedRead< G > upcoming = fetch_read< G >(A, upcoming_read);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
-        const long long r = tile * blockDim.x + tid;
+        const long long r = upcoming_read;
         const bool valid = r < A.n_reads;
 
         /* this lane's read (requested one tile ago); request the next one */
         const ObservedRead< G > observed = upcoming;
-        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        upcoming_read = read_of_item(A, (tile + gridDim.x) * blockDim.x + tid, items);
+        upcoming = fetch_read< G >(A, upcoming_read);
         const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
         uint32_t qcfail = observed.qcfail;
         uint32_t quality[G];
@@ -946,6 +975,422 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
             A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
             store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
         }
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, decided);
+            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
+            }
+        }
+        __syncwarp();
+    }
+    block_epilogue(S, P);
+}
+
+/* ------------------------------------------------------------------ PAMLD prefilter scans (f32)
+   The exact scans above spend their time on (read, barcode) pairs that cannot matter: for most reads one barcode
+   carries all but a vanishing part of sigma_p. The prefilter scans walk the same pairs in f32 — subset tables of
+   four positions in f32 ([entry][lane] rows of 128 bytes: ONE shared-memory wavefront per lookup instead of two, half
+   the footprint, so more resident warps), FMUL / FMNMX instead of DMUL and two-register selects — and keep, per read,
+   the largest product, its barcode and the sum of all the others (blocks of four summed in f32, blocks added in f64).
+
+   A read is EASY when the others sum to at most 2^-20 of the largest product: the maximum is then unique by six orders
+   of magnitude (f32 rounding, 2^-22 relative over a product chain, cannot reorder it; ties and near ties are never
+   easy), and everything the decision needs from the winner is recomputed exactly in f64 — its mismatch product from
+   the f64 ratios, P0 in position order, the prior from the barcode table — so P(r|b) > rbp and the f64 noise term are
+   what the exact scan forms. The only f32 quantity left in sigma_p is the sum of the others: a term with c mismatched
+   positions carries at most 2c + 1 roundings of 2^-24 and the block sums two more, so the error probability
+   1 - confidence of an easy read is within 6e-7 relative of the exact scan's in the worst case (typical: 1e-7) and the
+   confidence itself within 6e-7 x 2^-20 < 1e-12. Reads whose confidence lands within 2^-38 of the confidence
+   threshold are not easy either. Everything else — about one read in fifteen on the synthetic workloads: noise reads,
+   reads with a confidently called mismatch, all-N reads, products too small for f32 — is HARD: its index is appended
+   to a list and the exact scan (pamld_kernel / pamld_grid_kernel in index-list mode) followed by the tie pass decides
+   it exactly as before. */
+constexpr double FAST_EASY_RATIO = 9.5367431640625e-07;             /* 2^-20 */
+constexpr float FAST_MINIMUM_BEST = 8.6736173798840355e-19f;        /* 2^-60: below it f32 products of the others may underflow */
+constexpr double FAST_THRESHOLD_GUARD = 3.637978807091713e-12;      /* 2^-38 */
+constexpr int FAST_GROUP_FLOATS = 16 * WARP_SIZE;                   /* one table group: 16 subsets x 32 lanes, 2 KB */
+__host__ __device__ constexpr int fast_warps(int G) { return G <= 2 ? 24 : (G <= 4 ? 20 : 16); }
+
+/* subset product of table group TABLE_GROUP for the nibble at bits 4 * LOCAL of m: entry e of the lane at
+   base + TABLE_GROUP * 2048 + e * 128; the warp's block is 2 KB aligned in the shared window, so (nibble << 7) | base */
+template < int TABLE_GROUP, int LOCAL >
+__device__ __forceinline__ float fast_lookup(uint32_t base, uint32_t m) {
+    const uint32_t moved = (LOCAL < 2) ? (m << (LOCAL < 2 ? 7 - 4 * LOCAL : 0)) : (m >> (LOCAL < 2 ? 0 : 4 * LOCAL - 7));
+    uint32_t address;
+    asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(address) : "r"(moved), "r"(base));
+    float value;
+    asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(value) : "r"(address), "n"(TABLE_GROUP * FAST_GROUP_FLOATS * 4));
+    return value;
+}
+/* product over GROUPS consecutive table groups starting at FIRST; m holds the part's mismatch bits from bit 0 */
+template < int FIRST, int GROUPS, int k >
+struct FastProduct {
+    static __device__ __forceinline__ float of(uint32_t base, uint32_t m, float t) {
+        return FastProduct< FIRST, GROUPS, k + 1 >::of(base, m, t * fast_lookup< FIRST + k, k >(base, m));
+    }
+};
+template < int FIRST, int GROUPS >
+struct FastProduct< FIRST, GROUPS, GROUPS > {
+    static __device__ __forceinline__ float of(uint32_t, uint32_t, float t) { return t; }
+};
+template < int FIRST, int GROUPS >
+__device__ __forceinline__ float fast_product(uint32_t base, uint32_t m) {
+    return FastProduct< FIRST, GROUPS, 1 >::of(base, m, fast_lookup< FIRST, 0 >(base, m));
+}
+/* the 2^COUNT subset products of COUNT (1..4) positions into the lane's column of one table group */
+template < int COUNT >
+__device__ __forceinline__ void fast_store_group(float* t, const float* w) {
+    const float w0 = w[0];
+    const float w1 = COUNT > 1 ? w[COUNT > 1 ? 1 : 0] : 1.0f;
+    const float w2 = COUNT > 2 ? w[COUNT > 2 ? 2 : 0] : 1.0f;
+    const float w3 = COUNT > 3 ? w[COUNT > 3 ? 3 : 0] : 1.0f;
+    const float w01 = w0 * w1;
+    t[0 * WARP_SIZE] = 1.0f;
+    t[1 * WARP_SIZE] = w0;
+    if(COUNT > 1) {
+        t[2 * WARP_SIZE] = w1;
+        t[3 * WARP_SIZE] = w01;
+    }
+    if(COUNT > 2) {
+        const float w02 = w0 * w2, w12 = w1 * w2, w012 = w01 * w2;
+        t[4 * WARP_SIZE] = w2;
+        t[5 * WARP_SIZE] = w02;
+        t[6 * WARP_SIZE] = w12;
+        t[7 * WARP_SIZE] = w012;
+        if(COUNT > 3) {
+            t[8 * WARP_SIZE] = w3;
+            t[9 * WARP_SIZE] = w0 * w3;
+            t[10 * WARP_SIZE] = w1 * w3;
+            t[11 * WARP_SIZE] = w01 * w3;
+            t[12 * WARP_SIZE] = w2 * w3;
+            t[13 * WARP_SIZE] = w02 * w3;
+            t[14 * WARP_SIZE] = w12 * w3;
+            t[15 * WARP_SIZE] = w012 * w3;
+        }
+    }
+}
+/* per-position f32 mismatch ratios of a read and its P0 (f64, position order: the same bits the exact scans form) */
+template < int G, int POSITIONS >
+__device__ __forceinline__ double fast_factors(const double* __restrict__ match64, const float* __restrict__ ratio32, double uniform_factor,
+                                               const uint32_t (&quality)[G], uint32_t nmask, float (&w)[POSITIONS]) {
+    double base_probability = 1.0;
+    #pragma unroll
+    for(int j = 0; j < POSITIONS; ++j) {
+        uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        q = q > 127u ? 127u : q;
+        const bool ambiguous = (nmask >> j) & 1u;
+        float ratio = ratio32[q];
+        double factor = match64[q];
+        if(ambiguous) {
+            ratio = 1.0f;
+            if(q != 0u) { factor = uniform_factor; }
+        }
+        w[j] = ratio;
+        base_probability *= factor;
+    }
+    return base_probability;
+}
+/* the winner's mismatch product in f64 over the mismatched, unambiguous positions */
+template < int G, int POSITIONS >
+__device__ __forceinline__ double exact_product(const double* __restrict__ ratio64, const uint32_t (&quality)[G], uint32_t counted) {
+    double t = 1.0;
+    #pragma unroll
+    for(int j = 0; j < POSITIONS; ++j) {
+        if((counted >> j) & 1u) {
+            uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            q = q > 127u ? 127u : q;
+            t *= ratio64[q];
+        }
+    }
+    return t;
+}
+template < int G, int POSITIONS >
+__device__ __forceinline__ uint32_t quality_mask(const uint32_t (&quality)[G], int threshold) {
+    uint32_t mask = 0;
+    #pragma unroll
+    for(int j = 0; j < POSITIONS; ++j) {
+        if(static_cast< int >((quality[j >> 2] >> (8 * (j & 3))) & 0xffu) >= threshold) { mask |= 1u << j; }
+    }
+    return mask;
+}
+
+/* running selection of a prefilter scan: the maximum, its index, and the f64 sum of everything else */
+struct FastSelection {
+    float best;
+    int index;
+    double rest;
+};
+__device__ __forceinline__ void fast_duel(float a, int ia, float b, int ib, float& high, int& ihigh, float& low) {
+    const bool later = b > a;
+    high = fmaxf(a, b);
+    low = fminf(a, b);
+    ihigh = later ? ib : ia;
+}
+__device__ __forceinline__ void fast_select_one(FastSelection& s, float p, int i) {
+    float high, low; int ihigh;
+    fast_duel(s.best, s.index, p, i, high, ihigh, low);
+    s.best = high; s.index = ihigh;
+    s.rest += static_cast< double >(low);
+}
+__device__ __forceinline__ void fast_select_four(FastSelection& s, float p0, float p1, float p2, float p3, int i) {
+    float a, b, c, la, lb, lc, high, low; int ia, ib, ic, ihigh;
+    fast_duel(p0, i, p1, i + 1, a, ia, la);
+    fast_duel(p2, i + 2, p3, i + 3, b, ib, lb);
+    fast_duel(a, ia, b, ib, c, ic, lc);
+    fast_duel(s.best, s.index, c, ic, high, ihigh, low);
+    s.best = high; s.index = ihigh;
+    s.rest += static_cast< double >(((la + lb) + lc) + low);
+}
+
+/* append the lanes with `flag` set to a device list (one atomic per warp) */
+__device__ __forceinline__ void append_reads(bool flag, long long r, int* list, unsigned* count, int lane) {
+    const unsigned lanes = __ballot_sync(FULL_MASK, flag);
+    if(lanes) {
+        unsigned slot = 0;
+        if(lane == 0) { slot = atomicAdd(count, static_cast< unsigned >(__popc(lanes))); }
+        slot = __shfl_sync(FULL_MASK, slot, 0);
+        if(flag) { list[slot + __popc(lanes & ((1u << lane) - 1u))] = static_cast< int >(r); }
+    }
+}
+
+/*  What both prefilter scans do once the winner of an easy read is known: the exact f64 evaluation of the winner, the
+    guard around the confidence threshold, then the decision and the stores. Returns false when the read turns out
+    hard after all. */
+template < int G, int POSITIONS >
+__device__ __forceinline__ bool fast_decide(const DecoderParams& P, const TileArguments& A, const BlockState& S, long long r, int winner,
+                                            uint32_t o_lo, uint32_t o_hi, uint32_t nmask, const uint32_t (&quality)[G], double others,
+                                            double base_probability, uint32_t& qcfail) {
+    const BarcodeEntry e = P.barcodes[winner];
+    const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, e.lo, e.hi);
+    const double t = exact_product< G, POSITIONS >(S.phred + PHRED_MISMATCH_RATIO, quality, m & ~nmask);
+    const double p = t * e.prior;
+    const double sigma_p = p + (others + P.adjusted_noise_probability / base_probability);
+    const double confidence = p / sigma_p;
+    if(fabs(confidence - P.confidence_threshold) <= FAST_THRESHOLD_GUARD) { return false; }
+    uint32_t high_quality_mask = 0;
+    if(P.high_quality_distance_threshold > 0) {
+        high_quality_mask = quality_mask< G, POSITIONS >(quality, P.high_quality_threshold);
+        high_quality_mask &= (P.nucleotide_cardinality >= 32) ? 0xffffffffu : ((1u << P.nucleotide_cardinality) - 1u);
+    }
+    const Verdict v = pamld_apply(P, S.accumulator, &S.misc[3], winner, m, base_probability * t, confidence, false, high_quality_mask, qcfail);
+    qcfail = v.qcfail;
+    A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
+    store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
+    return true;
+}
+
+template < int G >
+__global__ void __launch_bounds__(fast_warps(G) * WARP_SIZE, 1)
+pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
+    extern __shared__ __align__(256) unsigned char smem[];
+    const BlockState S = block_prologue(smem, P, true, 0, true);
+    const BarcodeStream stream(S, P, P.fast_barcodes);
+    const float* const ratio32 = reinterpret_cast< const float* >(smem + S.plan.off_ratio32);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const uint32_t window = shared_address(smem);
+    const uint32_t aligned_tables = ((window + S.plan.off_tables + 2047u) & ~2047u) - window;
+    float* const table = reinterpret_cast< float* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * FAST_GROUP_FLOATS) + lane;
+    const uint32_t table_base = shared_address(table);
+    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
+    const int L = P.nucleotide_cardinality;
+    const uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+    unsigned* const hard_count = P.tie_count + 2;
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned long long total_iterations = static_cast< unsigned long long >(my_tiles) * stream.chunk_cardinality;
+    unsigned iteration = 0;
+    if(tid == 0 && total_iterations > 0) { stream.issue(0); }
+    const bool resident = stream.chunk_cardinality == 1;
+    const BarcodeEntry* resident_stage = nullptr;
+    if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
+
+    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+        const ObservedRead< G > observed = upcoming;
+        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
+        uint32_t qcfail = observed.qcfail;
+        uint32_t quality[G];
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
+
+        /* ---- f32 ratios, P0, subset tables */
+        float w[4 * G];
+        const double base_probability = fast_factors< G, 4 * G >(S.phred + PHRED_MATCH_FACTOR, ratio32, uniform_factor, quality, nmask, w);
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { fast_store_group< 4 >(table + g * FAST_GROUP_FLOATS, w + 4 * g); }
+        __syncwarp();
+
+        /* ---- every barcode, in f32 */
+        FastSelection selection;
+        selection.best = 0.0f; selection.index = 0; selection.rest = 0.0;
+        for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
+            const BarcodeEntry* stage;
+            if(resident) {
+                stage = resident_stage;
+            } else {
+                if(tid == 0 && iteration + 1 < total_iterations) { stream.issue(iteration + 1); }
+                stage = stream.wait(iteration);
+            }
+            const int count = stream.count(chunk);
+            const int first = chunk * S.plan.stage_capacity;
+            int i = 0;
+            #pragma unroll 2
+            for(; i + 4 <= count; i += 4) {
+                float p[4];
+                #pragma unroll
+                for(int u = 0; u < 4; ++u) {
+                    const uint4 raw = *reinterpret_cast< const uint4* >(stage + i + u);
+                    const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
+                    p[u] = fast_product< 0, G >(table_base, m) * __uint_as_float(raw.z);
+                }
+                fast_select_four(selection, p[0], p[1], p[2], p[3], first + i);
+            }
+            for(; i < count; ++i) {
+                const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
+                const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
+                fast_select_one(selection, fast_product< 0, G >(table_base, m) * __uint_as_float(raw.z), first + i);
+            }
+            if(!resident) {
+                __syncthreads();
+                ++iteration;
+            }
+        }
+
+        /* ---- easy reads are decided here, the others are left to the exact scan */
+        bool decided = valid && selection.rest <= FAST_EASY_RATIO * static_cast< double >(selection.best)
+                    && selection.best >= FAST_MINIMUM_BEST && (nmask & all_positions) != all_positions;
+        if(decided) {
+            decided = fast_decide< G, 4 * G >(P, A, S, r, selection.index, o_lo, o_hi, nmask, quality, selection.rest, base_probability, qcfail);
+        }
+        append_reads(valid && !decided, r, P.hard_list, hard_count, lane);
+        if(P.totals != nullptr) {
+            const unsigned live = __ballot_sync(FULL_MASK, decided);
+            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
+            if(lane == 0) {
+                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
+                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
+            }
+        }
+        __syncwarp();
+    }
+    block_epilogue(S, P);
+}
+
+/*  The separable form of the combinatorial scan (full KA x KB grid under one prior; pamld_grid_kernel, UNIFORM) as a
+    prefilter: KA + KB word products in f32, then sum of the others = SA* restB + restA (SB* + restB). */
+struct FastPart {
+    float best;
+    int index;
+    double rest;
+};
+__device__ __forceinline__ void fast_select_part(FastPart& s, float value, int i) {
+    const bool later = value > s.best;
+    const float low = fminf(s.best, value);
+    s.best = fmaxf(s.best, value);
+    s.index = later ? i : s.index;
+    s.rest += static_cast< double >(low);
+}
+constexpr int FAST_GRID_WARPS = 24;
+
+template < int LA, int LB >
+__global__ void __launch_bounds__(FAST_GRID_WARPS * WARP_SIZE, 1)
+pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
+    constexpr int L = LA + LB;
+    constexpr int G = (L + 3) / 4;
+    constexpr int GA = (LA + 3) / 4;            /* table groups of up to four positions per part */
+    constexpr int GB = (LB + 3) / 4;
+    constexpr uint32_t MASK_A = (1u << LA) - 1u;
+    constexpr uint32_t MASK_B = (1u << LB) - 1u;
+    extern __shared__ __align__(256) unsigned char smem[];
+    const BlockState S = block_prologue(smem, P, true, P.grid_a + P.grid_b + P.grid_entries, true);
+    const float* const ratio32 = reinterpret_cast< const float* >(smem + S.plan.off_ratio32);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int KA = P.grid_a;
+    const int KB = P.grid_b;
+    const GridHeader* const header = reinterpret_cast< const GridHeader* >(smem + S.plan.off_stage);
+    const GridWord* const word = reinterpret_cast< const GridWord* >(header + KA);
+    const GridEntry* const entry = reinterpret_cast< const GridEntry* >(word + KB);
+    if(tid == 0) {
+        const uint32_t bytes = static_cast< uint32_t >(KA + KB + P.grid_entries) * 16u;
+        mbarrier_expect_tx(&S.mbarrier[0], bytes);
+        tma_bulk_load(smem + S.plan.off_stage, P.grid, bytes, &S.mbarrier[0]);
+    }
+    mbarrier_wait(&S.mbarrier[0], 0);
+    const uint32_t window = shared_address(smem);
+    const uint32_t aligned_tables = ((window + S.plan.off_tables + 2047u) & ~2047u) - window;
+    float* const table = reinterpret_cast< float* >(smem + aligned_tables) + static_cast< size_t >(warp) * ((GA + GB) * FAST_GROUP_FLOATS) + lane;
+    const uint32_t table_base = shared_address(table);
+    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
+    constexpr uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+    unsigned* const hard_count = P.tie_count + 2;
+    const float prior32 = static_cast< float >(entry[0].prior);
+
+    const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
+    for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
+        const long long r = tile * blockDim.x + tid;
+        const bool valid = r < A.n_reads;
+        const ObservedRead< G > observed = upcoming;
+        upcoming = fetch_read< G >(A, (tile + gridDim.x) * blockDim.x + tid);
+        const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
+        uint32_t qcfail = observed.qcfail;
+        uint32_t quality[G];
+        #pragma unroll
+        for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
+
+        float w[L];
+        const double base_probability = fast_factors< G, L >(S.phred + PHRED_MATCH_FACTOR, ratio32, uniform_factor, quality, nmask, w);
+        #pragma unroll
+        for(int g = 0; g < GA; ++g) {
+            constexpr int full = LA / 4;
+            if(g < full) { fast_store_group< 4 >(table + g * FAST_GROUP_FLOATS, w + 4 * g); }
+            else { fast_store_group< (LA % 4 == 0 ? 4 : LA % 4) >(table + g * FAST_GROUP_FLOATS, w + 4 * g); }
+        }
+        #pragma unroll
+        for(int g = 0; g < GB; ++g) {
+            constexpr int full = LB / 4;
+            if(g < full) { fast_store_group< 4 >(table + (GA + g) * FAST_GROUP_FLOATS, w + LA + 4 * g); }
+            else { fast_store_group< (LB % 4 == 0 ? 4 : LB % 4) >(table + (GA + g) * FAST_GROUP_FLOATS, w + LA + 4 * g); }
+        }
+        __syncwarp();
+
+        const uint32_t a_lo = o_lo & MASK_A, a_hi = o_hi & MASK_A, a_n = nmask & MASK_A;
+        const uint32_t b_lo = (o_lo >> LA) & MASK_B, b_hi = (o_hi >> LA) & MASK_B, b_n = (nmask >> LA) & MASK_B;
+        FastPart part_b;
+        part_b.best = 0.0f; part_b.index = 0; part_b.rest = 0.0;
+        #pragma unroll 4
+        for(int k = 0; k < KB; ++k) {
+            const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+            const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+            fast_select_part(part_b, fast_product< GA, GB >(table_base, m), k);
+        }
+        FastPart part_a;
+        part_a.best = 0.0f; part_a.index = 0; part_a.rest = 0.0;
+        #pragma unroll 4
+        for(int a = 0; a < KA; ++a) {
+            const uint2 h = *reinterpret_cast< const uint2* >(header + a);
+            const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+            fast_select_part(part_a, fast_product< 0, GA >(table_base, m), a);
+        }
+        const float best = (part_a.best * part_b.best) * prior32;
+        const double others = (static_cast< double >(part_a.best) * part_b.rest + part_a.rest * (static_cast< double >(part_b.best) + part_b.rest)) * static_cast< double >(prior32);
+
+        bool decided = valid && others <= FAST_EASY_RATIO * static_cast< double >(best) && best >= FAST_MINIMUM_BEST && (nmask & all_positions) != all_positions;
+        if(decided) {
+            const int winner = static_cast< int >(entry[part_a.index * KB + part_b.index].index);
+            decided = fast_decide< G, L >(P, A, S, r, winner, o_lo, o_hi, nmask, quality, others, base_probability, qcfail);
+        }
+        append_reads(valid && !decided, r, P.hard_list, hard_count, lane);
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, decided);
             const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
@@ -2078,6 +2523,56 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
     return launch_pamld_grid_as< LA, LB, 0, false >(params, tile, geometry, stream);
 }
 
+/* the prefilter scan over every read of the launch, then the exact scan over the reads it left, then the tie pass */
+template < int G >
+cudaError_t launch_pamld_fast_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    const SharedPlan plan = make_plan(params.barcode_cardinality, true, 0, true);
+    const size_t per_warp = static_cast< size_t >(G) * FAST_GROUP_FLOATS * sizeof(float);
+    if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
+    warps = warps > fast_warps(G) ? fast_warps(G) : warps;
+    const size_t bytes = plan.fixed_bytes + per_warp * warps;
+    cudaError_t status = cudaFuncSetAttribute(pamld_fast_kernel< G >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    if(status != cudaSuccess) { return status; }
+    const int threads = warps * WARP_SIZE;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
+    status = cudaMemsetAsync(params.tie_count + 2, 0, sizeof(unsigned), stream);
+    if(status != cudaSuccess) { return status; }
+    pamld_fast_kernel< G ><<< grid, threads, bytes, stream >>>(params, tile);
+    status = cudaGetLastError();
+    if(status != cudaSuccess) { return status; }
+    TileArguments rest(tile);
+    rest.index_list = params.hard_list;
+    rest.index_count = params.tie_count + 2;
+    return launch_pamld_groups< G >(params, rest, geometry, stream);
+}
+template < int LA, int LB >
+cudaError_t launch_pamld_fast_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    constexpr int GROUPS = (LA + 3) / 4 + (LB + 3) / 4;
+    const int blob_entries = params.grid_a + params.grid_b + params.grid_entries;
+    const SharedPlan plan = make_plan(params.barcode_cardinality, true, blob_entries, true);
+    const size_t per_warp = static_cast< size_t >(GROUPS) * FAST_GROUP_FLOATS * sizeof(float);
+    if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
+    warps = warps > FAST_GRID_WARPS ? FAST_GRID_WARPS : warps;
+    const size_t bytes = plan.fixed_bytes + per_warp * warps;
+    cudaError_t status = cudaFuncSetAttribute(pamld_fast_grid_kernel< LA, LB >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    if(status != cudaSuccess) { return status; }
+    const int threads = warps * WARP_SIZE;
+    const long long tiles = (tile.n_reads + threads - 1) / threads;
+    const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
+    status = cudaMemsetAsync(params.tie_count + 2, 0, sizeof(unsigned), stream);
+    if(status != cudaSuccess) { return status; }
+    pamld_fast_grid_kernel< LA, LB ><<< grid, threads, bytes, stream >>>(params, tile);
+    status = cudaGetLastError();
+    if(status != cudaSuccess) { return status; }
+    TileArguments rest(tile);
+    rest.index_list = params.hard_list;
+    rest.index_count = params.tie_count + 2;
+    return launch_pamld_grid_as< LA, LB, 1, true >(params, rest, geometry, stream);
+}
+
 }   /* namespace */
 
 static cudaError_t launch_pamld_whitelist(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
@@ -2103,6 +2598,27 @@ static cudaError_t launch_pamld_whitelist(const DecoderParams& params, const Til
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     if(tile.n_reads <= 0) { return cudaSuccess; }
     if(params.whitelist != nullptr) { return launch_pamld_whitelist(params, tile, geometry, stream); }
+    if(params.fast_barcodes != nullptr) {
+        /* f32 prefilter scan first (see pamld_fast_kernel); the api only offers it for the shapes handled here */
+        if(params.grid != nullptr && params.grid_uniform) {
+            if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_fast_grid< 6, 6 >(params, tile, geometry, stream); }
+            if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_fast_grid< 8, 8 >(params, tile, geometry, stream); }
+            if(params.grid_split == 10 && params.nucleotide_cardinality == 20) { return launch_pamld_fast_grid< 10, 10 >(params, tile, geometry, stream); }
+            if(params.grid_split == 12 && params.nucleotide_cardinality == 24) { return launch_pamld_fast_grid< 12, 12 >(params, tile, geometry, stream); }
+            return cudaErrorInvalidValue;
+        }
+        switch(params.group_cardinality) {
+            case 1: return launch_pamld_fast_groups< 1 >(params, tile, geometry, stream);
+            case 2: return launch_pamld_fast_groups< 2 >(params, tile, geometry, stream);
+            case 3: return launch_pamld_fast_groups< 3 >(params, tile, geometry, stream);
+            case 4: return launch_pamld_fast_groups< 4 >(params, tile, geometry, stream);
+            case 5: return launch_pamld_fast_groups< 5 >(params, tile, geometry, stream);
+            case 6: return launch_pamld_fast_groups< 6 >(params, tile, geometry, stream);
+            case 7: return launch_pamld_fast_groups< 7 >(params, tile, geometry, stream);
+            case 8: return launch_pamld_fast_groups< 8 >(params, tile, geometry, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     if(params.grid != nullptr) {
         if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_grid< 6, 6, false >(params, tile, geometry, stream); }
         if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_grid< 8, 8, true >(params, tile, geometry, stream); }
@@ -2211,10 +2727,14 @@ void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, 
             snprintf(buffer, capacity, "pamld_whitelist_kernel + pamld_tie_kernel<4>");
         } else if(grid) {
             const bool dense = params.grid_dense != 0 && (params.grid_split == 8 || params.grid_split == 10);
-            snprintf(buffer, capacity, "pamld_grid_kernel<%d, %d, %d, %d, %d> + pamld_tie_kernel<%d>", params.grid_split, L - params.grid_split,
+            char prefilter[64] = "";
+            if(params.fast_barcodes != nullptr) { snprintf(prefilter, sizeof(prefilter), "pamld_fast_grid_kernel<%d, %d> + ", params.grid_split, L - params.grid_split); }
+            snprintf(buffer, capacity, "%spamld_grid_kernel<%d, %d, %d, %d, %d> + pamld_tie_kernel<%d>", prefilter, params.grid_split, L - params.grid_split,
                      GRID_GROUP_WIDTH, params.grid_uniform ? 1 : (dense ? params.grid_dense : 0), params.grid_uniform ? 1 : 0, (L + 3) / 4);
         } else {
-            snprintf(buffer, capacity, "pamld_kernel<%d> + pamld_tie_kernel<%d>", params.group_cardinality, params.group_cardinality);
+            char prefilter[64] = "";
+            if(params.fast_barcodes != nullptr) { snprintf(prefilter, sizeof(prefilter), "pamld_fast_kernel<%d> + ", params.group_cardinality); }
+            snprintf(buffer, capacity, "%spamld_kernel<%d> + pamld_tie_kernel<%d>", prefilter, params.group_cardinality, params.group_cardinality);
         }
     } else if(algorithm == 1) {
         const int scan = params.segment_cardinality <= 2 ? params.segment_cardinality : 0;

@@ -24,6 +24,14 @@ struct __align__(16) BarcodeEntry {
     double prior;           /* Barcode::concentration (barcode.h:37) */
 };
 
+/*  The same barcode for the f32 prefilter scans (pamld_fast_kernel): planes and the prior rounded to f32. */
+struct __align__(16) FastEntry {
+    uint32_t lo;
+    uint32_t hi;
+    float prior;
+    uint32_t pad;
+};
+
 /* offsets into the f64 Phred table uploaded once per handle */
 enum {
     PHRED_MATCH_FACTOR   = 0,       /* [128]  B ^ true_positive_quality[q]      (q = 0 -> 1)            */
@@ -128,7 +136,10 @@ struct DecoderParams {
     int32_t whitelist_chunks;
     double prior_maximum;                       /* largest barcode prior: the pruning bound of pamld_whitelist_kernel */
     TieRecord* tie_record;                      /* [reads of the launch] queue of reads whose winner needs the exact tie path (PAMLD) */
-    unsigned* tie_count;                        /* queue length, reset before every scan */
+    unsigned* tie_count;                        /* queue header: [0] tie queue length, [1] work counter of the whitelist scan, [2] hard list length */
+    const FastEntry* fast_barcodes;             /* [N] device; NULL = no f32 prefilter scan for this decoder (exact scan over every read) */
+    const float* phred32;                       /* [128] mismatch ratios rounded to f32 */
+    int* hard_list;                             /* [reads of the launch] reads the prefilter scan leaves to the exact scan */
 };
 
 struct TileArguments {
@@ -154,7 +165,9 @@ struct LaunchGeometry {
 
 /* each returns the CUDA error of the launch; all are asynchronous on `stream`.
    launch_pamld launches two kernels (scan, then the tie pass over the reads the scan queued). */
-enum { PAMLD_KERNEL_LAUNCHES = 2, MDD_KERNEL_LAUNCHES = 1, COUNT_KERNEL_LAUNCHES = 1 };
+enum { PAMLD_KERNEL_LAUNCHES = 2, PAMLD_FAST_KERNEL_LAUNCHES = 3, MDD_KERNEL_LAUNCHES = 1, COUNT_KERNEL_LAUNCHES = 1 };
+/* kernels launch_pamld launches for these parameters: prefilter scan + exact scan over the reads it left + tie pass, or scan + tie pass */
+inline int pamld_launches(const DecoderParams& params) { return (params.fast_barcodes != nullptr && params.whitelist == nullptr) ? PAMLD_FAST_KERNEL_LAUNCHES : PAMLD_KERNEL_LAUNCHES; }
 /* PAMLD launches cover at most this many reads, so the tie queue (80 bytes per read, worst case every read) stays bounded */
 constexpr long long PAMLD_LAUNCH_READS = 1ll << 24;
 cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);

@@ -362,8 +362,12 @@ class DecoderChain:
         check(self.lib.phq_totals(self.handle, C.byref(a), C.byref(b)), self.handle)
         return a.value, b.value
 
-    def reset(self):
-        check(self.lib.phq_reset_accumulators(self.handle), self.handle)
+    def reset(self, stream=None):
+        """Clear the accumulators (and the collected state): synchronously, or in `stream` order when one is given."""
+        if stream is None:
+            check(self.lib.phq_reset_accumulators(self.handle), self.handle)
+        else:
+            check(self.lib.phq_reset_accumulators_async(self.handle, C.c_void_p(stream.cuda_stream)), self.handle)
 
     def accumulator_tensors(self):
         """The handle's accumulator buffer as two torch views (int64 bit pattern of the u64 plane, float64 plane)."""

@@ -80,4 +80,7 @@ def compare_pamld(got, expected_index, expected_distance, expected_confidence, l
     # reference forms it as 1.0 - conf in f64 (read.h:189) and that difference is quantised at 2^-53
     e_got = 1.0 - got["confidence"][ok]
     e_ref = 1.0 - expected_confidence[ok]
-    assert np.all(np.abs(e_got - e_ref) <= 1e-6 * e_ref + 4 * 2.0 ** -53), label + " error probability"
+    excess = np.abs(e_got - e_ref) - (1e-6 * e_ref + 4 * 2.0 ** -53)
+    worst = int(np.argmax(excess)) if excess.size else 0
+    assert np.all(excess <= 0), "%s error probability: %d reads out of tolerance, worst read %d: got %.17g expected %.17g (difference %.3g = %.2f x 2^-53)" % (
+        label, int((excess > 0).sum()), int(np.nonzero(ok)[0][worst]), e_got[worst], e_ref[worst], e_got[worst] - e_ref[worst], (e_got[worst] - e_ref[worst]) * 2.0 ** 53)

@@ -66,8 +66,24 @@ def test_baseline_configs(name, device_path):
     code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 60000, seed=21, sampling="zipf" if name == "c4" else "prior")
     state = run_both(None, code, quality, offset, compiled=compiled, device_path=device_path)
     check(*state)
-    # scan + tie pass per PAMLD decoder, lookup + queued scan per MDD decoder, one count kernel per naive decoder
-    assert state[0].statistics()["kernel_launches"] == sum(2 if info.algorithm in (0, 1) else 1 for info in state[0].info)
+    # prefilter scan + exact scan + tie pass per PAMLD decoder, lookup + queued scan per MDD decoder, one count kernel per naive decoder
+    chain = state[0]
+    assert all("pamld_fast" in chain.kernel_description(k) for k, info in enumerate(chain.info) if info.algorithm == 0)
+    assert chain.statistics()["kernel_launches"] == sum(3 if info.algorithm == 0 else (2 if info.algorithm == 1 else 1) for info in chain.info)
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+def test_exact_scans_without_the_prefilter(name, monkeypatch):
+    """PHQ_DISABLE_FAST=1: every read goes through the f64 scans (the path the prefilter leaves its hard reads to)."""
+    monkeypatch.setenv("PHQ_DISABLE_FAST", "1")
+    spec = workload.load(name)
+    compiled = compile_job(spec["job"])
+    code, quality, offset, _ = workload.synthesize(compiled, spec["input segment length"], 40000, seed=22, sampling="zipf" if name == "c4" else "prior")
+    state = run_both(None, code, quality, offset, compiled=compiled)
+    check(*state)
+    chain = state[0]
+    assert not any("pamld_fast" in chain.kernel_description(k) for k in range(chain.n_decoders))
+    assert chain.statistics()["kernel_launches"] == sum(2 if info.algorithm in (0, 1) else 1 for info in chain.info)
 
 
 def test_whitelist_config_reduced():
