@@ -8,7 +8,7 @@
         ---------                                   ----
         TranscodingDecoder(const Value& ontology)   phq::BatchDecoder(compiled_json, device)
         classify(const Read&, Read&)                classify(batch)            (transcode.h:51-65)
-        collect(const TranscodingDecoder&)          accumulator_buffer() + one all-reduce (transcode.cpp:162-179)
+        collect(const TranscodingDecoder&)          collect(nccl_comm, stream): one all-reduce (transcode.cpp:162-179)
         finalize()                                  estimate_priors(k)         (classifier.h:94-124)
         Transcode::finalize report                  report()                   (transcode.cpp:1811-1863)
         Error subclasses with ErrorCode             phq::Error subclasses with the same codes (error.h:32-136)
@@ -39,6 +39,7 @@ class OutOfMemoryError : public Error { public: explicit OutOfMemoryError(const 
 class SequenceError : public Error { public: explicit SequenceError(const std::string& m) : Error(PHQ_SEQUENCE_ERROR, m) {} };
 class OverflowError : public Error { public: explicit OverflowError(const std::string& m) : Error(PHQ_OVERFLOW_ERROR, m) {} };
 
+/* status first, then the message it left behind: never both as arguments of one call (their evaluation order is unspecified) */
 inline void raise(int status, const char* message) {
     const std::string text(message != NULL ? message : "");
     switch(status) {
@@ -55,7 +56,8 @@ inline void raise(int status, const char* message) {
 /* Transcode::compile for the decoder sections of a job */
 inline std::string compile_job(const std::string& job_json) {
     char* out(NULL);
-    raise(phq_compile_job(job_json.c_str(), &out), phq_last_global_error());
+    const int status(phq_compile_job(job_json.c_str(), &out));
+    raise(status, phq_last_global_error());
     std::string compiled(out);
     phq_free(out);
     return compiled;
@@ -64,7 +66,8 @@ inline std::string compile_job(const std::string& job_json) {
 /* the job file with its imports merged underneath (Job::load_instruction_with_import, job.cpp:160-224) */
 inline std::string load_job(const std::string& path) {
     char* out(NULL);
-    raise(phq_load_job(path.c_str(), &out), phq_last_global_error());
+    const int status(phq_load_job(path.c_str(), &out));
+    raise(status, phq_last_global_error());
     std::string job(out);
     phq_free(out);
     return job;
@@ -73,7 +76,8 @@ inline std::string load_job(const std::string& path) {
 /* the prior adjusted job (tool/pheniqs-prior-api.py:39-56, classifier.h:125-160) */
 inline std::string adjust_job(const std::string& job_json, const std::string& report_json, int precision = 15) {
     char* out(NULL);
-    raise(phq_adjust_job(job_json.c_str(), report_json.c_str(), precision, &out), phq_last_global_error());
+    const int status(phq_adjust_job(job_json.c_str(), report_json.c_str(), precision, &out));
+    raise(status, phq_last_global_error());
     std::string adjusted(out);
     phq_free(out);
     return adjusted;
@@ -103,7 +107,7 @@ class TileBuffer {
         bool pinned_;
         void* get(size_t bytes) {
             void* p(NULL);
-            if(pinned_) { raise(phq_host_alloc(&p, bytes), phq_last_global_error()); }
+            if(pinned_) { const int status(phq_host_alloc(&p, bytes)); raise(status, phq_last_global_error()); }
             else { p = ::operator new(bytes ? bytes : 1); }
             return p;
         }
@@ -121,7 +125,8 @@ class TileBuffer {
 class BatchDecoder {
     public:
         BatchDecoder(const std::string& compiled_job_json, int device) : handle_(NULL) {
-            raise(phq_create(compiled_job_json.c_str(), device, &handle_), phq_last_global_error());
+            const int status(phq_create(compiled_job_json.c_str(), device, &handle_));
+            raise(status, phq_last_global_error());
             const int n(phq_decoder_count(handle_));
             info_.resize(static_cast< size_t >(n));
             for(int k(0); k < n; ++k) { check(phq_decoder_describe(handle_, k, &info_[k])); }
@@ -161,6 +166,14 @@ class BatchDecoder {
             check(phq_decode_batch_raw_tags(handle_, n_reads, static_cast< int32_t >(segments.size()), segments.data(), phred_offset, qcfail_in,
                                             aux, aux_stride, aux_length, qcfail_out, NULL));
         }
+        /* the reference's own decoded form of the barcode bearing segments in (Segment::code BAM bytes and Phred bytes,
+           sequence.h:264-300): slicing, reverse complement and packing happen on the device */
+        void classify_bam(int64_t n_reads, const std::vector< phq_raw_segment >& segments, const uint8_t* qcfail_in,
+                          const std::vector< phq_result* >& results, uint8_t* qcfail_out) {
+            check(phq_decode_batch_bam(handle_, n_reads, static_cast< int32_t >(segments.size()), segments.data(), qcfail_in, results.data(), qcfail_out));
+        }
+        /* Classifier::collect across GPUs: in-place all-reduce of the accumulator planes over the host's ncclComm_t */
+        void collect(void* nccl_comm, void* stream) { check(phq_collect(handle_, nccl_comm, stream)); }
         /* device pointers, asynchronous on `stream` */
         void classify_device(int64_t n_reads, const std::vector< phq_tile >& tiles, uint8_t* qcfail, const std::vector< phq_result* >& results, void* stream) {
             check(phq_decode_batch_device(handle_, n_reads, tiles.data(), qcfail, results.data(), stream));

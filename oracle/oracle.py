@@ -29,6 +29,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIBRARY = os.path.join(HERE, "libpheniqs_oracle.so")
 REF_LIBRARY = os.path.join(HERE, "_ref", "libpheniqs_ref.so")
+BINDING_LIBRARY = os.path.join(HERE, "_ref", "libpheniqs_binding.so")
 
 ALGORITHM = {"pamld": 0, "mdd": 1, "naive": 2, "passthrough": 3}
 TOPIC = {"sample": 0, "molecular": 1, "cellular": 2}
@@ -556,6 +557,44 @@ class RefOracle:
 
     def report(self, k: int, precision: int = 15) -> dict:
         return json.loads(self.lib.phq_ref_report(self.handle, k, precision).decode())
+
+
+def binding_available() -> bool:
+    return os.path.exists(BINDING_LIBRARY)
+
+
+def batched_binding(compiled_job: dict, batch: ReadBatch, device: int = 0, batch_reads: int = 2048, stride: int = 256):
+    """oracle/_ref/libpheniqs_binding.so (batched_binding.cpp): the reference-side binding — the reference's own Read /
+    Segment / decoder classes and Read::flush around the product's phq_decode_batch_bam on `device`. Returns what
+    RefOracle.tags returns (per read tag dict, final qcfail flags) plus the job report of the device accumulators.
+    Needs a GPU: the binding has no scoring code of its own."""
+    if not binding_available():
+        raise RuntimeError("oracle/_ref/libpheniqs_binding.so is not built (needs /root/reference; run make -C oracle ref)")
+    lib = C.CDLL(BINDING_LIBRARY)
+    lib.phq_binding_last_error.restype = C.c_char_p
+    code, quality, offset, qcfail = batch._pointers()
+    text = np.zeros((batch.n_reads, 10, stride), dtype=np.uint8)
+    probability = np.zeros((batch.n_reads, 3), dtype=np.float32)
+    flags = np.zeros(batch.n_reads, dtype=np.uint8)
+    report = C.c_void_p()
+    status = lib.phq_binding_run(json.dumps(compiled_job).encode(), device, C.c_int64(batch.n_reads), batch.n_segments, C.c_int64(batch_reads),
+                                 code, quality, offset, qcfail, stride, _p(text, C.c_char), _p(probability, C.c_float), _p(flags, C.c_uint8), C.byref(report))
+    if status != 0:
+        raise RuntimeError(lib.phq_binding_last_error().decode())
+    report_json = json.loads(C.string_at(report).decode())
+    C.CDLL(None).free(report)
+    out = []
+    for r in range(batch.n_reads):
+        record = {}
+        for t, name in enumerate(RefOracle.TAG_NAMES):
+            value = text[r, t].tobytes().split(b"\0", 1)[0]
+            if value:
+                record[name] = value.decode("latin-1")
+        for t, name in enumerate(("XB", "XM", "XC")):
+            if probability[r, t] > 0:
+                record[name] = np.float32(probability[r, t])
+        out.append(record)
+    return out, flags, report_json
 
 
 def best_oracle(compiled_job: dict, input_segment_cardinality: int = 0):
