@@ -338,6 +338,11 @@ int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exac
 /* names of the kernels decoder `decoder` launches with its current tables ("pamld_grid_kernel<8, 8, 2, 8, 1> +
    pamld_tie_kernel<4>"), NUL terminated into buffer[capacity]; for reports and profiles. No reference counterpart. */
 int phq_kernel_description(phq_handle* handle, int decoder, char* buffer, size_t capacity);
+/* power[i] = pow(PHRED_PROBABILITY_BASE, sigma[i]) (phred.h:34, barcode.h:163) as the device forms it where the
+   reference's decision depends on the rounding of pow itself (ties between barcodes whose Kahan sums differ in the
+   last bits): a correctly rounded double-double evaluation, which is what glibc's pow returns except within 2^-68 of a
+   rounding boundary. Host buffers; for parity tests. */
+int phq_reference_power(phq_handle* handle, int64_t n, const double* sigma, double* power);
 /* device time (ms) of the kernels of the last phq_decode_batch_device call, measured with CUDA
    events on the launching stream; synchronises that stream */
 int phq_last_kernel_milliseconds(phq_handle* handle, float* milliseconds);

@@ -72,7 +72,7 @@ EXPORTS = (
     "phq_decode_batch_raw_tags", "phq_tag_record_bytes", "phq_decode_batch_bam", "phq_decode_batch_bam_compact", "phq_decode_batch_bam_tags",
     "phq_host_alloc", "phq_host_free", "phq_accumulators", "phq_totals", "phq_accumulator_buffer",
     "phq_reset_accumulators", "phq_reset_accumulators_async", "phq_collect", "phq_comm_unique_id", "phq_comm_create", "phq_comm_destroy", "phq_estimate_priors", "phq_set_priors", "phq_report", "phq_encode_report", "phq_adjust_job",
-    "phq_statistics", "phq_kernel_description",
+    "phq_statistics", "phq_kernel_description", "phq_reference_power",
     "phq_last_kernel_milliseconds",
 )
 
@@ -131,6 +131,7 @@ def library() -> C.CDLL:
     lib.phq_report.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, P(C.c_void_p)]
     lib.phq_encode_report.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_void_p), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, P(C.c_void_p)]
     lib.phq_adjust_job.argtypes = [C.c_char_p, C.c_char_p, C.c_int, P(C.c_void_p)]
+    lib.phq_reference_power.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.phq_kernel_description.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.phq_last_kernel_milliseconds.argtypes = [C.c_void_p, P(C.c_float)]
     _library = lib

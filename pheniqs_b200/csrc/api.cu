@@ -1797,6 +1797,25 @@ int phq_adjust_job(const char* job_json, const char* report_json, int precision,
     catch(const std::exception& e) { global_error = e.what(); return PHQ_UNKNOWN_ERROR; }
 }
 
+int phq_reference_power(phq_handle* handle, int64_t n, const double* sigma, double* power) {
+    return guarded(handle, [&]() {
+        if(n < 0 || (n > 0 && (sigma == NULL || power == NULL))) { throw InternalError("illegal argument"); }
+        if(n == 0) { return; }
+        DeviceBuffer< double > in, out;
+        in.reserve(static_cast< size_t >(n));
+        out.reserve(static_cast< size_t >(n));
+        std::vector< double > phred;
+        double uniform_quality, base;
+        assemble_phred(phred, uniform_quality, base);
+        cudaError_t status(cudaMemcpy(in.pointer, sigma, static_cast< size_t >(n) * sizeof(double), cudaMemcpyHostToDevice));
+        if(status == cudaSuccess) { status = launch_reference_power(in.pointer, out.pointer, n, base, NULL); }
+        if(status == cudaSuccess) { status = cudaMemcpy(power, out.pointer, static_cast< size_t >(n) * sizeof(double), cudaMemcpyDeviceToHost); }
+        in.release();
+        out.release();
+        PHQ_CUDA(status);
+    });
+}
+
 int phq_kernel_description(phq_handle* handle, int decoder, char* buffer, size_t capacity) {
     return guarded(handle, [&]() {
         if(decoder < 0 || static_cast< size_t >(decoder) >= handle->chain.size()) { throw InternalError("decoder index out of range"); }

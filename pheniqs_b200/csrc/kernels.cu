@@ -61,7 +61,7 @@ __host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool ph
     unsigned at = 0;
     p.off_stage = at;       at += align_up(unsigned(p.stage_capacity) * unsigned(p.stage_buffers) * 16u, 128u);
     p.off_phred = at;       at += phred_tables ? 256u * 8u : 0u;
-    p.off_ratio32 = at;     at += ratio32 ? 128u * 4u : 0u;      /* f32 mismatch ratios of the prefilter scans */
+    p.off_ratio32 = at;     at += ratio32 ? 512u * 16u : 0u;     /* position table of the prefilter scans (PositionEntry) */
     p.off_acc_f64 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_F64_COLUMNS * 8u, 16u);
     p.off_acc_u32 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_U64_COLUMNS * 4u, 16u);
     p.off_misc = at;        at += 16u;          /* totals count, pf_count; diagnostics exact, band */
@@ -172,13 +172,31 @@ struct Accumulator {
             if(passes) { atomicAdd(&global_u64[static_cast< long long >(row) * ACC_U64_COLUMNS + pass_filter], static_cast< unsigned long long >(value)); }
         }
     }
+    /*  Confidences (0 < value <= 1) are summed per CTA in 2^-46 fixed point: shared memory has native 32-bit integer
+        atomics only (a f64 atomicAdd there is a compare-and-swap loop), so the cell — the 8 bytes of the double it
+        stands for — is a low and a high word, the carry of the low word travelling with the high word's add. Exact
+        to 1.4e-14 per read and independent of the order of the adds; a launch covers at most 2^24 reads, far from
+        the 2^18 x 2^14 the high word holds. flush_accumulators converts back. */
     __device__ __forceinline__ void add_pair(int row, int total, int pass_filter, double value, bool passes) const {
-        if(shared_f64 != nullptr) { atomicAdd(&shared_f64[row * ACC_F64_COLUMNS + (passes ? pass_filter : total)], value); }
+        if(shared_f64 != nullptr) {
+            const unsigned long long fixed = static_cast< unsigned long long >(value * 70368744177664.0 + 0.5);
+            uint32_t* const cell = reinterpret_cast< uint32_t* >(&shared_f64[row * ACC_F64_COLUMNS + (passes ? pass_filter : total)]);
+            const uint32_t low = static_cast< uint32_t >(fixed);
+            const uint32_t before = atomicAdd(cell, low);
+            atomicAdd(cell + 1, static_cast< uint32_t >(fixed >> 32) + (before + low < before ? 1u : 0u));
+        }
         else {
             atomicAdd(&global_f64[static_cast< long long >(row) * ACC_F64_COLUMNS + total], value);
             if(passes) { atomicAdd(&global_f64[static_cast< long long >(row) * ACC_F64_COLUMNS + pass_filter], value); }
         }
     }
+};
+
+/* per-position factors of the prefilter scans: B ^ s(match) in f64 (it goes into P0) and B ^ (s(mismatch) - s(match)) in f32 */
+struct __align__(16) PositionEntry {
+    double factor;
+    float ratio;
+    uint32_t pad;
 };
 
 struct BlockState {
@@ -207,8 +225,22 @@ __device__ __forceinline__ BlockState block_prologue(unsigned char* smem, const 
         for(int i = tid; i < 256; i += blockDim.x) { s.phred[i] = P.phred[i]; }
     }
     if(ratio32) {
-        float* const ratio = reinterpret_cast< float* >(smem + s.plan.off_ratio32);
-        for(int i = tid; i < 128; i += blockDim.x) { ratio[i] = P.phred32[i]; }
+        /* what one position contributes, by Phred byte (0..255, clamped at 127 like the reference's table) and,
+           from entry 256 on, for a base that is not A / C / G / T: one 16-byte load per position */
+        PositionEntry* const position = reinterpret_cast< PositionEntry* >(smem + s.plan.off_ratio32);
+        for(int i = tid; i < 512; i += blockDim.x) {
+            const int q = (i & 255) > 127 ? 127 : (i & 255);
+            PositionEntry e;
+            e.pad = 0u;
+            if(i < 256) {
+                e.factor = P.phred[PHRED_MATCH_FACTOR + q];
+                e.ratio = P.phred32[q];
+            } else {
+                e.factor = q != 0 ? P.phred[PHRED_UNIFORM_FACTOR] : 1.0;
+                e.ratio = 1.0f;
+            }
+            position[i] = e;
+        }
     }
     for(int i = tid; i < s.plan.accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) { s.accumulator.shared_u32[i] = 0; }
     for(int i = tid; i < s.plan.accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) { s.accumulator.shared_f64[i] = 0.0; }
@@ -234,9 +266,10 @@ __device__ __forceinline__ void flush_accumulators(const Accumulator& accumulato
         if(v) { atomicAdd(&P.acc_u64[i], v); }
     }
     for(int i = tid; i < rows * ACC_F64_COLUMNS; i += blockDim.x) {
-        double v = accumulator.shared_f64[i];
-        if(i % ACC_F64_COLUMNS == ACC_CONFIDENCE) { v += accumulator.shared_f64[i - ACC_CONFIDENCE + ACC_PF_CONFIDENCE]; }
-        if(v != 0.0) { atomicAdd(&P.acc_f64[i], v); }
+        /* 2^-46 fixed point cells (Accumulator::add_pair) back to f64 */
+        unsigned long long fixed = reinterpret_cast< const unsigned long long* >(accumulator.shared_f64)[i];
+        if(i % ACC_F64_COLUMNS == ACC_CONFIDENCE) { fixed += reinterpret_cast< const unsigned long long* >(accumulator.shared_f64)[i - ACC_CONFIDENCE + ACC_PF_CONFIDENCE]; }
+        if(fixed != 0ull) { atomicAdd(&P.acc_f64[i], static_cast< double >(fixed) * 1.4210854715202004e-14); }
     }
 }
 
@@ -353,6 +386,31 @@ __device__ __forceinline__ void select_four(Selection& s, double p0, double p1, 
     s.second = max(max(s.second, second), __double2hiint(low));
 }
 
+/*  The barcodes that can still tie with the running maximum. Two products tie in the reference when they are equal up
+    to the rounding of its Kahan sums, i.e. their high words differ by at most one; so every barcode whose high word
+    reaches (high word of the running maximum) - 1 when it is scanned is pushed, and a value that exceeds everything
+    before it by more than that empties the list first. Whatever ties with the FINAL maximum is then in the list (the
+    running maximum never exceeds the final one); stale entries are harmless, the tie pass evaluates what is listed and
+    a barcode that is not a candidate loses. More than TIE_CANDIDATES pushes since the last reset = overflow: the tie
+    pass scans the table itself. Used where the test is cheap: the exact path of the whitelist scan (per surviving
+    candidate) and, as bit masks over the distinct words, the separable form of the combinatorial scan. */
+struct CandidateList {
+    uint32_t count;
+    uint32_t entry[TIE_CANDIDATES];
+    __device__ __forceinline__ void reset() { count = 0u; }
+    __device__ __forceinline__ void push(uint32_t index) {
+        if(count < static_cast< uint32_t >(TIE_CANDIDATES)) { entry[count] = index; }
+        ++count;
+    }
+};
+__device__ __forceinline__ void capture_one(CandidateList& list, int& running, double p, int i) {
+    const int h = __double2hiint(p);
+    if(h >= running - 1) {
+        if(h > running + 1) { list.reset(); }
+        list.push(static_cast< uint32_t >(i));
+        running = max(running, h);
+    }
+}
 /*  Selection over the word probabilities of one part of a separable codec: the maximum (first on equality),
     the largest of the others and the sum of the others. */
 struct PartSelection {
@@ -360,8 +418,12 @@ struct PartSelection {
     double second;
     double rest;
     int index;
+    uint32_t near;          /* words (first 32) that can still tie with the running maximum, as CandidateList does it */
 };
 __device__ __forceinline__ void select_part(PartSelection& s, double value, int i) {
+    const int hv = __double2hiint(value), hb = __double2hiint(s.best);
+    const uint32_t bit = 1u << (i & 31);
+    s.near = hv > hb + 1 ? bit : (hv >= hb - 1 ? (s.near | bit) : s.near);
     const bool higher = value > s.best;
     const double low = higher ? s.best : value;
     s.index = higher ? i : s.index;
@@ -508,6 +570,38 @@ __device__ __forceinline__ PositionFactor position_factor(const double* __restri
     return f;
 }
 
+/* queue the lanes with `tied` set for the tie pass: one TieRecord each (one atomic per warp) */
+template < int G >
+__device__ __forceinline__ void queue_ties(const DecoderParams& P, bool tied, int lane, const Selection& selection, double base_probability,
+                                           uint32_t high_quality_mask, bool uniform, uint32_t o_lo, uint32_t o_hi, uint32_t nmask, long long r,
+                                           const uint32_t (&quality)[G], const CandidateList& candidates) {
+    const unsigned queued = __ballot_sync(FULL_MASK, tied);
+    if(queued) {
+        unsigned slot = 0;
+        if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
+        slot = __shfl_sync(FULL_MASK, slot, 0);
+        if(tied) {
+            const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
+            TieRecord record;
+            record.best = selection.best;
+            record.rest = selection.rest;
+            record.base_probability = base_probability;
+            record.high_quality_mask = high_quality_mask;
+            record.uniform = uniform ? 1u : 0u;
+            record.o_lo = o_lo;
+            record.o_hi = o_hi;
+            record.nmask = nmask;
+            record.read = static_cast< uint32_t >(r);
+            #pragma unroll
+            for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
+            record.candidate_count = candidates.count <= static_cast< uint32_t >(TIE_CANDIDATES) ? candidates.count : TIE_RESCAN;
+            #pragma unroll
+            for(int c = 0; c < TIE_CANDIDATES; ++c) { record.candidate[c] = candidates.entry[c]; }
+            P.tie_record[at] = record;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ PAMLD scan kernel */
 /* warps per CTA of the generic scan: as many as the per-warp tables (G x 4 KB) and the register file allow; short
    barcodes leave room for more warps, which is what hides the latency of the dependent lookup -> multiply chains */
@@ -540,7 +634,10 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
     const BarcodeEntry* resident_stage = nullptr;
     if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
 
+    /* the observation of the next tile and the read number of the one after it are requested a tile ahead: in index-list
+       mode the planes cannot be requested before the list entry has arrived */
     long long upcoming_read = read_of_item(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid, items);
+    long long following_read = read_of_item(A, (static_cast< long long >(blockIdx.x) + gridDim.x) * blockDim.x + tid, items);
     ObservedRead< G > upcoming = fetch_read< G >(A, upcoming_read);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = upcoming_read;
@@ -548,7 +645,8 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
 
         /* ---- this lane's read (requested one tile ago); request the next one */
         const ObservedRead< G > observed = upcoming;
-        upcoming_read = read_of_item(A, (tile + gridDim.x) * blockDim.x + tid, items);
+        upcoming_read = following_read;
+        following_read = read_of_item(A, (tile + 2 * static_cast< long long >(gridDim.x)) * blockDim.x + tid, items);
         upcoming = fetch_read< G >(A, upcoming_read);
         const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
         uint32_t qcfail = observed.qcfail;
@@ -640,27 +738,13 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
         /* ---- structural ties (runner-up within 2^-19 of the winner) are resolved by the reference through the
            rounding of its Kahan sums; pamld_tie_kernel reproduces that. Such reads are only queued here. */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        const unsigned queued = __ballot_sync(FULL_MASK, tied);
-        if(queued) {
-            unsigned slot = 0;
-            if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
-            slot = __shfl_sync(FULL_MASK, slot, 0);
-            if(tied) {
-                const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
-                TieRecord record;
-                record.best = selection.best;
-                record.rest = selection.rest;
-                record.base_probability = base_probability;
-                record.high_quality_mask = high_quality_mask;
-                record.uniform = uniform_positions == L ? 1u : 0u;
-                record.o_lo = o_lo;
-                record.o_hi = o_hi;
-                record.nmask = nmask;
-                record.read = static_cast< uint32_t >(r);
-                #pragma unroll
-                for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
-                P.tie_record[at] = record;
-            }
+        {
+            /* the candidates are not collected in this loop (a test per pair costs more than it saves): the tie pass finds them */
+            CandidateList candidates;
+            candidates.count = TIE_CANDIDATES + 1;
+            #pragma unroll
+            for(int c = 0; c < TIE_CANDIDATES; ++c) { candidates.entry[c] = 0u; }
+            queue_ties< G >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
         }
 
         /* ---- decision for this lane's read */
@@ -787,14 +871,16 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
     const long long items = item_cardinality_of(A);
     const long long tile_cardinality = (items + blockDim.x - 1) / blockDim.x;
     long long upcoming_read = read_of_item(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid, items);
+    long long following_read = read_of_item(A, (static_cast< long long >(blockIdx.x) + gridDim.x) * blockDim.x + tid, items);
     ObservedRead< G > upcoming = fetch_read< G >(A, upcoming_read);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = upcoming_read;
         const bool valid = r < A.n_reads;
 
-        /* this lane's read (requested one tile ago); request the next one */
+        /* this lane's read (requested one tile ago); request the next one (and the read number of the one after it) */
         const ObservedRead< G > observed = upcoming;
-        upcoming_read = read_of_item(A, (tile + gridDim.x) * blockDim.x + tid, items);
+        upcoming_read = following_read;
+        following_read = read_of_item(A, (tile + 2 * static_cast< long long >(gridDim.x)) * blockDim.x + tid, items);
         upcoming = fetch_read< G >(A, upcoming_read);
         const uint32_t o_lo = observed.o_lo, o_hi = observed.o_hi, nmask = observed.nmask;
         uint32_t qcfail = observed.qcfail;
@@ -857,13 +943,18 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
+        CandidateList candidates;       /* separable form only: grid entry numbers until the queue step turns them into barcodes */
+        candidates.reset();
+        #pragma unroll
+        for(int c = 0; c < TIE_CANDIDATES; ++c) { candidates.entry[c] = 0u; }
+        if constexpr(!UNIFORM) { candidates.count = TIE_CANDIDATES + 1; }       /* the pair loops do not collect: the tie pass scans */
         if constexpr(UNIFORM) {
             /* ---- full grid under one prior: p(a, k) = SA[a] * SB[k] * prior is separable, so the maximum is
                (argmax SA, argmax SB), the runner-up is one of (best A, second B) / (second A, best B), and the
                sum of everything else follows from the two parts' sums. KA + KB word products per read instead
                of KA * KB pair products; the values are the same single roundings the pair loop would form. */
             PartSelection part_b;
-            part_b.best = 0.0; part_b.second = 0.0; part_b.rest = 0.0; part_b.index = 0;
+            part_b.best = 0.0; part_b.second = 0.0; part_b.rest = 0.0; part_b.index = 0; part_b.near = 0u;
             #pragma unroll 4
             for(int k = 0; k < KB; ++k) {
                 const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
@@ -871,7 +962,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                 select_part(part_b, part_product< W, GA, GB >(table_base, m), k);
             }
             PartSelection part_a;
-            part_a.best = 0.0; part_a.second = 0.0; part_a.rest = 0.0; part_a.index = 0;
+            part_a.best = 0.0; part_a.second = 0.0; part_a.rest = 0.0; part_a.index = 0; part_a.near = 0u;
             #pragma unroll 4
             for(int a = 0; a < KA; ++a) {
                 const uint2 h = *reinterpret_cast< const uint2* >(header + a);
@@ -886,6 +977,17 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
             selection.index = part_a.index * KB + part_b.index;
             selection.rest = (part_a.best * part_b.rest + part_a.rest * (part_b.best + part_b.rest)) * prior;
             selection.best = best * prior;
+            if(selection.second != 0) {
+                /* whatever ties with the maximum pairs a word that ties with the best A word and one that ties with the best B word */
+                if(KA > 32 || KB > 32) { candidates.count = TIE_CANDIDATES + 1; }
+                else {
+                    for(uint32_t wa = part_a.near; wa != 0u; wa &= wa - 1u) {
+                        for(uint32_t wb = part_b.near; wb != 0u; wb &= wb - 1u) {
+                            candidates.push(static_cast< uint32_t >((__ffs(static_cast< int >(wa)) - 1) * KB + (__ffs(static_cast< int >(wb)) - 1)));
+                        }
+                    }
+                }
+            }
         } else if constexpr(KBP > 0) {
             /* ---- dense grid: B word probabilities in registers */
             double sb[KBP];
@@ -941,28 +1043,10 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         /* ---- ties are queued; everything else is decided here */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        const unsigned queued = __ballot_sync(FULL_MASK, tied);
-        if(queued) {
-            unsigned slot = 0;
-            if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
-            slot = __shfl_sync(FULL_MASK, slot, 0);
-            if(tied) {
-                const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
-                TieRecord record;
-                record.best = selection.best;
-                record.rest = selection.rest;
-                record.base_probability = base_probability;
-                record.high_quality_mask = high_quality_mask;
-                record.uniform = uniform_positions == L ? 1u : 0u;
-                record.o_lo = o_lo;
-                record.o_hi = o_hi;
-                record.nmask = nmask;
-                record.read = static_cast< uint32_t >(r);
-                #pragma unroll
-                for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
-                P.tie_record[at] = record;
-            }
+        if(tied && candidates.count <= static_cast< uint32_t >(TIE_CANDIDATES)) {
+            for(uint32_t c = 0; c < candidates.count; ++c) { candidates.entry[c] = entry[candidates.entry[c]].index; }
         }
+        queue_ties< G >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
         const bool decided = valid && !tied;
         if(decided) {
             const int winner = static_cast< int >(entry[selection.index].index);
@@ -1071,26 +1155,33 @@ __device__ __forceinline__ void fast_store_group(float* t, const float* w) {
         }
     }
 }
-/* per-position f32 mismatch ratios of a read and its P0 (f64, position order: the same bits the exact scans form) */
-template < int G, int POSITIONS >
-__device__ __forceinline__ double fast_factors(const double* __restrict__ match64, const float* __restrict__ ratio32, double uniform_factor,
-                                               const uint32_t (&quality)[G], uint32_t nmask, float (&w)[POSITIONS]) {
-    double base_probability = 1.0;
+/*  One table group of a read: the f32 mismatch ratios of its COUNT positions (from `first` on) out of the CTA's position
+    table — one LDS.128 per position, indexed by the Phred byte and the no-call bit —, their match factors multiplied
+    into P0 (f64, position order: the same bits the exact scans form), and the 2^COUNT subset products stored. Group by
+    group, so only four ratios are live at a time. */
+template < int G, int COUNT >
+__device__ __forceinline__ void fast_group(uint32_t position_table, const uint32_t (&quality)[G], uint32_t nmask, int first, double& base_probability, float* t) {
+    float w[COUNT];
     #pragma unroll
-    for(int j = 0; j < POSITIONS; ++j) {
-        uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        q = q > 127u ? 127u : q;
-        const bool ambiguous = (nmask >> j) & 1u;
-        float ratio = ratio32[q];
-        double factor = match64[q];
-        if(ambiguous) {
-            ratio = 1.0f;
-            if(q != 0u) { factor = uniform_factor; }
-        }
-        w[j] = ratio;
-        base_probability *= factor;
+    for(int k = 0; k < COUNT; ++k) {
+        const int j = first + k;
+        const uint32_t q = __byte_perm(quality[j >> 2], 0u, 0x4440 + (j & 3));
+        const uint32_t ambiguity = (j <= 8) ? (nmask << (j <= 8 ? 8 - j : 0)) : (nmask >> (j <= 8 ? 0 : j - 8));
+        uint32_t index;
+        asm("lop3.b32 %0, %1, 0x100, %2, 0xEA;" : "=r"(index) : "r"(ambiguity), "r"(q));      /* (ambiguity & 0x100) | q */
+        uint32_t factor_lo, factor_hi, ratio, pad;
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(factor_lo), "=r"(factor_hi), "=r"(ratio), "=r"(pad) : "r"(position_table + index * 16u));
+        w[k] = __uint_as_float(ratio);
+        base_probability *= __hiloint2double(static_cast< int >(factor_hi), static_cast< int >(factor_lo));
     }
-    return base_probability;
+    fast_store_group< COUNT >(t, w);
+}
+template < int G >
+__device__ __forceinline__ void fast_group_of(int count, uint32_t position_table, const uint32_t (&quality)[G], uint32_t nmask, int first, double& base_probability, float* t) {
+    if(count >= 4) { fast_group< G, 4 >(position_table, quality, nmask, first, base_probability, t); }
+    else if(count == 3) { fast_group< G, 3 >(position_table, quality, nmask, first, base_probability, t); }
+    else if(count == 2) { fast_group< G, 2 >(position_table, quality, nmask, first, base_probability, t); }
+    else { fast_group< G, 1 >(position_table, quality, nmask, first, base_probability, t); }
 }
 /* the winner's mismatch product in f64 over the mismatched, unambiguous positions */
 template < int G, int POSITIONS >
@@ -1187,7 +1278,7 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     extern __shared__ __align__(256) unsigned char smem[];
     const BlockState S = block_prologue(smem, P, true, 0, true);
     const BarcodeStream stream(S, P, P.fast_barcodes);
-    const float* const ratio32 = reinterpret_cast< const float* >(smem + S.plan.off_ratio32);
+    const uint32_t position_table = shared_address(smem + S.plan.off_ratio32);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -1195,7 +1286,6 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     const uint32_t aligned_tables = ((window + S.plan.off_tables + 2047u) & ~2047u) - window;
     float* const table = reinterpret_cast< float* >(smem + aligned_tables) + static_cast< size_t >(warp) * (G * FAST_GROUP_FLOATS) + lane;
     const uint32_t table_base = shared_address(table);
-    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
     const int L = P.nucleotide_cardinality;
     const uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
     unsigned* const hard_count = P.tie_count + 2;
@@ -1222,10 +1312,9 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
         for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
 
         /* ---- f32 ratios, P0, subset tables */
-        float w[4 * G];
-        const double base_probability = fast_factors< G, 4 * G >(S.phred + PHRED_MATCH_FACTOR, ratio32, uniform_factor, quality, nmask, w);
+        double base_probability = 1.0;
         #pragma unroll
-        for(int g = 0; g < G; ++g) { fast_store_group< 4 >(table + g * FAST_GROUP_FLOATS, w + 4 * g); }
+        for(int g = 0; g < G; ++g) { fast_group< G, 4 >(position_table, quality, nmask, 4 * g, base_probability, table + g * FAST_GROUP_FLOATS); }
         __syncwarp();
 
         /* ---- every barcode, in f32 */
@@ -1311,7 +1400,7 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
     constexpr uint32_t MASK_B = (1u << LB) - 1u;
     extern __shared__ __align__(256) unsigned char smem[];
     const BlockState S = block_prologue(smem, P, true, P.grid_a + P.grid_b + P.grid_entries, true);
-    const float* const ratio32 = reinterpret_cast< const float* >(smem + S.plan.off_ratio32);
+    const uint32_t position_table = shared_address(smem + S.plan.off_ratio32);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -1330,7 +1419,6 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
     const uint32_t aligned_tables = ((window + S.plan.off_tables + 2047u) & ~2047u) - window;
     float* const table = reinterpret_cast< float* >(smem + aligned_tables) + static_cast< size_t >(warp) * ((GA + GB) * FAST_GROUP_FLOATS) + lane;
     const uint32_t table_base = shared_address(table);
-    const double uniform_factor = P.phred[PHRED_UNIFORM_FACTOR];
     constexpr uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
     unsigned* const hard_count = P.tie_count + 2;
     const float prior32 = static_cast< float >(entry[0].prior);
@@ -1348,20 +1436,11 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
         #pragma unroll
         for(int g = 0; g < G; ++g) { quality[g] = decode_quality< G >(A, observed.raw, g); }
 
-        float w[L];
-        const double base_probability = fast_factors< G, L >(S.phred + PHRED_MATCH_FACTOR, ratio32, uniform_factor, quality, nmask, w);
+        double base_probability = 1.0;          /* position order: the A part, then the B part */
         #pragma unroll
-        for(int g = 0; g < GA; ++g) {
-            constexpr int full = LA / 4;
-            if(g < full) { fast_store_group< 4 >(table + g * FAST_GROUP_FLOATS, w + 4 * g); }
-            else { fast_store_group< (LA % 4 == 0 ? 4 : LA % 4) >(table + g * FAST_GROUP_FLOATS, w + 4 * g); }
-        }
+        for(int g = 0; g < GA; ++g) { fast_group_of< G >(LA - 4 * g, position_table, quality, nmask, 4 * g, base_probability, table + g * FAST_GROUP_FLOATS); }
         #pragma unroll
-        for(int g = 0; g < GB; ++g) {
-            constexpr int full = LB / 4;
-            if(g < full) { fast_store_group< 4 >(table + (GA + g) * FAST_GROUP_FLOATS, w + LA + 4 * g); }
-            else { fast_store_group< (LB % 4 == 0 ? 4 : LB % 4) >(table + (GA + g) * FAST_GROUP_FLOATS, w + LA + 4 * g); }
-        }
+        for(int g = 0; g < GB; ++g) { fast_group_of< G >(LB - 4 * g, position_table, quality, nmask, LA + 4 * g, base_probability, table + (GA + g) * FAST_GROUP_FLOATS); }
         __syncwarp();
 
         const uint32_t a_lo = o_lo & MASK_A, a_hi = o_hi & MASK_A, a_n = nmask & MASK_A;
@@ -1442,6 +1521,7 @@ constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold ba
 constexpr int WHITELIST_WORDS = 128;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 2 x 32); expanded up to 32 at a time */
 constexpr int WHITELIST_MAX_WARPS = 15;
 constexpr double WHITELIST_TOLERANCE = 4.76837158203125e-07;       /* 2^-21: half of the 1e-6 the path allows, as a worst case bound */
+constexpr double WHITELIST_ABSOLUTE = 4.656612873077393e-10;       /* 2^-31: the most the pruned mass may move a confidence, as a fraction of sigma_p */
 
 /* per-warp shared memory of pamld_whitelist_kernel */
 constexpr unsigned WL_OFF_TABLE = 0;                                                    /* 32 entries x 256 B: subset products of 8 groups of 2 positions, lane skewed */
@@ -1562,6 +1642,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
     const int L = P.nucleotide_cardinality;
     const int group_cardinality = P.whitelist_chunks;
     const double tolerance_per_barcode = WHITELIST_TOLERANCE / static_cast< double >(P.barcode_cardinality);
+    const double absolute_per_barcode = WHITELIST_ABSOLUTE / static_cast< double >(P.barcode_cardinality);
     const long long unit_cardinality = (A.n_reads + 31) / 32;
     /* the ring: groups are copied and consumed in one running order; the stage and the mbarrier phase of the next
        group to consume and of the next one to copy are carried along */
@@ -1701,6 +1782,8 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
 
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
+        CandidateList candidates;               /* the barcodes that can tie with the maximum, for the tie pass */
+        candidates.reset();
         unsigned head = 0, tail = 0;            /* candidates evaluated / appended so far (warp uniform) */
 
         /*  Evaluate candidates [head, head + n) of the queue, one per lane (the barcode word and prior come from the
@@ -1736,14 +1819,21 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
                         /* below half the maximum: neither the winner nor a tie, it only adds to the rest */
                         selection.rest += p;
                     } else {
-                        select_one(selection, p, static_cast< int >(queue_key[(head + e) & (WHITELIST_QUEUE - 1)] & 0x7ffffffu));
+                        const int barcode = static_cast< int >(queue_key[(head + e) & (WHITELIST_QUEUE - 1)] & 0x7ffffffu);
+                        int running = __double2hiint(selection.best);
+                        capture_one(candidates, running, p, barcode);       /* whatever can tie with the maximum is at least half of it */
+                        select_one(selection, p, barcode);
                         half_best = 0.5 * selection.best;
                     }
                 }
             }
             if(mine) {
                 /* the threshold follows the maximum and the rest once per batch: it only grows, so the older one was conservative */
-                threshold = fmin(half_best, tolerance_per_barcode * (noise_term + selection.rest));
+                /* the pruned barcodes together stay below 2^-21 of the part of sigma_p that is not the winner (the error
+                   probability keeps six digits) AND below 2^-31 of sigma_p itself (no confidence moves by more than
+                   that, whatever the read: the accumulated confidences stay within 1e-9) */
+                threshold = fmin(fmin(half_best, tolerance_per_barcode * (noise_term + selection.rest)),
+                                 absolute_per_barcode * (selection.best + (noise_term + selection.rest)));
                 while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
             }
             head += n;
@@ -1845,28 +1935,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
 
         /* ---- structural ties are queued for pamld_tie_kernel, everything else is decided here (as pamld_kernel) */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        const unsigned queued = __ballot_sync(FULL_MASK, tied);
-        if(queued) {
-            unsigned slot = 0;
-            if(lane == 0) { slot = atomicAdd(P.tie_count, static_cast< unsigned >(__popc(queued))); }
-            slot = __shfl_sync(FULL_MASK, slot, 0);
-            if(tied) {
-                const unsigned at = slot + __popc(queued & ((1u << lane) - 1u));
-                TieRecord record;
-                record.best = selection.best;
-                record.rest = selection.rest;
-                record.base_probability = base_probability;
-                record.high_quality_mask = high_quality_mask;
-                record.uniform = uniform_positions == L ? 1u : 0u;
-                record.o_lo = o_lo;
-                record.o_hi = o_hi;
-                record.nmask = nmask;
-                record.read = static_cast< uint32_t >(r);
-                #pragma unroll
-                for(int g = 0; g < 8; ++g) { record.quality[g] = g < 4 ? quality[g < 4 ? g : 0] : 0u; }
-                P.tie_record[at] = record;
-            }
-        }
+        queue_ties< 4 >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
         const bool decided = valid && !tied;
         if(decided) {
             const BarcodeEntry e = P.barcodes[selection.index];
@@ -1915,17 +1984,111 @@ struct Candidate {
     double sigma;
     int index;              /* -1 = none */
 };
-__device__ __noinline__ double adjusted_probability(double base, double sigma, double prior) {
-    return pow(base, sigma) * prior;
+
+/*  pow(B, sigma) as the reference's libm forms it. The reference compares p = pow(B, sigma) * prior with strict >, so
+    two candidates whose sigma_q differ in the last bits can still have EQUAL p (then the first keeps the read), and
+    candidates with different priors are ordered by the rounded products. glibc's pow is correctly rounded except
+    within 2^-68 (relative) of a rounding boundary, so the correctly rounded value is computed here: B^sigma =
+    2^k exp(r), r = sigma ln B - k ln 2 in double-double arithmetic (ln of the DOUBLE B = pow(10.0, -0.1) the
+    reference raises, to 160 bits), exp by its Taylor series to degree 24, rounded once. Only the tie pass calls it,
+    and only where the comparison needs it (see beats); B itself is checked against the constant it was derived for. */
+struct DoubleDouble { double hi, lo; };
+__device__ __forceinline__ DoubleDouble two_sum(double a, double b) {
+    DoubleDouble r;
+    r.hi = __dadd_rn(a, b);
+    const double bb = __dsub_rn(r.hi, a);
+    r.lo = __dadd_rn(__dsub_rn(a, __dsub_rn(r.hi, bb)), __dsub_rn(b, bb));
+    return r;
+}
+__device__ __forceinline__ DoubleDouble quick_two_sum(double a, double b) {
+    DoubleDouble r;
+    r.hi = __dadd_rn(a, b);
+    r.lo = __dsub_rn(b, __dsub_rn(r.hi, a));
+    return r;
+}
+__device__ __forceinline__ DoubleDouble two_product(double a, double b) {
+    DoubleDouble r;
+    r.hi = __dmul_rn(a, b);
+    r.lo = __fma_rn(a, b, -r.hi);
+    return r;
+}
+__device__ __forceinline__ DoubleDouble dd_add(DoubleDouble a, DoubleDouble b) {
+    DoubleDouble s = two_sum(a.hi, b.hi);
+    const DoubleDouble t = two_sum(a.lo, b.lo);
+    s.lo = __dadd_rn(s.lo, t.hi);
+    s = quick_two_sum(s.hi, s.lo);
+    s.lo = __dadd_rn(s.lo, t.lo);
+    return quick_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ DoubleDouble dd_multiply(DoubleDouble a, DoubleDouble b) {
+    DoubleDouble p = two_product(a.hi, b.hi);
+    p.lo = __dadd_rn(p.lo, __dadd_rn(__dmul_rn(a.hi, b.lo), __dmul_rn(a.lo, b.hi)));
+    return quick_two_sum(p.hi, p.lo);
+}
+__constant__ double INVERSE_FACTORIAL[25][2] = {
+    { 0x1.0000000000000p+0, 0x0.0p+0 },
+    { 0x1.0000000000000p+0, 0x0.0p+0 },
+    { 0x1.0000000000000p-1, 0x0.0p+0 },
+    { 0x1.5555555555555p-3, 0x1.5555555555555p-57 },
+    { 0x1.5555555555555p-5, 0x1.5555555555555p-59 },
+    { 0x1.1111111111111p-7, 0x1.1111111111111p-63 },
+    { 0x1.6c16c16c16c17p-10, -0x1.f49f49f49f49fp-65 },
+    { 0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-73 },
+    { 0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76 },
+    { 0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73 },
+    { 0x1.27e4fb7789f5cp-22, 0x1.cbbc05b4fa99ap-76 },
+    { 0x1.ae64567f544e4p-26, -0x1.c062e06d1f209p-80 },
+    { 0x1.1eed8eff8d898p-29, -0x1.2aec959e14c06p-83 },
+    { 0x1.6124613a86d09p-33, 0x1.f28e0cc748ebep-87 },
+    { 0x1.93974a8c07c9dp-37, 0x1.05d6f8a2efd1fp-92 },
+    { 0x1.ae7f3e733b81fp-41, 0x1.1d8656b0ee8cbp-97 },
+    { 0x1.ae7f3e733b81fp-45, 0x1.1d8656b0ee8cbp-101 },
+    { 0x1.952c77030ad4ap-49, 0x1.ac981465ddc6cp-103 },
+    { 0x1.6827863b97d97p-53, 0x1.eec01221a8b0bp-107 },
+    { 0x1.2f49b46814157p-57, 0x1.2650f61dbdcb4p-112 },
+    { 0x1.e542ba4020225p-62, 0x1.ea72b4afe3c2fp-120 },
+    { 0x1.71b8ef6dcf572p-66, -0x1.d043ae40c4647p-120 },
+    { 0x1.0ce396db7f853p-70, -0x1.aebcdbd20331cp-124 },
+    { 0x1.761b41316381ap-75, -0x1.3423c7d91404fp-130 },
+    { 0x1.f2cf01972f578p-80, -0x1.9ada5fcc1ab14p-135 },
+};
+constexpr double REFERENCE_BASE = 0x1.96b230bcdc434p-1;            /* pow(10.0, -0.1), phred.h:34 */
+__device__ __noinline__ double reference_power(double base, double sigma) {
+    if(base != REFERENCE_BASE || !(sigma >= 0.0) || sigma > 3000.0) { return pow(base, sigma); }      /* another libm's B, or a subnormal result */
+    /* y = sigma ln B */
+    DoubleDouble y = two_product(sigma, -0x1.d791c5f888823p-3);
+    y.lo = __dadd_rn(y.lo, __dmul_rn(sigma, 0x1.28d13257a2671p-60));
+    y = quick_two_sum(y.hi, y.lo);
+    /* r = y - k ln 2 */
+    const double k = rint(__dmul_rn(y.hi, 0x1.71547652b82fep+0));
+    DoubleDouble t = two_product(k, -0x1.62e42fefa39efp-1);
+    t.lo = __dadd_rn(t.lo, __dmul_rn(k, -0x1.abc9e3b39803fp-56));
+    t = quick_two_sum(t.hi, t.lo);
+    DoubleDouble r = dd_add(y, t);
+    r.lo = __dadd_rn(r.lo, __dmul_rn(k, -0x1.7b57a079a1934p-111));
+    r = quick_two_sum(r.hi, r.lo);
+    /* exp(r), |r| <= 0.35: Horner over the Taylor coefficients */
+    DoubleDouble e;
+    e.hi = INVERSE_FACTORIAL[24][0]; e.lo = INVERSE_FACTORIAL[24][1];
+    #pragma unroll 1
+    for(int n = 23; n >= 0; --n) {
+        DoubleDouble c;
+        c.hi = INVERSE_FACTORIAL[n][0]; c.lo = INVERSE_FACTORIAL[n][1];
+        e = dd_add(dd_multiply(e, r), c);
+    }
+    return scalbn(e.hi, static_cast< int >(k));
 }
 __device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, double base) {
     if(a.index < 0) { return false; }
     if(b.index < 0) { return true; }
     if(a.prior == b.prior) {
-        return a.sigma < b.sigma || (a.sigma == b.sigma && a.index < b.index);
+        if(a.sigma == b.sigma) { return a.index < b.index; }
+        /* from 64 on, one ulp of sigma moves pow(B, sigma) by more than 2^-48: neither pow nor the product with the
+           common prior can merge or reorder the two, the smaller sigma is the larger p */
+        if(fmin(a.sigma, b.sigma) >= 64.0) { return a.sigma < b.sigma; }
     }
-    const double pa = adjusted_probability(base, a.sigma, a.prior);
-    const double pb = adjusted_probability(base, b.sigma, b.prior);
+    const double pa = reference_power(base, a.sigma) * a.prior;
+    const double pb = reference_power(base, b.sigma) * b.prior;
     return pa > pb || (pa == pb && a.index < b.index);
 }
 
@@ -2029,16 +2192,24 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
             W.ratio[slot][j] = ambiguous ? 1.0 : phred_shared[PHRED_MISMATCH_RATIO + q];
         }
         __syncwarp();
-        /* subset product table (linear: any lane -> entry mapping is conflict free or a broadcast), same
-           association as the scan kernel: ((w0 w1) w2) w3 */
-        for(int e = sub; e < G * 16; e += TIE_LANES) {
-            const int g = e >> 4;
-            double t = 1.0;
-            #pragma unroll
-            for(int k = 0; k < 4; ++k) {
-                if((e >> k) & 1) { t *= W.ratio[slot][g * 4 + k]; }
+        /*  The scan usually names the candidates (TieRecord::candidate): then only those are evaluated. A read whose
+            list overflowed, or that comes from a scan that does not collect (the whitelist scan), has its candidates
+            found here by a scan of the whole table; the subset product table is only built when the warp has one. */
+        const uint32_t listed = live ? record.candidate_count : 0u;
+        const bool rescan = listed > static_cast< uint32_t >(TIE_CANDIDATES);
+        const bool any_rescan = __any_sync(FULL_MASK, rescan);
+        if(any_rescan) {
+            /* subset product table (linear: any lane -> entry mapping is conflict free or a broadcast), same
+               association as the scan kernel: ((w0 w1) w2) w3 */
+            for(int e = sub; e < G * 16; e += TIE_LANES) {
+                const int g = e >> 4;
+                double t = 1.0;
+                #pragma unroll
+                for(int k = 0; k < 4; ++k) {
+                    if((e >> k) & 1) { t *= W.ratio[slot][g * 4 + k]; }
+                }
+                W.table[slot][e] = t;
             }
-            W.table[slot][e] = t;
         }
         __syncwarp();
 
@@ -2087,18 +2258,8 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
             __syncwarp();
         };
 
-        #pragma unroll 1
-        for(int first = 0; first < N; first += TIE_LANES) {
-            const int b = first + sub;
-            bool candidate = false;
-            if(live && b < N) {
-                const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
-                const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
-                double p = table[m & 15u];
-                #pragma unroll
-                for(int g = 1; g < G; ++g) { p *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
-                candidate = p * __hiloint2double(raw.w, raw.z) >= threshold;
-            }
+        /* offer one barcode per lane (or none) to the pool of candidates the warp evaluates 32 at a time */
+        auto offer = [&](bool candidate, int b) {
             const unsigned found = __ballot_sync(FULL_MASK, candidate);
             if(found) {
                 const int fresh = __popc(found);
@@ -2110,18 +2271,76 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
                 count += fresh;
                 __syncwarp();
             }
+        };
+        /*  The candidates the scan named: lane `sub` of a read evaluates its candidate c + sub on the spot (no pooling),
+            then the read's lanes reduce to the one the reference's scan would keep (beats is a strict total order, so
+            the butterfly leaves every lane of the read with the same winner). */
+        {
+            const uint32_t mine = rescan ? 0u : listed;
+            const uint32_t most = __reduce_max_sync(FULL_MASK, mine);
+            for(uint32_t c = 0; c < most; c += TIE_LANES) {
+                Candidate own;
+                own.prior = 0; own.sigma = 0; own.index = -1;
+                if(c + sub < mine) {
+                    const int b = static_cast< int >(P.tie_record[item].candidate[c + sub]);
+                    if(b < N) {
+                        const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
+                        const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
+                        /* Barcode::compensated_decoding_probability's accumulation, bit for bit (barcode.h:147-162) */
+                        const double* const on_match = W.match_value[slot];
+                        const double* const on_mismatch = W.mismatch_value[slot];
+                        double sigma = 0.0, compensation = 0.0;
+                        #pragma unroll 4
+                        for(int j = 0; j < L; ++j) {
+                            const double value = ((m >> j) & 1u) ? on_mismatch[j] : on_match[j];
+                            const double y = __dsub_rn(value, compensation);
+                            const double t = __dadd_rn(sigma, y);
+                            compensation = __dsub_rn(__dsub_rn(t, sigma), y);
+                            sigma = t;
+                        }
+                        own.prior = __hiloint2double(raw.w, raw.z); own.sigma = sigma; own.index = b;
+                    }
+                }
+                #pragma unroll
+                for(int offset = TIE_LANES / 2; offset > 0; offset >>= 1) {
+                    Candidate other;
+                    other.prior = __shfl_xor_sync(FULL_MASK, own.prior, offset);
+                    other.sigma = __shfl_xor_sync(FULL_MASK, own.sigma, offset);
+                    other.index = __shfl_xor_sync(FULL_MASK, own.index, offset);
+                    if(beats(other, own, base)) { own = other; }
+                }
+                if(sub == 0 && beats(own, best, base)) { best = own; }
+            }
+        }
+        if(any_rescan) {
+            #pragma unroll 1
+            for(int first = 0; first < N; first += TIE_LANES) {
+                const int b = first + sub;
+                bool candidate = false;
+                if(rescan && b < N) {
+                    const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
+                    const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
+                    double p = table[m & 15u];
+                    #pragma unroll
+                    for(int g = 1; g < G; ++g) { p *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
+                    candidate = p * __hiloint2double(raw.w, raw.z) >= threshold;
+                }
+                offer(candidate, b);
+            }
         }
         if(count) { evaluate(count); }
 
+        /* the winner's mismatch product, the read's lanes sharing its positions (ratio 1 where the base is ambiguous) */
+        const int winner = max(__shfl_sync(FULL_MASK, best.index, slot * TIE_LANES), 0);
+        const uint4 winner_entry = *reinterpret_cast< const uint4* >(barcodes + winner);
+        const uint32_t m = ((o_lo ^ winner_entry.x) | (o_hi ^ winner_entry.y)) | nmask;
+        double t = 1.0;
+        for(int j = sub; j < L; j += TIE_LANES) { if((m >> j) & 1u) { t *= W.ratio[slot][j]; } }
+        #pragma unroll
+        for(int offset = TIE_LANES / 2; offset > 0; offset >>= 1) { t *= __shfl_xor_sync(FULL_MASK, t, offset); }
         if(sub == 0 && live) {
             const long long r = record.read;
-            const int winner = best.index >= 0 ? best.index : 0;
-            const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + winner);
-            const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
-            const double prior = __hiloint2double(raw.w, raw.z);
-            double t = table[m & 15u];
-            #pragma unroll
-            for(int g = 1; g < G; ++g) { t *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
+            const double prior = __hiloint2double(winner_entry.w, winner_entry.z);
             /* everything but the winner: the scan's total minus the winner. The winner is within 2^-18 of
                the scan's maximum, so the first difference is exact (Sterbenz) and nothing cancels. */
             const double others = (record.best - t * prior) + record.rest;
@@ -2450,6 +2669,13 @@ count_kernel(const DecoderParams P, const TileArguments A) {
     }
 }
 
+/* pow(B, sigma) as the tie pass forms it, for the parity tests (phq_reference_power) */
+__global__ void reference_power_kernel(const double* __restrict__ sigma, double* __restrict__ out, long long n, double base) {
+    for(long long i = static_cast< long long >(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x) {
+        out[i] = reference_power(base, sigma[i]);
+    }
+}
+
 /* the tie pass over the reads the scan queued; the queue length is only known on the device: a fixed grid strides over it */
 template < int G >
 cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
@@ -2705,6 +2931,12 @@ cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, c
     rest.index_list = queue;
     rest.index_count = queue_count;
     return launch_mdd_scan(params, rest, geometry, stream);
+}
+
+cudaError_t launch_reference_power(const double* sigma, double* out, long long n, double base, cudaStream_t stream) {
+    if(n <= 0) { return cudaSuccess; }
+    reference_power_kernel<<< 296, 256, 0, stream >>>(sigma, out, n, base);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {

@@ -85,6 +85,8 @@ constexpr int WHITELIST_CHUNK_BYTES = WHITELIST_EQUALITY_WORDS * 4;
 constexpr int WHITELIST_MINIMUM_BARCODES = 4096;    /* smaller codecs use the exhaustive scans (PHQ_WHITELIST_MINIMUM overrides, for tests) */
 
 /* what the scan kernel hands to the tie kernel for a queued read */
+constexpr int TIE_CANDIDATES = 11;                  /* barcodes the scan can name as possible winners of a queued read */
+constexpr uint32_t TIE_RESCAN = 0xffffffffu;        /* candidate_count of a read whose candidates the tie kernel has to find itself */
 struct __align__(16) TieRecord {
     double best;                /* the scan's maximum prior adjusted product (relative to P0) */
     double rest;                /* the scan's sum of all other products */
@@ -94,7 +96,10 @@ struct __align__(16) TieRecord {
     uint32_t o_lo, o_hi, nmask; /* the observation */
     uint32_t read;              /* read index within the launch */
     uint32_t quality[8];
+    uint32_t candidate_count;   /* barcodes named below; more than TIE_CANDIDATES (TIE_RESCAN) = scan the whole table */
+    uint32_t candidate[TIE_CANDIDATES];     /* every barcode whose product is within 2^-19 of the maximum is among them */
 };
+static_assert(sizeof(TieRecord) == 128, "one tie record is 128 bytes");
 
 struct DecoderParams {
     int32_t algorithm;
@@ -176,6 +181,8 @@ cudaError_t launch_mdd(const DecoderParams& params, const TileArguments& tile, c
 void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, size_t capacity);
 cudaError_t launch_count(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& geometry);
+/* out[i] = pow(base, sigma[i]) as the tie pass forms it (correctly rounded double-double evaluation); device pointers */
+cudaError_t launch_reference_power(const double* sigma, double* out, long long n, double base, cudaStream_t stream);
 /* (first segment length, total length) pairs the combinatorial scan is instantiated for */
 inline bool grid_shape_supported(int split, int total) { return (split == 6 && total == 12) || (split == 8 && total == 16) || (split == 10 && total == 20) || (split == 12 && total == 24); }
 

@@ -455,6 +455,13 @@ class DecoderChain:
                 noise, concentration = self.estimate_priors(k)
                 self.set_priors(k, noise, concentration)
 
+    def reference_power(self, sigma):
+        """pow(B, sigma) as the tie pass forms it (phq_reference_power)."""
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+        out = np.zeros_like(sigma)
+        check(self.lib.phq_reference_power(self.handle, sigma.size, sigma.ctypes.data, out.ctypes.data), self.handle)
+        return out
+
     def statistics(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(self.lib.phq_statistics(self.handle, C.byref(a), C.byref(b), C.byref(c)), self.handle)

@@ -346,3 +346,54 @@ def test_large_batch_properties():
     got = results[0][begin:begin + count].cpu().numpy().view(RESULT_DTYPE).reshape(-1)
     helpers.compare_pamld(got, expected.index[:, 0], expected.distance[:, 0], expected.confidence[:, 0], "slice")
     assert np.array_equal(flags[begin:begin + count].cpu().numpy(), expected.qcfail)
+
+
+def test_reference_power_is_the_libm_pow():
+    """The tie pass compares p = pow(B, sigma) * prior where the reference's decision hangs on the rounding of pow itself
+    (barcode.h:163, pamld.cpp:73). The device evaluates pow in double-double arithmetic, correctly rounded; glibc's pow is
+    correctly rounded except in about one case in a thousand, where it is one ulp off: so the two agree bit for bit
+    on at least 99.8 % of random exponents and never differ by more than one ulp."""
+    import math
+    rng = np.random.default_rng(5)
+    sigma = np.concatenate([rng.random(100000) * 8, rng.random(100000) * 64, rng.random(100000) * 1200, np.arange(0, 130, dtype=np.float64), np.array([0.0, 3000.0])])
+    job = {"sample": helpers.random_job(rng, "pamld", (8,), 12)}
+    chain = DecoderChain(compile_job(job), device=0)
+    got = chain.reference_power(sigma)
+    base = math.pow(10.0, -0.1)
+    want = np.array([math.pow(base, x) for x in sigma])
+    same = got == want
+    assert same.mean() >= 0.998, same.mean()
+    assert np.all(np.abs(got - want) <= np.spacing(want)), "more than one ulp from libm"
+    chain.close()
+
+
+def test_ties_between_sigmas_one_ulp_apart_keep_the_first_barcode():
+    """Two barcodes one low quality mismatch away from the read, at different positions: their Kahan sums hold the same
+    values in a different order and can differ in the last bit while pow() of both is the same double, and the reference
+    then keeps the FIRST barcode (strict >, pamld.cpp:73). Small sigma is where that happens (one ulp of sigma is less
+    than one ulp of pow below sigma = 8)."""
+    rng = np.random.default_rng(99)
+    letters = "ACGT"
+    base_word = "ACGTTGCAAC"
+    codec = {}
+    # pairs of barcodes that differ from a common word at one position each
+    words = []
+    for i in range(10):
+        w = list(base_word)
+        w[i] = letters[(letters.index(w[i]) + 1) % 4]
+        words.append("".join(w))
+    for i, w in enumerate(words):
+        codec["@%02d" % i] = {"barcode": [w], "concentration": 1.0}
+    job = {"sample": {"algorithm": "pamld", "transform": {"token": ["0:0:10"]}, "codec": codec, "noise": 0.02, "confidence threshold": 0.05}}
+    n = 6000
+    lut = {c: v for c, v in zip("ACGT", (1, 2, 4, 8))}
+    code = np.tile(np.array([lut[c] for c in base_word], dtype=np.uint8), (n, 1))
+    quality = rng.integers(2, 41, size=(n, 10)).astype(np.uint8)       # every read mismatches each barcode at exactly one position
+    same_quality = rng.random(n) < 0.7
+    quality[same_quality] = quality[same_quality, :1]                  # ... mostly with one quality everywhere: ten way structural ties
+    low = rng.random(n) < 0.5
+    quality[low] = np.minimum(quality[low], 7)
+    batch = O.ReadBatch.from_fixed([code], [quality])
+    state = run_both(job, batch.code, batch.quality, batch.offset)
+    check(*state)
+    assert state[0].statistics()["exact_path_reads"] > n // 2
