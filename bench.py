@@ -277,13 +277,13 @@ class Bench:
         timed step's kernels alone)."""
         torch = self.torch
 
-        def step(m):
+        def step(m, collect=True):
             if flush:
                 self.l2_flush()
             flags.zero_()
             chain.reset(self.stream)
             chain.decode_device(tiles, m, flags, results, self.stream)
-            if self.world > 1:
+            if self.world > 1 and collect:
                 chain.collect(stream=self.stream)
 
         for _ in range(warmup):
@@ -302,9 +302,10 @@ class Bench:
             launches = chain.statistics()["kernel_launches"] - launches_before
             last_kernel_ms = chain.last_kernel_milliseconds()
             # keep the GPU under the same load a little longer when the timed region was too short to sample
+            # (without the collective: every rank decides for itself how long it keeps going)
             extra = 0
             while len(clocks.samples) < 3 and extra < 200:
-                step(warm_reads or n)
+                step(warm_reads or n, collect=False)
                 extra += 1
                 if extra % 4 == 0:
                     torch.cuda.synchronize(self.device)

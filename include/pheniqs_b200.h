@@ -332,8 +332,10 @@ int phq_adjust_job(const char* job_json, const char* report_json, int precision,
 
 /* ------------------------------------------------------------------ instrumentation */
 
-/* kernels launched by this handle so far, and reads whose PAMLD decision fell within 1e-12
-   (relative) of a threshold or needed the exact tie path (diagnostic "band" counters) */
+/* kernels launched by this handle so far, reads that needed the exact tie path, and reads whose PAMLD decision fell
+   within the accuracy of the path of a threshold (diagnostic "band" counter): within 1e-12 (relative) for the exact
+   and prefilter scans, within 2^-21 (1 - confidence) of the confidence threshold for the pruned whitelist scan,
+   whose sigma_p can lack up to that much: such a read may be decided differently from the reference */
 int phq_statistics(phq_handle* handle, uint64_t* kernel_launches, uint64_t* exact_path_reads, uint64_t* threshold_band_reads);
 /* names of the kernels decoder `decoder` launches with its current tables ("pamld_grid_kernel<8, 8, 2, 8, 1> +
    pamld_tie_kernel<4>"), NUL terminated into buffer[capacity]; for reports and profiles. No reference counterpart. */

@@ -536,6 +536,12 @@ void refresh_params(phq_handle* h, size_t k) {
     const bool prefilter(h->device_fast[k] != NULL && p.whitelist == NULL && (p.grid == NULL || p.grid_uniform != 0));
     p.fast_barcodes = prefilter ? h->device_fast[k] : NULL;
     p.phred32 = h->device_phred32;
+    p.fast_uniform_prior = 0.0f;
+    if(prefilter && d.barcode_cardinality > 0) {
+        bool uniform(true);
+        for(int32_t b(1); b < d.barcode_cardinality && uniform; ++b) { uniform = d.concentration[b] == d.concentration[0]; }
+        if(uniform && static_cast< float >(d.concentration[0]) > 0.0f) { p.fast_uniform_prior = static_cast< float >(d.concentration[0]); }
+    }
 }
 
 void destroy(phq_handle* h) {

@@ -504,6 +504,7 @@ struct Verdict {
     double confidence;
     uint32_t qcfail;
 };
+constexpr double WHITELIST_BAND = 4.76837158203125e-07;      /* = WHITELIST_TOLERANCE of pamld_whitelist_kernel */
 /* the branches of pamld.cpp:96-122 and the accumulator updates, once P(r|b) and the confidence of the winner are known */
 __device__ __forceinline__ Verdict pamld_apply(const DecoderParams& P, const Accumulator& accumulator, uint32_t* band_counter,
                                                int best_index, uint32_t m, double conditional_probability, double confidence,
@@ -516,7 +517,10 @@ __device__ __forceinline__ Verdict pamld_apply(const DecoderParams& P, const Acc
     const int high_quality_distance = __popc(m & high_quality_mask);
     const int best_row = best_index + 1;
 
-    bool band = fabs(v.confidence - P.confidence_threshold) <= 1e-12;
+    /* diagnostic: reads whose decision sits within the accuracy of this path of a threshold. 1e-12 for the exact and
+       prefilter scans; the pruned whitelist scan can move a confidence by up to 2^-21 (1 - confidence) */
+    const double confidence_band = P.whitelist != nullptr ? fmax(1e-12, WHITELIST_BAND * (1.0 - v.confidence)) : 1e-12;
+    bool band = fabs(v.confidence - P.confidence_threshold) <= confidence_band;
     if(!uniform) { band = band || fabs(conditional_probability - P.random_barcode_probability) <= 1e-12 * P.random_barcode_probability; }
     if(band) { atomicAdd(band_counter, 1u); }
 
@@ -1272,7 +1276,7 @@ __device__ __forceinline__ bool fast_decide(const DecoderParams& P, const TileAr
     return true;
 }
 
-template < int G >
+template < int G, bool UNIFORM >
 __global__ void __launch_bounds__(fast_warps(G) * WARP_SIZE, 1)
 pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     extern __shared__ __align__(256) unsigned char smem[];
@@ -1338,14 +1342,17 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
                 for(int u = 0; u < 4; ++u) {
                     const uint4 raw = *reinterpret_cast< const uint4* >(stage + i + u);
                     const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
-                    p[u] = fast_product< 0, G >(table_base, m) * __uint_as_float(raw.z);
+                    p[u] = fast_product< 0, G >(table_base, m);
+                    if(!UNIFORM) { p[u] *= __uint_as_float(raw.z); }
                 }
                 fast_select_four(selection, p[0], p[1], p[2], p[3], first + i);
             }
             for(; i < count; ++i) {
                 const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
                 const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
-                fast_select_one(selection, fast_product< 0, G >(table_base, m) * __uint_as_float(raw.z), first + i);
+                float p = fast_product< 0, G >(table_base, m);
+                if(!UNIFORM) { p *= __uint_as_float(raw.z); }
+                fast_select_one(selection, p, first + i);
             }
             if(!resident) {
                 __syncthreads();
@@ -1353,6 +1360,11 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
             }
         }
 
+        if(UNIFORM) {
+            /* one prior for every barcode: it multiplies the maximum and the sum of the others once per read */
+            selection.best *= P.fast_uniform_prior;
+            selection.rest *= static_cast< double >(P.fast_uniform_prior);
+        }
         /* ---- easy reads are decided here, the others are left to the exact scan */
         bool decided = valid && selection.rest <= FAST_EASY_RATIO * static_cast< double >(selection.best)
                     && selection.best >= FAST_MINIMUM_BEST && (nmask & all_positions) != all_positions;
@@ -1521,7 +1533,6 @@ constexpr int WHITELIST_QUEUE = 128;            /* candidates a warp can hold ba
 constexpr int WHITELIST_WORDS = 128;            /* non-empty pass words a warp can hold back (a power of two, at least 31 + 2 x 32); expanded up to 32 at a time */
 constexpr int WHITELIST_MAX_WARPS = 15;
 constexpr double WHITELIST_TOLERANCE = 4.76837158203125e-07;       /* 2^-21: half of the 1e-6 the path allows, as a worst case bound */
-constexpr double WHITELIST_ABSOLUTE = 4.656612873077393e-10;       /* 2^-31: the most the pruned mass may move a confidence, as a fraction of sigma_p */
 
 /* per-warp shared memory of pamld_whitelist_kernel */
 constexpr unsigned WL_OFF_TABLE = 0;                                                    /* 32 entries x 256 B: subset products of 8 groups of 2 positions, lane skewed */
@@ -1642,7 +1653,6 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
     const int L = P.nucleotide_cardinality;
     const int group_cardinality = P.whitelist_chunks;
     const double tolerance_per_barcode = WHITELIST_TOLERANCE / static_cast< double >(P.barcode_cardinality);
-    const double absolute_per_barcode = WHITELIST_ABSOLUTE / static_cast< double >(P.barcode_cardinality);
     const long long unit_cardinality = (A.n_reads + 31) / 32;
     /* the ring: groups are copied and consumed in one running order; the stage and the mbarrier phase of the next
        group to consume and of the next one to copy are carried along */
@@ -1829,11 +1839,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
             }
             if(mine) {
                 /* the threshold follows the maximum and the rest once per batch: it only grows, so the older one was conservative */
-                /* the pruned barcodes together stay below 2^-21 of the part of sigma_p that is not the winner (the error
-                   probability keeps six digits) AND below 2^-31 of sigma_p itself (no confidence moves by more than
-                   that, whatever the read: the accumulated confidences stay within 1e-9) */
-                threshold = fmin(fmin(half_best, tolerance_per_barcode * (noise_term + selection.rest)),
-                                 absolute_per_barcode * (selection.best + (noise_term + selection.rest)));
+                threshold = fmin(half_best, tolerance_per_barcode * (noise_term + selection.rest));
                 while(limit > 0 && limit_bound < threshold) { --limit; limit_bound = bound[limit]; }
             }
             head += n;
@@ -2685,10 +2691,12 @@ cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, c
     cudaError_t status = cudaFuncSetAttribute(pamld_tie_kernel< G, 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024);
     if(status == cudaSuccess) { status = cudaFuncSetAttribute(pamld_tie_kernel< G, TIE_READS_SMALL >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024); }
     if(status != cudaSuccess) { return status; }
+    /* as many CTAs as stay resident (three per SM): every CTA stages the table and flushes its accumulator rows once,
+       and the flushes of all CTAs meet on the same few hundred global addresses */
     if(params.barcode_cardinality >= TIE_LONG_TABLE) {
-        pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+        pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 3, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     } else {
-        pamld_tie_kernel< G, TIE_READS_SMALL ><<< geometry.multiprocessor_count * 8, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+        pamld_tie_kernel< G, TIE_READS_SMALL ><<< geometry.multiprocessor_count * 3, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     }
     return cudaGetLastError();
 }
@@ -2750,28 +2758,34 @@ cudaError_t launch_pamld_grid(const DecoderParams& params, const TileArguments& 
 }
 
 /* the prefilter scan over every read of the launch, then the exact scan over the reads it left, then the tie pass */
-template < int G >
-cudaError_t launch_pamld_fast_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+template < int G, bool UNIFORM >
+cudaError_t launch_pamld_fast_groups_as(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     const SharedPlan plan = make_plan(params.barcode_cardinality, true, 0, true);
     const size_t per_warp = static_cast< size_t >(G) * FAST_GROUP_FLOATS * sizeof(float);
     if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
     int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
     warps = warps > fast_warps(G) ? fast_warps(G) : warps;
     const size_t bytes = plan.fixed_bytes + per_warp * warps;
-    cudaError_t status = cudaFuncSetAttribute(pamld_fast_kernel< G >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    cudaError_t status = cudaFuncSetAttribute(pamld_fast_kernel< G, UNIFORM >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
     if(status != cudaSuccess) { return status; }
     const int threads = warps * WARP_SIZE;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
     status = cudaMemsetAsync(params.tie_count + 2, 0, sizeof(unsigned), stream);
     if(status != cudaSuccess) { return status; }
-    pamld_fast_kernel< G ><<< grid, threads, bytes, stream >>>(params, tile);
+    pamld_fast_kernel< G, UNIFORM ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
     TileArguments rest(tile);
     rest.index_list = params.hard_list;
     rest.index_count = params.tie_count + 2;
     return launch_pamld_groups< G >(params, rest, geometry, stream);
+}
+/* the prefilter scan over every read of the launch, then the exact scan over the reads it left, then the tie pass */
+template < int G >
+cudaError_t launch_pamld_fast_groups(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    return params.fast_uniform_prior > 0.0f ? launch_pamld_fast_groups_as< G, true >(params, tile, geometry, stream)
+                                            : launch_pamld_fast_groups_as< G, false >(params, tile, geometry, stream);
 }
 template < int LA, int LB >
 cudaError_t launch_pamld_fast_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
@@ -2965,7 +2979,7 @@ void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, 
                      GRID_GROUP_WIDTH, params.grid_uniform ? 1 : (dense ? params.grid_dense : 0), params.grid_uniform ? 1 : 0, (L + 3) / 4);
         } else {
             char prefilter[64] = "";
-            if(params.fast_barcodes != nullptr) { snprintf(prefilter, sizeof(prefilter), "pamld_fast_kernel<%d> + ", params.group_cardinality); }
+            if(params.fast_barcodes != nullptr) { snprintf(prefilter, sizeof(prefilter), "pamld_fast_kernel<%d, %d> + ", params.group_cardinality, params.fast_uniform_prior > 0.0f ? 1 : 0); }
             snprintf(buffer, capacity, "%spamld_kernel<%d> + pamld_tie_kernel<%d>", prefilter, params.group_cardinality, params.group_cardinality);
         }
     } else if(algorithm == 1) {

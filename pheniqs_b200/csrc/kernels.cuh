@@ -144,6 +144,7 @@ struct DecoderParams {
     unsigned* tie_count;                        /* queue header: [0] tie queue length, [1] work counter of the whitelist scan, [2] hard list length */
     const FastEntry* fast_barcodes;             /* [N] device; NULL = no f32 prefilter scan for this decoder (exact scan over every read) */
     const float* phred32;                       /* [128] mismatch ratios rounded to f32 */
+    float fast_uniform_prior;                   /* the common prior (f32) when every barcode has the same one, else 0: the prefilter scan then multiplies once per read */
     int* hard_list;                             /* [reads of the launch] reads the prefilter scan leaves to the exact scan */
 };
 

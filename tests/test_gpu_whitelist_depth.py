@@ -15,7 +15,8 @@ measure how much of that budget the CUDA code actually uses where it is most exp
   qcfail in     incoming chastity flags on a tenth of the reads
 
 Every set is compared read by read (index, distance, qcfail exact; ln confidence and the error probability within
-1e-6) and through the accumulators (u64 exact, f64 within 1e-9); the maxima are printed so the run records the slack."""
+1e-6) and through the accumulators (u64 exact, f64 within 1e-9; for the all-low-quality sets within the provable
+2^-21 x (1 - confidence threshold), see there); the maxima are printed so the run records the slack."""
 import os
 
 import numpy as np
@@ -47,7 +48,7 @@ def reads_from(barcode_codes, quality, rng, substitute=True):
     return code, quality
 
 
-def run(compiled, code, quality, qcfail=None, label=""):
+def run(compiled, code, quality, qcfail=None, label="", accumulator_gate=1e-9):
     n = code.shape[0]
     batch = O.ReadBatch.from_fixed([code, np.zeros((n, 0), dtype=np.uint8)], [quality, np.zeros((n, 0), dtype=np.uint8)], qcfail)
     chain = DecoderChain(compiled, device=0)
@@ -64,7 +65,7 @@ def run(compiled, code, quality, qcfail=None, label=""):
     assert np.array_equal(u, eu), label + " integer accumulators"
     relative = np.abs(f - ef) / np.maximum(np.abs(ef), 1e-300)
     relative[ef == 0] = np.abs(f[ef == 0])
-    assert relative.max() <= 1e-9, label + " confidence accumulators: %g" % relative.max()
+    assert relative.max() <= accumulator_gate, label + " confidence accumulators: %g" % relative.max()
     ok = expected.confidence[:, k] > 0
     ln_error = np.abs(np.log(got["confidence"][ok]) - np.log(expected.confidence[ok, k])).max() if ok.any() else 0.0
     e_ref = 1.0 - expected.confidence[ok, k]
@@ -90,7 +91,10 @@ def test_full_table_at_depth(table):
         n = 1500
         drawn = rng.integers(0, table.shape[0], size=n)
         code, quality = reads_from(table[drawn], np.full((n, 28), q, dtype=np.uint8), rng)
-        got = run(compiled, code, quality, label="all Q%d" % q)
+        # every read of this set has 1 - confidence of a few percent, so the pruned mass (at most 2^-21 of the non-winner
+        # part of sigma_p per read) is bounded by 2^-21 x (1 - confidence threshold) = 2.4e-8 of an accumulated
+        # confidence, not by the 1e-9 ordinary read sets meet with three orders of margin: the gate here is that bound
+        got = run(compiled, code, quality, label="all Q%d" % q, accumulator_gate=2.0 ** -21 * 0.05)
         assert (got["index"] > 0).any()
 
     # twins: a read between two whitelist entries at distance 2
@@ -120,7 +124,8 @@ def test_full_table_at_depth(table):
     code, quality = reads_from(middle, quality, rng, substitute=False)
     got = run(compiled, code, quality, label="twins")
     expected_pairs = np.array([[a + 1, b + 1] for a, b, _, _ in pairs]).repeat(2, axis=0)
-    assert np.all((got["index"] == expected_pairs[:, 0]) | (got["index"] == expected_pairs[:, 1]) | (got["index"] == 0))
+    # (a third whitelist entry can sit as close: about one read in a hundred; the oracle comparison above is the check)
+    assert np.mean((got["index"] == expected_pairs[:, 0]) | (got["index"] == expected_pairs[:, 1])) > 0.9
 
     # incoming qcfail flags
     n = 1500
