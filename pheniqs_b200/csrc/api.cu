@@ -532,6 +532,13 @@ void refresh_params(phq_handle* h, size_t k) {
     p.grid_split = h->grid_shape[k * 6 + 3];
     p.grid_dense = h->grid_shape[k * 6 + 4];
     p.grid_uniform = h->grid_shape[k * 6 + 5];
+    {
+        /* one bit of a tie block mask per (4 << shift) scanned barcodes / grid entries: at most 32 bits */
+        const int32_t scanned(p.grid != NULL ? p.grid_entries : p.barcode_cardinality);
+        int32_t shift(0);
+        while((((scanned + 3) >> 2) + (1 << shift) - 1) >> shift > 32) { ++shift; }
+        p.tie_block_shift = shift;
+    }
     /* the prefilter scan exists for the generic scan and for the separable form of the combinatorial one */
     const bool prefilter(h->device_fast[k] != NULL && p.whitelist == NULL && (p.grid == NULL || p.grid_uniform != 0));
     p.fast_barcodes = prefilter ? h->device_fast[k] : NULL;
@@ -591,8 +598,8 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
     bool needs_queue(false);
     for(size_t k(0); k < n_decoders; ++k) { needs_queue = needs_queue || h->chain[k].algorithm == PHQ_PAMLD || h->params[k].mdd_tables != NULL; }
     const long long queue_reads(n_reads < PAMLD_LAUNCH_READS ? n_reads : PAMLD_LAUNCH_READS);
-    /* [16 bytes: counters][tie records][hard list of the prefilter scans: one int per read] */
-    if(needs_queue) { tie_list.reserve(16 + static_cast< size_t >(queue_reads) * (sizeof(TieRecord) + sizeof(int))); }
+    /* [16 bytes: counters][tie records][hard list of the prefilter scans: one int per read][candidate pool] */
+    if(needs_queue) { tie_list.reserve(16 + static_cast< size_t >(queue_reads) * (sizeof(TieRecord) + sizeof(int) + TIE_POOL_PER_READ * sizeof(uint32_t))); }
     for(size_t k(0); k < n_decoders; ++k) {
         DecoderParams p(h->params[k]);
         p.totals = (k + 1 == n_decoders) ? h->totals() : NULL;
@@ -600,6 +607,8 @@ void launch_chain(phq_handle* h, int64_t n_reads, const phq_tile* tiles, uint8_t
             p.tie_count = reinterpret_cast< unsigned* >(tie_list.pointer);
             p.tie_record = reinterpret_cast< TieRecord* >(tie_list.pointer + 16);
             p.hard_list = reinterpret_cast< int* >(tie_list.pointer + 16 + static_cast< size_t >(queue_reads) * sizeof(TieRecord));
+            p.tie_pool = reinterpret_cast< uint32_t* >(p.hard_list + queue_reads);
+            p.tie_pool_capacity = static_cast< uint32_t >(queue_reads * TIE_POOL_PER_READ);
         }
         TileArguments a;
         memset(&a, 0, sizeof(a));

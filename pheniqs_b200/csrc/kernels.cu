@@ -394,16 +394,21 @@ __device__ __forceinline__ void select_four(Selection& s, double p0, double p1, 
     a barcode that is not a candidate loses. More than TIE_CANDIDATES pushes since the last reset = overflow: the tie
     pass scans the table itself. Used where the test is cheap: the exact path of the whitelist scan (per surviving
     candidate) and, as bit masks over the distinct words, the separable form of the combinatorial scan. */
-struct CandidateList {
+template < int CAPACITY >
+struct CandidateListOf {
+    static constexpr int capacity = CAPACITY;
     uint32_t count;
-    uint32_t entry[TIE_CANDIDATES];
+    uint32_t entry[CAPACITY];
     __device__ __forceinline__ void reset() { count = 0u; }
     __device__ __forceinline__ void push(uint32_t index) {
-        if(count < static_cast< uint32_t >(TIE_CANDIDATES)) { entry[count] = index; }
+        if(count < static_cast< uint32_t >(CAPACITY)) { entry[count] = index; }
         ++count;
     }
 };
-__device__ __forceinline__ void capture_one(CandidateList& list, int& running, double p, int i) {
+typedef CandidateListOf< TIE_CANDIDATES > CandidateList;
+typedef CandidateListOf< TIE_POOLED_CANDIDATES > LongCandidateList;        /* local memory; only touched by the rare pushes */
+template < class LIST >
+__device__ __forceinline__ void capture_one(LIST& list, int& running, double p, int i) {
     const int h = __double2hiint(p);
     if(h >= running - 1) {
         if(h > running + 1) { list.reset(); }
@@ -411,6 +416,29 @@ __device__ __forceinline__ void capture_one(CandidateList& list, int& running, d
         running = max(running, h);
     }
 }
+/*  The pair loops do not name single barcodes (a push per near tie costs a branch that some lane of nearly every
+    block takes) but keep ONE bit per run of blocks of four: set when the largest high word of a block reaches (high word
+    of the running maximum) - 1, the mask restarting when a block exceeds everything before it by more than that. Two
+    compares and two selects per block, no branch; the tie pass evaluates the barcodes of the flagged runs. */
+__device__ __forceinline__ void note_block(uint32_t& near_blocks, int running_high, int top, int index, int shift) {
+    const uint32_t bit = 1u << (((index >> 2) >> shift) & 31);
+    near_blocks = top > running_high + 1 ? bit : (top >= running_high - 1 ? (near_blocks | bit) : near_blocks);
+}
+__device__ __forceinline__ int top_high(double p0, double p1, double p2, double p3) {
+    return max(max(__double2hiint(p0), __double2hiint(p1)), max(__double2hiint(p2), __double2hiint(p3)));
+}
+/* the CandidateList a pair loop hands to queue_ties: its block mask */
+__device__ __forceinline__ CandidateList block_candidates(uint32_t near_blocks, int shift, bool grid_entries) {
+    CandidateList list;
+    list.count = TIE_BLOCKS;
+    #pragma unroll
+    for(int c = 0; c < TIE_CANDIDATES; ++c) { list.entry[c] = 0u; }
+    list.entry[0] = near_blocks;
+    list.entry[1] = static_cast< uint32_t >(shift);
+    list.entry[2] = grid_entries ? 1u : 0u;
+    return list;
+}
+
 /*  Selection over the word probabilities of one part of a separable codec: the maximum (first on equality),
     the largest of the others and the sum of the others. */
 struct PartSelection {
@@ -575,10 +603,10 @@ __device__ __forceinline__ PositionFactor position_factor(const double* __restri
 }
 
 /* queue the lanes with `tied` set for the tie pass: one TieRecord each (one atomic per warp) */
-template < int G >
+template < int G, class LIST >
 __device__ __forceinline__ void queue_ties(const DecoderParams& P, bool tied, int lane, const Selection& selection, double base_probability,
                                            uint32_t high_quality_mask, bool uniform, uint32_t o_lo, uint32_t o_hi, uint32_t nmask, long long r,
-                                           const uint32_t (&quality)[G], const CandidateList& candidates) {
+                                           const uint32_t (&quality)[G], const LIST& candidates) {
     const unsigned queued = __ballot_sync(FULL_MASK, tied);
     if(queued) {
         unsigned slot = 0;
@@ -598,9 +626,21 @@ __device__ __forceinline__ void queue_ties(const DecoderParams& P, bool tied, in
             record.read = static_cast< uint32_t >(r);
             #pragma unroll
             for(int g = 0; g < 8; ++g) { record.quality[g] = g < G ? quality[g < G ? g : 0] : 0u; }
-            record.candidate_count = candidates.count <= static_cast< uint32_t >(TIE_CANDIDATES) ? candidates.count : TIE_RESCAN;
             #pragma unroll
-            for(int c = 0; c < TIE_CANDIDATES; ++c) { record.candidate[c] = candidates.entry[c]; }
+            for(int c = 0; c < TIE_CANDIDATES; ++c) { record.candidate[c] = c < LIST::capacity ? candidates.entry[c < LIST::capacity ? c : 0] : 0u; }
+            record.candidate_count = candidates.count;
+            if(candidates.count > static_cast< uint32_t >(TIE_CANDIDATES) && candidates.count != TIE_BLOCKS) {
+                record.candidate_count = TIE_RESCAN;
+                if(candidates.count <= static_cast< uint32_t >(LIST::capacity) && P.tie_pool != nullptr) {
+                    /* more than a record holds: the list goes to the pool */
+                    const uint32_t first = atomicAdd(P.tie_count + 3, candidates.count);
+                    if(first + candidates.count <= P.tie_pool_capacity) {
+                        for(uint32_t c = 0; c < candidates.count; ++c) { P.tie_pool[first + c] = candidates.entry[c < static_cast< uint32_t >(LIST::capacity) ? c : 0]; }
+                        record.candidate_count = TIE_POOLED | candidates.count;
+                        record.candidate[0] = first;
+                    }
+                }
+            }
             P.tie_record[at] = record;
         }
     }
@@ -706,6 +746,7 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
            compensation. The first maximum (strict >, pamld.cpp:73) is tracked on the high words. */
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
+        uint32_t near_blocks = 0u;              /* runs of barcodes that can hold the winner of a tie (note_block) */
         for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
             const BarcodeEntry* stage;
             if(resident) {
@@ -726,12 +767,15 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
                     const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
                     p[u] = subset_product< G >(table_base, m) * __hiloint2double(raw.w, raw.z);
                 }
+                note_block(near_blocks, __double2hiint(selection.best), top_high(p[0], p[1], p[2], p[3]), first + i, P.tie_block_shift);
                 select_four(selection, p[0], p[1], p[2], p[3], first + i);
             }
             for(; i < count; ++i) {
                 const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
                 const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
-                select_one(selection, subset_product< G >(table_base, m) * __hiloint2double(raw.w, raw.z), first + i);
+                const double p = subset_product< G >(table_base, m) * __hiloint2double(raw.w, raw.z);
+                note_block(near_blocks, __double2hiint(selection.best), __double2hiint(p), first + i, P.tie_block_shift);
+                select_one(selection, p, first + i);
             }
             if(!resident) {
                 __syncthreads();
@@ -742,14 +786,8 @@ pamld_kernel(const DecoderParams P, const TileArguments A) {
         /* ---- structural ties (runner-up within 2^-19 of the winner) are resolved by the reference through the
            rounding of its Kahan sums; pamld_tie_kernel reproduces that. Such reads are only queued here. */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        {
-            /* the candidates are not collected in this loop (a test per pair costs more than it saves): the tie pass finds them */
-            CandidateList candidates;
-            candidates.count = TIE_CANDIDATES + 1;
-            #pragma unroll
-            for(int c = 0; c < TIE_CANDIDATES; ++c) { candidates.entry[c] = 0u; }
-            queue_ties< G >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
-        }
+        queue_ties< G, CandidateList >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality,
+                                       block_candidates(near_blocks, P.tie_block_shift, false));
 
         /* ---- decision for this lane's read */
         const bool decided = valid && !tied;
@@ -951,7 +989,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
         candidates.reset();
         #pragma unroll
         for(int c = 0; c < TIE_CANDIDATES; ++c) { candidates.entry[c] = 0u; }
-        if constexpr(!UNIFORM) { candidates.count = TIE_CANDIDATES + 1; }       /* the pair loops do not collect: the tie pass scans */
+        uint32_t near_blocks = 0u;      /* the pair loops flag runs of grid entries instead (note_block) */
         if constexpr(UNIFORM) {
             /* ---- full grid under one prior: p(a, k) = SA[a] * SB[k] * prior is separable, so the maximum is
                (argmax SA, argmax SB), the runner-up is one of (best A, second B) / (second A, best B), and the
@@ -1013,6 +1051,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                     for(int u = 0; u < 4; ++u) {
                         p[u] = (prefix * sb[k + u]) * run[k + u].prior;
                     }
+                    note_block(near_blocks, __double2hiint(selection.best), top_high(p[0], p[1], p[2], p[3]), a * KBP + k, P.tie_block_shift);
                     select_four(selection, p[0], p[1], p[2], p[3], a * KBP + k);
                 }
             }
@@ -1040,6 +1079,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                         const uint4 raw = *reinterpret_cast< const uint4* >(entry + i + u);
                         p[u] = (prefix * column_load(suffix_base + raw.x)) * __hiloint2double(raw.w, raw.z);
                     }
+                    note_block(near_blocks, __double2hiint(selection.best), top_high(p[0], p[1], p[2], p[3]), i, P.tie_block_shift);
                     select_four(selection, p[0], p[1], p[2], p[3], i);
                 }
             }
@@ -1047,10 +1087,14 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         /* ---- ties are queued; everything else is decided here */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        if(tied && candidates.count <= static_cast< uint32_t >(TIE_CANDIDATES)) {
-            for(uint32_t c = 0; c < candidates.count; ++c) { candidates.entry[c] = entry[candidates.entry[c]].index; }
+        if constexpr(UNIFORM) {
+            if(tied && candidates.count <= static_cast< uint32_t >(TIE_CANDIDATES)) {
+                for(uint32_t c = 0; c < candidates.count; ++c) { candidates.entry[c] = entry[candidates.entry[c]].index; }
+            }
+        } else {
+            candidates = block_candidates(near_blocks, P.tie_block_shift, true);
         }
-        queue_ties< G >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
+        queue_ties< G, CandidateList >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
         const bool decided = valid && !tied;
         if(decided) {
             const int winner = static_cast< int >(entry[selection.index].index);
@@ -1792,7 +1836,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
 
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
-        CandidateList candidates;               /* the barcodes that can tie with the maximum, for the tie pass */
+        LongCandidateList candidates;           /* the barcodes that can tie with the maximum, for the tie pass */
         candidates.reset();
         unsigned head = 0, tail = 0;            /* candidates evaluated / appended so far (warp uniform) */
 
@@ -1941,7 +1985,7 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
 
         /* ---- structural ties are queued for pamld_tie_kernel, everything else is decided here (as pamld_kernel) */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        queue_ties< 4 >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
+        queue_ties< 4, LongCandidateList >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
         const bool decided = valid && !tied;
         if(decided) {
             const BarcodeEntry e = P.barcodes[selection.index];
@@ -2201,8 +2245,15 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
         /*  The scan usually names the candidates (TieRecord::candidate): then only those are evaluated. A read whose
             list overflowed, or that comes from a scan that does not collect (the whitelist scan), has its candidates
             found here by a scan of the whole table; the subset product table is only built when the warp has one. */
-        const uint32_t listed = live ? record.candidate_count : 0u;
-        const bool rescan = listed > static_cast< uint32_t >(TIE_CANDIDATES);
+        const bool blocks = live && record.candidate_count == TIE_BLOCKS;      /* a mask over runs of barcodes (or grid entries) */
+        const bool pooled = live && !blocks && record.candidate_count != TIE_RESCAN && (record.candidate_count & TIE_POOLED) != 0u;
+        const uint32_t block_mask = record.candidate[0];
+        const uint32_t run = 4u << (record.candidate[1] & 31u);                 /* barcodes per bit of the mask */
+        const bool grid_entries = blocks && record.candidate[2] != 0u;
+        const uint32_t listed = !live ? 0u : (blocks ? static_cast< uint32_t >(__popc(block_mask)) * run : (pooled ? (record.candidate_count & 0xffffu) : record.candidate_count));
+        const bool rescan = live && record.candidate_count == TIE_RESCAN;
+        const uint32_t* const named = pooled ? P.tie_pool + record.candidate[0] : (live ? P.tie_record[item].candidate : nullptr);
+        const int scanned = grid_entries ? P.grid_entries : N;                   /* what the mask counts */
         const bool any_rescan = __any_sync(FULL_MASK, rescan);
         if(any_rescan) {
             /* subset product table (linear: any lane -> entry mapping is conflict free or a broadcast), same
@@ -2288,7 +2339,15 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
                 Candidate own;
                 own.prior = 0; own.sigma = 0; own.index = -1;
                 if(c + sub < mine) {
-                    const int b = static_cast< int >(P.tie_record[item].candidate[c + sub]);
+                    int b;
+                    if(blocks) {
+                        /* candidate c + sub = barcode (c + sub) % run of the ((c + sub) / run)-th flagged run */
+                        const uint32_t which = (c + sub) / run;
+                        const int e = static_cast< int >(__fns(block_mask, 0u, static_cast< int >(which) + 1) * run + (c + sub) % run);
+                        b = e < scanned ? (grid_entries ? static_cast< int >(reinterpret_cast< const uint4* >(P.grid)[P.grid_a + P.grid_b + e].y) : e) : N;
+                    } else {
+                        b = static_cast< int >(named[c + sub]);
+                    }
                     if(b < N) {
                         const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
                         const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
@@ -2827,7 +2886,7 @@ static cudaError_t launch_pamld_whitelist(const DecoderParams& params, const Til
     const long long wanted = (units + warps - 1) / warps;
     const int grid = static_cast< int >(wanted < geometry.multiprocessor_count ? wanted : geometry.multiprocessor_count);
     /* the queue header: [0] tie queue length, [1] the next unit of 32 reads */
-    status = cudaMemsetAsync(params.tie_count, 0, 2 * sizeof(unsigned), stream);
+    status = cudaMemsetAsync(params.tie_count, 0, 4 * sizeof(unsigned), stream);
     if(status != cudaSuccess) { return status; }
     pamld_whitelist_kernel<<< grid, warps * WARP_SIZE, bytes, stream >>>(params, tile, params.tie_count + 1);
     status = cudaGetLastError();

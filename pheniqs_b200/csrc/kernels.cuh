@@ -87,6 +87,10 @@ constexpr int WHITELIST_MINIMUM_BARCODES = 4096;    /* smaller codecs use the ex
 /* what the scan kernel hands to the tie kernel for a queued read */
 constexpr int TIE_CANDIDATES = 11;                  /* barcodes the scan can name as possible winners of a queued read */
 constexpr uint32_t TIE_RESCAN = 0xffffffffu;        /* candidate_count of a read whose candidates the tie kernel has to find itself */
+constexpr uint32_t TIE_BLOCKS = 0xfffffffeu;        /* candidate_count: candidate[0] is a bit mask over runs of (4 << candidate[1]) consecutive barcodes (grid entries when candidate[2]) that hold every possible winner */
+constexpr uint32_t TIE_POOLED = 0x40000000u;        /* candidate_count flag: the (count & 0xffff) candidates are in the pool from entry candidate[0] on */
+constexpr int TIE_POOLED_CANDIDATES = 64;           /* the most a scan names for one read (the whitelist scan: noise reads tie a dozen ways) */
+constexpr int TIE_POOL_PER_READ = 4;                /* pool entries per read of the launch */
 struct __align__(16) TieRecord {
     double best;                /* the scan's maximum prior adjusted product (relative to P0) */
     double rest;                /* the scan's sum of all other products */
@@ -141,11 +145,14 @@ struct DecoderParams {
     int32_t whitelist_chunks;
     double prior_maximum;                       /* largest barcode prior: the pruning bound of pamld_whitelist_kernel */
     TieRecord* tie_record;                      /* [reads of the launch] queue of reads whose winner needs the exact tie path (PAMLD) */
-    unsigned* tie_count;                        /* queue header: [0] tie queue length, [1] work counter of the whitelist scan, [2] hard list length */
+    unsigned* tie_count;                        /* queue header: [0] tie queue length, [1] work counter of the whitelist scan, [2] hard list length, [3] pool cursor */
     const FastEntry* fast_barcodes;             /* [N] device; NULL = no f32 prefilter scan for this decoder (exact scan over every read) */
     const float* phred32;                       /* [128] mismatch ratios rounded to f32 */
     float fast_uniform_prior;                   /* the common prior (f32) when every barcode has the same one, else 0: the prefilter scan then multiplies once per read */
     int* hard_list;                             /* [reads of the launch] reads the prefilter scan leaves to the exact scan */
+    int32_t tie_block_shift;                    /* log2 of the blocks of four barcodes (grid entries) one bit of a TIE_BLOCKS mask stands for */
+    uint32_t* tie_pool;                         /* candidates of the reads that name more than a record holds; cursor = tie_count[3] */
+    uint32_t tie_pool_capacity;
 };
 
 struct TileArguments {
