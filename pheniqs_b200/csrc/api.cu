@@ -540,7 +540,8 @@ void refresh_params(phq_handle* h, size_t k) {
         p.tie_block_shift = shift;
     }
     /* the prefilter scan exists for the generic scan and for the separable form of the combinatorial one */
-    const bool prefilter(h->device_fast[k] != NULL && p.whitelist == NULL && (p.grid == NULL || p.grid_uniform != 0));
+    const bool dense_shape((p.grid_split == 8 && p.nucleotide_cardinality == 16) || (p.grid_split == 10 && p.nucleotide_cardinality == 20));
+    const bool prefilter(h->device_fast[k] != NULL && p.whitelist == NULL && (p.grid == NULL || p.grid_uniform != 0 || (p.grid_dense != 0 && dense_shape)));
     p.fast_barcodes = prefilter ? h->device_fast[k] : NULL;
     p.phred32 = h->device_phred32;
     p.fast_uniform_prior = 0.0f;

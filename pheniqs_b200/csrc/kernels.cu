@@ -45,7 +45,7 @@ struct SharedPlan {
     int stage_capacity;         /* entries per stage buffer */
     int stage_buffers;          /* 1 when the whole table fits one chunk, else 2 */
     int accumulator_rows;       /* N + 1 when accumulators are staged in shared memory, else 0 */
-    unsigned off_stage, off_phred, off_ratio32, off_acc_f64, off_acc_u32, off_misc, off_mbarrier, off_tables;
+    unsigned off_stage, off_phred, off_ratio32, off_hard, off_acc_f64, off_acc_u32, off_misc, off_mbarrier, off_tables;
     unsigned fixed_bytes;       /* everything except the per-warp tables */
 };
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
@@ -62,6 +62,7 @@ __host__ __device__ inline SharedPlan make_plan(int barcode_cardinality, bool ph
     p.off_stage = at;       at += align_up(unsigned(p.stage_capacity) * unsigned(p.stage_buffers) * 16u, 128u);
     p.off_phred = at;       at += phred_tables ? 256u * 8u : 0u;
     p.off_ratio32 = at;     at += ratio32 ? 512u * 16u : 0u;     /* position table of the prefilter scans (PositionEntry) */
+    p.off_hard = at;        at += ratio32 ? 32u * 256u : 0u;     /* per-warp staging of the hard list (HardList): 64 reads per warp */
     p.off_acc_f64 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_F64_COLUMNS * 8u, 16u);
     p.off_acc_u32 = at;     at += align_up(unsigned(p.accumulator_rows) * ACC_U64_COLUMNS * 4u, 16u);
     p.off_misc = at;        at += 16u;          /* totals count, pf_count; diagnostics exact, band */
@@ -1283,16 +1284,42 @@ __device__ __forceinline__ void fast_select_four(FastSelection& s, float p0, flo
     s.rest += static_cast< double >(((la + lb) + lc) + low);
 }
 
-/* append the lanes with `flag` set to a device list (one atomic per warp) */
-__device__ __forceinline__ void append_reads(bool flag, long long r, int* list, unsigned* count, int lane) {
-    const unsigned lanes = __ballot_sync(FULL_MASK, flag);
-    if(lanes) {
-        unsigned slot = 0;
-        if(lane == 0) { slot = atomicAdd(count, static_cast< unsigned >(__popc(lanes))); }
-        slot = __shfl_sync(FULL_MASK, slot, 0);
-        if(flag) { list[slot + __popc(lanes & ((1u << lane) - 1u))] = static_cast< int >(r); }
+/*  The hard list of a prefilter scan. Every tile leaves a few reads per warp (about 7 % of them); appending those with
+    one global atomic per warp and tile means half a million atomics per launch on ONE address and a round trip to L2
+    in every tile. So each warp stages its hard reads in 256 bytes of shared memory and moves them out 32 at a time:
+    one atomic and one full 128-byte line per 32 reads. */
+struct HardList {
+    int* staged;            /* this warp's 64 slots in shared memory */
+    unsigned held;          /* slots in use (warp uniform) */
+    int* list;
+    unsigned* count;
+    __device__ __forceinline__ void append(bool flag, long long r, int lane) {
+        const unsigned lanes = __ballot_sync(FULL_MASK, flag);
+        if(lanes == 0u) { return; }
+        if(flag) { staged[held + __popc(lanes & ((1u << lane) - 1u))] = static_cast< int >(r); }
+        held += static_cast< unsigned >(__popc(lanes));
+        __syncwarp();
+        if(held >= 32u) {
+            unsigned first = 0;
+            if(lane == 0) { first = atomicAdd(count, 32u); }
+            first = __shfl_sync(FULL_MASK, first, 0);
+            list[first + lane] = staged[lane];
+            const int moved = (static_cast< unsigned >(lane) + 32u < held) ? staged[32 + lane] : 0;
+            __syncwarp();
+            staged[lane] = moved;
+            held -= 32u;
+            __syncwarp();
+        }
     }
-}
+    __device__ __forceinline__ void flush(int lane) {
+        if(held == 0u) { return; }
+        unsigned first = 0;
+        if(lane == 0) { first = atomicAdd(count, held); }
+        first = __shfl_sync(FULL_MASK, first, 0);
+        if(static_cast< unsigned >(lane) < held) { list[first + lane] = staged[lane]; }
+        held = 0u;
+    }
+};
 
 /*  What both prefilter scans do once the winner of an easy read is known: the exact f64 evaluation of the winner, the
     guard around the confidence threshold, then the decision and the stores. Returns false when the read turns out
@@ -1336,7 +1363,11 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     const uint32_t table_base = shared_address(table);
     const int L = P.nucleotide_cardinality;
     const uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
-    unsigned* const hard_count = P.tie_count + 2;
+    HardList hard;
+    hard.staged = reinterpret_cast< int* >(smem + S.plan.off_hard) + warp * 64;
+    hard.held = 0u;
+    hard.list = P.hard_list;
+    hard.count = P.tie_count + 2;
 
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
     const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -1415,7 +1446,7 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
         if(decided) {
             decided = fast_decide< G, 4 * G >(P, A, S, r, selection.index, o_lo, o_hi, nmask, quality, selection.rest, base_probability, qcfail);
         }
-        append_reads(valid && !decided, r, P.hard_list, hard_count, lane);
+        hard.append(valid && !decided, r, lane);
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, decided);
             const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
@@ -1426,6 +1457,7 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
         }
         __syncwarp();
     }
+    hard.flush(lane);
     block_epilogue(S, P);
 }
 
@@ -1444,9 +1476,11 @@ __device__ __forceinline__ void fast_select_part(FastPart& s, float value, int i
     s.rest += static_cast< double >(low);
 }
 constexpr int FAST_GRID_WARPS = 24;
+/* the dense form keeps the B word products in registers: fewer warps, no spills */
+__host__ __device__ constexpr int fast_grid_warps(int KBP) { return KBP > 0 ? 20 : FAST_GRID_WARPS; }
 
-template < int LA, int LB >
-__global__ void __launch_bounds__(FAST_GRID_WARPS * WARP_SIZE, 1)
+template < int LA, int LB, int KBP >
+__global__ void __launch_bounds__(fast_grid_warps(KBP) * WARP_SIZE, 1)
 pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
     constexpr int L = LA + LB;
     constexpr int G = (L + 3) / 4;
@@ -1476,8 +1510,18 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
     float* const table = reinterpret_cast< float* >(smem + aligned_tables) + static_cast< size_t >(warp) * ((GA + GB) * FAST_GROUP_FLOATS) + lane;
     const uint32_t table_base = shared_address(table);
     constexpr uint32_t all_positions = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
-    unsigned* const hard_count = P.tie_count + 2;
+    HardList hard;
+    hard.staged = reinterpret_cast< int* >(smem + S.plan.off_hard) + warp * 64;
+    hard.held = 0u;
+    hard.list = P.hard_list;
+    hard.count = P.tie_count + 2;
     const float prior32 = static_cast< float >(entry[0].prior);
+    /* dense form: the priors of the grid entries in f32, behind the per-warp tables */
+    float* const dense_prior = reinterpret_cast< float* >(smem + aligned_tables + static_cast< size_t >(blockDim.x >> 5) * ((GA + GB) * FAST_GROUP_FLOATS * sizeof(float)));
+    if(KBP > 0) {
+        for(int i = tid; i < P.grid_entries; i += blockDim.x) { dense_prior[i] = static_cast< float >(entry[i].prior); }
+        __syncthreads();
+    }
 
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
     ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
@@ -1501,31 +1545,63 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         const uint32_t a_lo = o_lo & MASK_A, a_hi = o_hi & MASK_A, a_n = nmask & MASK_A;
         const uint32_t b_lo = (o_lo >> LA) & MASK_B, b_hi = (o_hi >> LA) & MASK_B, b_n = (nmask >> LA) & MASK_B;
-        FastPart part_b;
-        part_b.best = 0.0f; part_b.index = 0; part_b.rest = 0.0;
-        #pragma unroll 4
-        for(int k = 0; k < KB; ++k) {
-            const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
-            const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
-            fast_select_part(part_b, fast_product< GA, GB >(table_base, m), k);
+        float best;
+        double others;
+        int winner_entry;
+        if constexpr(KBP == 0) {
+            /* separable: the full grid under one prior */
+            FastPart part_b;
+            part_b.best = 0.0f; part_b.index = 0; part_b.rest = 0.0;
+            #pragma unroll 4
+            for(int k = 0; k < KB; ++k) {
+                const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+                const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+                fast_select_part(part_b, fast_product< GA, GB >(table_base, m), k);
+            }
+            FastPart part_a;
+            part_a.best = 0.0f; part_a.index = 0; part_a.rest = 0.0;
+            #pragma unroll 4
+            for(int a = 0; a < KA; ++a) {
+                const uint2 h = *reinterpret_cast< const uint2* >(header + a);
+                const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+                fast_select_part(part_a, fast_product< 0, GA >(table_base, m), a);
+            }
+            best = (part_a.best * part_b.best) * prior32;
+            others = (static_cast< double >(part_a.best) * part_b.rest + part_a.rest * (static_cast< double >(part_b.best) + part_b.rest)) * static_cast< double >(prior32);
+            winner_entry = part_a.index * KB + part_b.index;
+        } else {
+            /* dense: any priors (after prior estimation), holes in the grid as prior 0. The B word products stay in
+               registers; a pair costs one FMUL by the A word product, one by its f32 prior and the selection step */
+            float sb[KBP];
+            #pragma unroll
+            for(int k = 0; k < KBP; ++k) {
+                const uint2 raw = *reinterpret_cast< const uint2* >(word + k);
+                const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
+                sb[k] = fast_product< GA, GB >(table_base, m);
+            }
+            FastSelection selection;
+            selection.best = 0.0f; selection.index = 0; selection.rest = 0.0;
+            for(int a = 0; a < KA; ++a) {
+                const uint2 h = *reinterpret_cast< const uint2* >(header + a);
+                const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
+                const float sa = fast_product< 0, GA >(table_base, m);
+                #pragma unroll
+                for(int k = 0; k < KBP; k += 4) {
+                    const float4 prior = *reinterpret_cast< const float4* >(dense_prior + a * KBP + k);
+                    fast_select_four(selection, (sa * sb[k]) * prior.x, (sa * sb[k + 1]) * prior.y, (sa * sb[k + 2]) * prior.z, (sa * sb[k + 3]) * prior.w, a * KBP + k);
+                }
+            }
+            best = selection.best;
+            others = selection.rest;
+            winner_entry = selection.index;
         }
-        FastPart part_a;
-        part_a.best = 0.0f; part_a.index = 0; part_a.rest = 0.0;
-        #pragma unroll 4
-        for(int a = 0; a < KA; ++a) {
-            const uint2 h = *reinterpret_cast< const uint2* >(header + a);
-            const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
-            fast_select_part(part_a, fast_product< 0, GA >(table_base, m), a);
-        }
-        const float best = (part_a.best * part_b.best) * prior32;
-        const double others = (static_cast< double >(part_a.best) * part_b.rest + part_a.rest * (static_cast< double >(part_b.best) + part_b.rest)) * static_cast< double >(prior32);
 
         bool decided = valid && others <= FAST_EASY_RATIO * static_cast< double >(best) && best >= FAST_MINIMUM_BEST && (nmask & all_positions) != all_positions;
         if(decided) {
-            const int winner = static_cast< int >(entry[part_a.index * KB + part_b.index].index);
+            const int winner = static_cast< int >(entry[winner_entry].index);
             decided = fast_decide< G, L >(P, A, S, r, winner, o_lo, o_hi, nmask, quality, others, base_probability, qcfail);
         }
-        append_reads(valid && !decided, r, P.hard_list, hard_count, lane);
+        hard.append(valid && !decided, r, lane);
         if(P.totals != nullptr) {
             const unsigned live = __ballot_sync(FULL_MASK, decided);
             const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
@@ -1536,6 +1612,7 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
         }
         __syncwarp();
     }
+    hard.flush(lane);
     block_epilogue(S, P);
 }
 
@@ -2846,30 +2923,40 @@ cudaError_t launch_pamld_fast_groups(const DecoderParams& params, const TileArgu
     return params.fast_uniform_prior > 0.0f ? launch_pamld_fast_groups_as< G, true >(params, tile, geometry, stream)
                                             : launch_pamld_fast_groups_as< G, false >(params, tile, geometry, stream);
 }
-template < int LA, int LB >
-cudaError_t launch_pamld_fast_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+template < int LA, int LB, int KBP >
+cudaError_t launch_pamld_fast_grid_as(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
     constexpr int GROUPS = (LA + 3) / 4 + (LB + 3) / 4;
     const int blob_entries = params.grid_a + params.grid_b + params.grid_entries;
     const SharedPlan plan = make_plan(params.barcode_cardinality, true, blob_entries, true);
     const size_t per_warp = static_cast< size_t >(GROUPS) * FAST_GROUP_FLOATS * sizeof(float);
-    if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
-    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
-    warps = warps > FAST_GRID_WARPS ? FAST_GRID_WARPS : warps;
-    const size_t bytes = plan.fixed_bytes + per_warp * warps;
-    cudaError_t status = cudaFuncSetAttribute(pamld_fast_grid_kernel< LA, LB >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+    const size_t dense_bytes = KBP > 0 ? (static_cast< size_t >(params.grid_entries) * sizeof(float) + 15) / 16 * 16 : 0;
+    if(plan.fixed_bytes + dense_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
+    int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes - dense_bytes) / per_warp);
+    warps = warps > fast_grid_warps(KBP) ? fast_grid_warps(KBP) : warps;
+    const size_t bytes = plan.fixed_bytes + per_warp * warps + dense_bytes;
+    cudaError_t status = cudaFuncSetAttribute(pamld_fast_grid_kernel< LA, LB, KBP >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
     if(status != cudaSuccess) { return status; }
     const int threads = warps * WARP_SIZE;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
     status = cudaMemsetAsync(params.tie_count + 2, 0, sizeof(unsigned), stream);
     if(status != cudaSuccess) { return status; }
-    pamld_fast_grid_kernel< LA, LB ><<< grid, threads, bytes, stream >>>(params, tile);
+    pamld_fast_grid_kernel< LA, LB, KBP ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
     if(status != cudaSuccess) { return status; }
     TileArguments rest(tile);
     rest.index_list = params.hard_list;
     rest.index_count = params.tie_count + 2;
-    return launch_pamld_grid_as< LA, LB, 1, true >(params, rest, geometry, stream);
+    if(KBP == 0) { return launch_pamld_grid_as< LA, LB, 1, true >(params, rest, geometry, stream); }
+    return launch_pamld_grid_as< LA, LB, (KBP == 0 ? 8 : KBP), false >(params, rest, geometry, stream);
+}
+/* the prefilter exists for the separable form (any supported shape) and for the dense form of the 8 + 8 and 10 + 10 shapes */
+template < int LA, int LB, bool DENSE >
+cudaError_t launch_pamld_fast_grid(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
+    if(params.grid_uniform) { return launch_pamld_fast_grid_as< LA, LB, 0 >(params, tile, geometry, stream); }
+    if(DENSE && params.grid_dense == 8) { return launch_pamld_fast_grid_as< LA, LB, 8 >(params, tile, geometry, stream); }
+    if(DENSE && params.grid_dense == 16) { return launch_pamld_fast_grid_as< LA, LB, 16 >(params, tile, geometry, stream); }
+    return cudaErrorInvalidValue;
 }
 
 }   /* namespace */
@@ -2899,11 +2986,11 @@ cudaError_t launch_pamld(const DecoderParams& params, const TileArguments& tile,
     if(params.whitelist != nullptr) { return launch_pamld_whitelist(params, tile, geometry, stream); }
     if(params.fast_barcodes != nullptr) {
         /* f32 prefilter scan first (see pamld_fast_kernel); the api only offers it for the shapes handled here */
-        if(params.grid != nullptr && params.grid_uniform) {
-            if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_fast_grid< 6, 6 >(params, tile, geometry, stream); }
-            if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_fast_grid< 8, 8 >(params, tile, geometry, stream); }
-            if(params.grid_split == 10 && params.nucleotide_cardinality == 20) { return launch_pamld_fast_grid< 10, 10 >(params, tile, geometry, stream); }
-            if(params.grid_split == 12 && params.nucleotide_cardinality == 24) { return launch_pamld_fast_grid< 12, 12 >(params, tile, geometry, stream); }
+        if(params.grid != nullptr) {
+            if(params.grid_split == 6 && params.nucleotide_cardinality == 12) { return launch_pamld_fast_grid< 6, 6, false >(params, tile, geometry, stream); }
+            if(params.grid_split == 8 && params.nucleotide_cardinality == 16) { return launch_pamld_fast_grid< 8, 8, true >(params, tile, geometry, stream); }
+            if(params.grid_split == 10 && params.nucleotide_cardinality == 20) { return launch_pamld_fast_grid< 10, 10, true >(params, tile, geometry, stream); }
+            if(params.grid_split == 12 && params.nucleotide_cardinality == 24) { return launch_pamld_fast_grid< 12, 12, false >(params, tile, geometry, stream); }
             return cudaErrorInvalidValue;
         }
         switch(params.group_cardinality) {
@@ -3033,7 +3120,7 @@ void describe_kernels(const DecoderParams& params, int algorithm, char* buffer, 
         } else if(grid) {
             const bool dense = params.grid_dense != 0 && (params.grid_split == 8 || params.grid_split == 10);
             char prefilter[64] = "";
-            if(params.fast_barcodes != nullptr) { snprintf(prefilter, sizeof(prefilter), "pamld_fast_grid_kernel<%d, %d> + ", params.grid_split, L - params.grid_split); }
+            if(params.fast_barcodes != nullptr) { snprintf(prefilter, sizeof(prefilter), "pamld_fast_grid_kernel<%d, %d, %d> + ", params.grid_split, L - params.grid_split, params.grid_uniform ? 0 : params.grid_dense); }
             snprintf(buffer, capacity, "%spamld_grid_kernel<%d, %d, %d, %d, %d> + pamld_tie_kernel<%d>", prefilter, params.grid_split, L - params.grid_split,
                      GRID_GROUP_WIDTH, params.grid_uniform ? 1 : (dense ? params.grid_dense : 0), params.grid_uniform ? 1 : 0, (L + 3) / 4);
         } else {
