@@ -47,7 +47,7 @@ UNIT = "reads/s"
 C5_READS = 125_000_000                      # 10^9 reads over 8 GPUs (BASELINE.json configs[4])
 DEFAULT_READS = {"c1": 1 << 28, "c2": 1 << 28, "c3": 1 << 26, "c4": 1 << 26, "c5": C5_READS}
 # the short runs of the `configs` object: (reads per GPU, warm-up reads, steps)
-SHORT_RUN = {"c2": (1 << 26, None, 5), "c3": (1 << 24, None, 5), "c4": (1 << 24, None, 5), "c5": (C5_READS, 148 * 15 * 32 * 8, 1)}
+SHORT_RUN = {"c1": (1 << 26, None, 5), "c2": (1 << 26, None, 5), "c3": (1 << 24, None, 5), "c4": (1 << 24, None, 5), "c5": (C5_READS, 148 * 15 * 32 * 8, 1)}
 WORKLOAD_LABEL = {
     "c1": "C1: Illumina dual-index (i7+i5, 8 bp each) 96-sample PAMLD, noise 0.05, confidence threshold 0.95",
     "c2": "C2: same 96-sample dual-index set, MDD, distance tolerance [1,1]",

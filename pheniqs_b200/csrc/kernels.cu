@@ -1148,30 +1148,36 @@ __host__ __device__ constexpr int fast_warps(int G) { return G <= 2 ? 24 : (G <=
 
 /* subset product of table group TABLE_GROUP for the nibble at bits 4 * LOCAL of m: entry e of the lane at
    base + TABLE_GROUP * 2048 + e * 128; the warp's block is 2 KB aligned in the shared window, so (nibble << 7) | base */
-template < int TABLE_GROUP, int LOCAL >
+template < int TABLE_GROUP, int LOCAL, int SHIFTED >
 __device__ __forceinline__ float fast_lookup(uint32_t base, uint32_t m) {
-    const uint32_t moved = (LOCAL < 2) ? (m << (LOCAL < 2 ? 7 - 4 * LOCAL : 0)) : (m >> (LOCAL < 2 ? 0 : 4 * LOCAL - 7));
+    /* the nibble sits at bit SHIFTED + 4 * LOCAL of m (the scan can hand the mask over already shifted left) and belongs at bit 7 */
+    constexpr int left = 7 - SHIFTED - 4 * LOCAL;
+    const uint32_t moved = left == 0 ? m : (left > 0 ? (m << (left > 0 ? left : 0)) : (m >> (left < 0 ? -left : 0)));
     uint32_t address;
     asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(address) : "r"(moved), "r"(base));
     float value;
     asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(value) : "r"(address), "n"(TABLE_GROUP * FAST_GROUP_FLOATS * 4));
     return value;
 }
-/* product over GROUPS consecutive table groups starting at FIRST; m holds the part's mismatch bits from bit 0 */
-template < int FIRST, int GROUPS, int k >
+/* product over GROUPS consecutive table groups starting at FIRST; m holds the part's mismatch bits from bit SHIFTED */
+template < int FIRST, int GROUPS, int SHIFTED, int k >
 struct FastProduct {
     static __device__ __forceinline__ float of(uint32_t base, uint32_t m, float t) {
-        return FastProduct< FIRST, GROUPS, k + 1 >::of(base, m, t * fast_lookup< FIRST + k, k >(base, m));
+        return FastProduct< FIRST, GROUPS, SHIFTED, k + 1 >::of(base, m, t * fast_lookup< FIRST + k, k, SHIFTED >(base, m));
     }
 };
-template < int FIRST, int GROUPS >
-struct FastProduct< FIRST, GROUPS, GROUPS > {
+template < int FIRST, int GROUPS, int SHIFTED >
+struct FastProduct< FIRST, GROUPS, SHIFTED, GROUPS > {
     static __device__ __forceinline__ float of(uint32_t, uint32_t, float t) { return t; }
 };
-template < int FIRST, int GROUPS >
+template < int FIRST, int GROUPS, int SHIFTED = 0 >
 __device__ __forceinline__ float fast_product(uint32_t base, uint32_t m) {
-    return FastProduct< FIRST, GROUPS, 1 >::of(base, m, fast_lookup< FIRST, 0 >(base, m));
+    return FastProduct< FIRST, GROUPS, SHIFTED, 1 >::of(base, m, fast_lookup< FIRST, 0, SHIFTED >(base, m));
 }
+/*  Shift the planes of FastEntry (and of the observation) travel with. Tried: 7, so that the first lookup needs no shift — but
+    the second then needs a RIGHT shift (SHF, ALU pipe) where it had a left shift (IMAD.SHL, FMA pipe), and the ALU pipe
+    is what binds this loop (LOP3, FMNMX, FSETP, SEL): no gain, so the planes travel unshifted. */
+__host__ __device__ constexpr int fast_preshift(int) { return 0; }
 /* the 2^COUNT subset products of COUNT (1..4) positions into the lane's column of one table group */
 template < int COUNT >
 __device__ __forceinline__ void fast_store_group(float* t, const float* w) {
@@ -1232,17 +1238,20 @@ __device__ __forceinline__ void fast_group_of(int count, uint32_t position_table
     else if(count == 2) { fast_group< G, 2 >(position_table, quality, nmask, first, base_probability, t); }
     else { fast_group< G, 1 >(position_table, quality, nmask, first, base_probability, t); }
 }
-/* the winner's mismatch product in f64 over the mismatched, unambiguous positions */
+/* the winner's mismatch product in f64 over the mismatched, unambiguous positions, in position order: a loop over the
+   set bits (most winners have none, a few have one or two) */
 template < int G, int POSITIONS >
 __device__ __forceinline__ double exact_product(const double* __restrict__ ratio64, const uint32_t (&quality)[G], uint32_t counted) {
     double t = 1.0;
-    #pragma unroll
-    for(int j = 0; j < POSITIONS; ++j) {
-        if((counted >> j) & 1u) {
-            uint32_t q = (quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
-            q = q > 127u ? 127u : q;
-            t *= ratio64[q];
-        }
+    while(counted != 0u) {
+        const int j = __ffs(static_cast< int >(counted)) - 1;
+        counted &= counted - 1u;
+        uint32_t word = quality[0];
+        #pragma unroll
+        for(int g = 1; g < G; ++g) { if((j >> 2) == g) { word = quality[g]; } }
+        uint32_t q = (word >> (8 * (j & 3))) & 0xffu;
+        q = q > 127u ? 127u : q;
+        t *= ratio64[q];
     }
     return t;
 }
@@ -1396,7 +1405,9 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
         for(int g = 0; g < G; ++g) { fast_group< G, 4 >(position_table, quality, nmask, 4 * g, base_probability, table + g * FAST_GROUP_FLOATS); }
         __syncwarp();
 
-        /* ---- every barcode, in f32 */
+        /* ---- every barcode, in f32 (observation and FastEntry planes shifted left by PRE) */
+        constexpr int PRE = fast_preshift(G);
+        const uint32_t s_lo = o_lo << PRE, s_hi = o_hi << PRE, s_n = nmask << PRE;
         FastSelection selection;
         selection.best = 0.0f; selection.index = 0; selection.rest = 0.0;
         for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
@@ -1416,16 +1427,16 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
                 #pragma unroll
                 for(int u = 0; u < 4; ++u) {
                     const uint4 raw = *reinterpret_cast< const uint4* >(stage + i + u);
-                    const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
-                    p[u] = fast_product< 0, G >(table_base, m);
+                    const uint32_t m = mismatch_mask(s_lo, s_hi, s_n, raw.x, raw.y);
+                    p[u] = fast_product< 0, G, PRE >(table_base, m);
                     if(!UNIFORM) { p[u] *= __uint_as_float(raw.z); }
                 }
                 fast_select_four(selection, p[0], p[1], p[2], p[3], first + i);
             }
             for(; i < count; ++i) {
                 const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
-                const uint32_t m = mismatch_mask(o_lo, o_hi, nmask, raw.x, raw.y);
-                float p = fast_product< 0, G >(table_base, m);
+                const uint32_t m = mismatch_mask(s_lo, s_hi, s_n, raw.x, raw.y);
+                float p = fast_product< 0, G, PRE >(table_base, m);
                 if(!UNIFORM) { p *= __uint_as_float(raw.z); }
                 fast_select_one(selection, p, first + i);
             }
@@ -2244,7 +2255,7 @@ struct TieWorkspace {
 };
 
 template < int G, int TIE_READS >
-__global__ void __launch_bounds__(tie_warps(G) * WARP_SIZE, 3)
+__global__ void __launch_bounds__(tie_warps(G) * WARP_SIZE, 4)
 pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     constexpr int TIE_LANES = WARP_SIZE / TIE_READS;
     extern __shared__ __align__(16) unsigned char tie_smem[];   /* barcode table when it fits TIE_STAGE_ENTRIES */
@@ -2827,12 +2838,12 @@ cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, c
     cudaError_t status = cudaFuncSetAttribute(pamld_tie_kernel< G, 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024);
     if(status == cudaSuccess) { status = cudaFuncSetAttribute(pamld_tie_kernel< G, TIE_READS_SMALL >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024); }
     if(status != cudaSuccess) { return status; }
-    /* as many CTAs as stay resident (three per SM): every CTA stages the table and flushes its accumulator rows once,
+    /* as many CTAs as stay resident (four per SM): every CTA stages the table and flushes its accumulator rows once,
        and the flushes of all CTAs meet on the same few hundred global addresses */
     if(params.barcode_cardinality >= TIE_LONG_TABLE) {
-        pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 3, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+        pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 4, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     } else {
-        pamld_tie_kernel< G, TIE_READS_SMALL ><<< geometry.multiprocessor_count * 3, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
+        pamld_tie_kernel< G, TIE_READS_SMALL ><<< geometry.multiprocessor_count * 4, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
     }
     return cudaGetLastError();
 }

@@ -111,10 +111,16 @@ def test_no_silent_fallback_without_a_gpu():
     # the feed-bytes and tag entry points refuse the same way; the record size is host arithmetic and still answers
     sequence = np.frombuffer(b"ACGTACGT" * 4, dtype=np.uint8)
     segments = [(sequence, sequence, None, 8), (sequence, sequence, None, 8)]
-    for call in (lambda: host_only.decode_raw(segments, 4), lambda: host_only.decode_raw_tags(segments, 4)):
+    calls = (lambda: host_only.decode_raw(segments, 4), lambda: host_only.decode_raw_tags(segments, 4),
+             lambda: host_only.decode_raw(segments, 4, 0, bam=True), lambda: host_only.decode_raw(segments, 4, 0, compact=True, bam=True),
+             lambda: host_only.decode_raw_tags(segments, 4, 0, bam=True), lambda: host_only.reference_power([1.0, 2.0]))
+    for call in calls:
         with pytest.raises(PheniqsError) as error:
             call()
         assert "no CPU classification path" in str(error.value)
+    # so does the collective (a null communicator is refused before anything else on a device handle; here the handle itself is)
+    assert host_only.lib.phq_collect(host_only.handle, None, None) == binding.PHQ_INTERNAL_ERROR
+    assert host_only.lib.phq_reset_accumulators_async(host_only.handle, None) == binding.PHQ_INTERNAL_ERROR
     assert host_only.tag_record_bytes() % 16 == 0 and host_only.tag_record_bytes() >= 3 + 16 + 1
 
 
