@@ -548,7 +548,7 @@ class Bench:
         seconds = self.max_over_ranks(time.perf_counter() - t0)
         return seconds / repeats
 
-    def end_to_end(self, line, spec, compiled, chain, tiles, n):
+    def end_to_end(self, line, spec, compiled, chain, tiles, n, brief=False):
         """Host buffers in, per-read results out, every copy inside the timed region, through the C-ABI calls a host makes.
         Forms, by what the timed region starts from:
           e2e        phq_decode_batch_raw_compact: the FASTQ bytes of the barcode segments (what a feed holds); the device
@@ -558,10 +558,10 @@ class Bench:
           e2e_full   phq_decode_batch: tiles packed beforehand (Phred bytes), 16-byte results + qcfail byte
           e2e_packed phq_decode_batch_compact: tiles packed beforehand with codebook qualities, 8-byte records — starts
                      from the device's own format: packing is NOT inside its timed region
-        The per-rank batch is the same at every N."""
+        The per-rank batch is the same at every N. `brief` (the short runs under `configs`): e2e and e2e_full only, on 2^22 reads."""
         torch = self.torch
         from pheniqs_b200 import COMPACT_DTYPE, RESULT_DTYPE, workload
-        m = self.args.e2e_reads or min(n, 1 << 25)
+        m = min(n, 1 << 22) if brief else (self.args.e2e_reads or min(n, 1 << 25))
         e2e_steps = max(3, min(self.args.steps, 5))
         keep = []
 
@@ -614,7 +614,7 @@ class Bench:
         line["e2e_full"] = describe(seconds, sum(t.bytes_per_read() * m for t in host_tiles if t is not None), 16 * m * sum(tiled) + m,
                                     "phq_decode_batch (tiles packed beforehand, Phred bytes; 16-byte results + qcfail byte out)")
         compact_results = None
-        if one_decoder_per_topic:
+        if one_decoder_per_topic and not brief:
             forms = [t.compress_quality() for t in host_tiles if t is not None]
             compact_results = pinned_results(COMPACT_DTYPE, 1)
             seconds = time_host(lambda: chain.decode_compact(host_tiles, m, None, results=compact_results))
@@ -632,7 +632,10 @@ class Bench:
         if one_decoder_per_topic:
             raw_results = pinned_results(COMPACT_DTYPE, 1)
             seconds = time_host(lambda: chain.decode_raw(segments, m, 33, None, compact=True, results=raw_results))
-            assert all(a is None or np.array_equal(a["packed"], b["packed"]) for a, b in zip(raw_results, compact_results)), "raw and packed forms disagree"
+            if compact_results is not None:
+                assert all(a is None or np.array_equal(a["packed"], b["packed"]) for a, b in zip(raw_results, compact_results)), "raw and packed forms disagree"
+            else:
+                assert all(a is None or np.array_equal(a["packed"] & 0xffffff, b["index"].astype(np.uint32)) for a, b in zip(raw_results, full_results)), "raw and packed forms disagree"
             d2h, record = 8 * m * sum(tiled), "8-byte records out"
         else:
             raw_results = pinned_results(RESULT_DTYPE, 2)
@@ -641,6 +644,9 @@ class Bench:
             d2h, record = 16 * m * sum(tiled) + m, "16-byte results + qcfail byte out (several decoders per topic)"
         line["e2e"] = describe(seconds, raw_bytes, d2h, "phq_decode_batch_raw%s (FASTQ bytes of the barcode segments in, decoded / sliced / packed on the device; %s)" % ("_compact" if one_decoder_per_topic else "", record))
 
+        if brief:
+            chain.reset()
+            return
         # the reference's decoded Segment buffers: BAM codes and Phred bytes (sequence.h:264-300), same byte count
         bam_of_ascii = np.full(256, 15, dtype=np.uint8)
         for letter, code in ((b"A", 1), (b"C", 2), (b"G", 4), (b"T", 8)):
@@ -736,7 +742,9 @@ def main():
     for name in [c for c in args.configs.split(",") if c and c != args.workload]:
         reads, warm, steps = SHORT_RUN[name]
         try:
-            entry, (_, _, chain, tiles) = bench.run(name, reads, steps, 3, warm_reads=warm)
+            entry, (spec_k, compiled_k, chain, tiles) = bench.run(name, reads, steps, 3, warm_reads=warm)
+            if not args.no_e2e:
+                bench.end_to_end(entry, spec_k, compiled_k, chain, tiles, reads, brief=True)
             configs[name] = entry
             chain.close()
             del chain, tiles

@@ -2,7 +2,7 @@
 profiles/ncu_summary.json that bench.py quotes in `roofline` (DRAM bytes per read and the counters that name the
 binding resource of the workload's dominant kernel).
 
-usage: ncu_to_profiles.py report.ncu-rep workload reads_per_launch kernel_substring output_name
+usage: ncu_to_profiles.py report.ncu-rep|raw.csv workload reads_per_launch kernel_substring output_name
 """
 import csv, json, os, subprocess, sys
 
@@ -25,7 +25,8 @@ def number(text):
 def main():
     rep, workload, reads, kernel, name = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # either the .ncu-rep itself or the `ncu -i rep --page raw --csv` dump of it (what travels back from the GPU box)
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     header, units = rows[0], rows[1]
     row = next(r for r in rows[2:] if kernel in r[header.index("Kernel Name")])
