@@ -548,7 +548,7 @@ class Bench:
         seconds = self.max_over_ranks(time.perf_counter() - t0)
         return seconds / repeats
 
-    def end_to_end(self, line, spec, compiled, chain, tiles, n, brief=False):
+    def end_to_end(self, line, spec, compiled, chain, tiles, n, brief=False, brief_reads=1 << 24):
         """Host buffers in, per-read results out, every copy inside the timed region, through the C-ABI calls a host makes.
         Forms, by what the timed region starts from:
           e2e        phq_decode_batch_raw_compact: the FASTQ bytes of the barcode segments (what a feed holds); the device
@@ -558,10 +558,11 @@ class Bench:
           e2e_full   phq_decode_batch: tiles packed beforehand (Phred bytes), 16-byte results + qcfail byte
           e2e_packed phq_decode_batch_compact: tiles packed beforehand with codebook qualities, 8-byte records — starts
                      from the device's own format: packing is NOT inside its timed region
-        The per-rank batch is the same at every N. `brief` (the short runs under `configs`): e2e and e2e_full only, on 2^22 reads."""
+        The per-rank batch is the same at every N. `brief` (the short runs under `configs`): e2e and e2e_full only, on 2^24
+        reads (four sub-batches in flight over three staging slots; 2^22 for the whitelist config, which is kernel bound)."""
         torch = self.torch
         from pheniqs_b200 import COMPACT_DTYPE, RESULT_DTYPE, workload
-        m = min(n, 1 << 22) if brief else (self.args.e2e_reads or min(n, 1 << 25))
+        m = min(n, brief_reads) if brief else (self.args.e2e_reads or min(n, 1 << 25))
         e2e_steps = max(3, min(self.args.steps, 5))
         keep = []
 
@@ -744,7 +745,7 @@ def main():
         try:
             entry, (spec_k, compiled_k, chain, tiles) = bench.run(name, reads, steps, 3, warm_reads=warm)
             if not args.no_e2e:
-                bench.end_to_end(entry, spec_k, compiled_k, chain, tiles, reads, brief=True)
+                bench.end_to_end(entry, spec_k, compiled_k, chain, tiles, reads, brief=True, brief_reads=(1 << 22) if name == "c5" else (1 << 24))
             configs[name] = entry
             chain.close()
             del chain, tiles
