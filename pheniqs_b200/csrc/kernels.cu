@@ -1143,6 +1143,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 constexpr double FAST_EASY_RATIO = 9.5367431640625e-07;             /* 2^-20 */
 constexpr float FAST_MINIMUM_BEST = 8.6736173798840355e-19f;        /* 2^-60: below it f32 products of the others may underflow */
 constexpr double FAST_THRESHOLD_GUARD = 3.637978807091713e-12;      /* 2^-38 */
+constexpr int FAST_BLOCK_SELECTION = 32;                            /* codecs from this size on keep the index per block of four (fast_select_block) */
 constexpr int FAST_GROUP_FLOATS = 16 * WARP_SIZE;                   /* one table group: 16 subsets x 32 lanes, 2 KB */
 __host__ __device__ constexpr int fast_warps(int G) { return G <= 2 ? 24 : (G <= 4 ? 20 : 16); }
 
@@ -1293,6 +1294,26 @@ __device__ __forceinline__ void fast_select_four(FastSelection& s, float p0, flo
     s.rest += static_cast< double >(((la + lb) + lc) + low);
 }
 
+/*  The same selection with the index kept per BLOCK of four: the block's maximum and sum cost three FMNMX and three
+    FADD, and only the duel between the block and the running best carries an index (and the sums: the loser's whole
+    sum goes to the rest, the leader's is held back). 13 instructions per block instead of 21, 8 of them on the ALU pipe
+    instead of 16 — the pipe that binds these loops. The scan recomputes the four products of the leading block once
+    per read to name the winner and to add the other three (fast_block_winner). */
+struct FastBlockSelection {
+    float best;             /* the largest product so far */
+    float best_sum;         /* the sum of the block it sits in */
+    int index;              /* that block's first barcode */
+    double rest;            /* the sum of all other blocks */
+};
+__device__ __forceinline__ void fast_select_block(FastBlockSelection& s, float block_max, float block_sum, int i) {
+    const bool later = block_max > s.best;
+    const float loser = later ? s.best_sum : block_sum;
+    s.best_sum = later ? block_sum : s.best_sum;
+    s.index = later ? i : s.index;
+    s.best = fmaxf(s.best, block_max);
+    s.rest += static_cast< double >(loser);
+}
+
 /*  The hard list of a prefilter scan. Every tile leaves a few reads per warp (about 7 % of them); appending those with
     one global atomic per warp and tile means half a million atomics per launch on ONE address and a round trip to L2
     in every tile. So each warp stages its hard reads in 256 bytes of shared memory and moves them out 32 at a time:
@@ -1377,6 +1398,7 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     hard.held = 0u;
     hard.list = P.hard_list;
     hard.count = P.tie_count + 2;
+    const bool by_block = P.barcode_cardinality >= FAST_BLOCK_SELECTION;
 
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
     const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -1410,6 +1432,62 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
         const uint32_t s_lo = o_lo << PRE, s_hi = o_hi << PRE, s_n = nmask << PRE;
         FastSelection selection;
         selection.best = 0.0f; selection.index = 0; selection.rest = 0.0;
+        if(by_block) {
+            /* codecs of 32 barcodes or more: the index travels per block of four (fast_select_block) */
+            FastBlockSelection leader;
+            leader.best = 0.0f; leader.best_sum = 0.0f; leader.index = 0; leader.rest = 0.0;
+            for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
+                const BarcodeEntry* stage;
+                if(resident) {
+                    stage = resident_stage;
+                } else {
+                    if(tid == 0 && iteration + 1 < total_iterations) { stream.issue(iteration + 1); }
+                    stage = stream.wait(iteration);
+                }
+                const int count = stream.count(chunk);
+                const int first = chunk * S.plan.stage_capacity;
+                int i = 0;
+                #pragma unroll 2
+                for(; i + 4 <= count; i += 4) {
+                    float p[4];
+                    #pragma unroll
+                    for(int u = 0; u < 4; ++u) {
+                        const uint4 raw = *reinterpret_cast< const uint4* >(stage + i + u);
+                        const uint32_t m = mismatch_mask(s_lo, s_hi, s_n, raw.x, raw.y);
+                        p[u] = fast_product< 0, G, PRE >(table_base, m);
+                        if(!UNIFORM) { p[u] *= __uint_as_float(raw.z); }
+                    }
+                    fast_select_block(leader, fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), (p[0] + p[1]) + (p[2] + p[3]), first + i);
+                }
+                for(; i < count; ++i) {          /* the last barcodes of a codec that is not a multiple of four: blocks of one */
+                    const uint4 raw = *reinterpret_cast< const uint4* >(stage + i);
+                    const uint32_t m = mismatch_mask(s_lo, s_hi, s_n, raw.x, raw.y);
+                    float p = fast_product< 0, G, PRE >(table_base, m);
+                    if(!UNIFORM) { p *= __uint_as_float(raw.z); }
+                    fast_select_block(leader, p, p, first + i);
+                }
+                if(!resident) {
+                    __syncthreads();
+                    ++iteration;
+                }
+            }
+            /* the leading block once more: which of its four it was, and the other three into the rest */
+            selection.index = leader.index;
+            selection.rest = leader.rest;
+            if(leader.index < (P.barcode_cardinality & ~3)) {
+                float p[4];
+                #pragma unroll
+                for(int u = 0; u < 4; ++u) {
+                    const uint4 raw = __ldg(reinterpret_cast< const uint4* >(P.fast_barcodes + leader.index + u));
+                    const uint32_t m = mismatch_mask(s_lo, s_hi, s_n, raw.x, raw.y);
+                    p[u] = fast_product< 0, G, PRE >(table_base, m);
+                    if(!UNIFORM) { p[u] *= __uint_as_float(raw.z); }
+                }
+                fast_select_four(selection, p[0], p[1], p[2], p[3], leader.index);
+            } else {
+                selection.best = leader.best;
+            }
+        } else {
         for(int chunk = 0; chunk < stream.chunk_cardinality; ++chunk) {
             const BarcodeEntry* stage;
             if(resident) {
@@ -1444,6 +1522,7 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
                 __syncthreads();
                 ++iteration;
             }
+        }
         }
 
         if(UNIFORM) {
@@ -2104,19 +2183,10 @@ pamld_whitelist_kernel(const DecoderParams P, const TileArguments A, unsigned* c
    Structural ties (equal multisets of mismatch qualities under equal priors) are common for noise reads
    (~2 % of the synthetic workloads). The reference resolves them by the rounding of its position ordered
    Kahan sums (barcode.h:147-162) and then keeps the first maximum (pamld.cpp:73), so the queued reads are
-   re-decoded here in exactly that operation order. One warp per read, lanes = barcodes:
-
-     1. the read's per-position factors and its subset product table (linear, so any lane -> entry mapping
-        is conflict free or a broadcast) are rebuilt in shared memory;
-     2. every barcode's prior adjusted product is computed, 32 per step; the warp keeps the maximum and the
-        sum of everything else;
-     3. barcodes within 2^-18 of the maximum are candidates; each candidate's sigma_q is evaluated bit for
-        bit as the reference does; among equal priors the smaller sigma wins and equal sigmas keep the
-        lower index, which is what strict > over p = pow(B, sigma) * prior yields. pow() is only consulted
-        across different priors;
-     4. lane 0 takes the decision and updates the accumulators.
-
-   Full occupancy (no per-lane tables) hides the latency of the serial Kahan chains. */
+   re-decoded in exactly that operation order: every barcode that can be the winner (within 2^-18 of the scan's
+   maximum; the scan names them) has its sigma_q evaluated bit for bit as the reference does; among equal priors the
+   smaller sigma wins and equal sigmas keep the lower index, which is what strict > over p = pow(B, sigma) * prior
+   yields. pow() is only consulted across different priors or for small sigma (see beats). */
 struct Candidate {
     double prior;
     double sigma;
@@ -2221,68 +2291,145 @@ __device__ __forceinline__ bool beats(const Candidate& a, const Candidate& b, do
     if(b.index < 0) { return true; }
     if(a.prior == b.prior) {
         if(a.sigma == b.sigma) { return a.index < b.index; }
-        /* from 64 on, one ulp of sigma moves pow(B, sigma) by more than 2^-48: neither pow nor the product with the
-           common prior can merge or reorder the two, the smaller sigma is the larger p */
-        if(fmin(a.sigma, b.sigma) >= 64.0) { return a.sigma < b.sigma; }
+        /* from 32 on, one ulp of sigma (2^-47 or more) moves pow(B, sigma) by 0.23 x 2^-47 = 7 x 2^-52 relative or more;
+           pow (under one ulp) and the product with the common prior (half an ulp) move each side by at most
+           1.5 x 2^-52: they can neither merge nor reorder the two, the smaller sigma is the larger p */
+        if(fmin(a.sigma, b.sigma) >= 32.0) { return a.sigma < b.sigma; }
     }
     const double pa = reference_power(base, a.sigma) * a.prior;
     const double pb = reference_power(base, b.sigma) * b.prior;
     return pa > pb || (pa == pb && a.index < b.index);
 }
 
-/* warps per CTA of the tie kernel: its per-warp workspace is static shared memory (48 KB limit) */
-__host__ __device__ constexpr int tie_warps(int G) { return G <= 4 ? 8 : 4; }
+/*  The tie pass proper. ONE THREAD PER QUEUED READ: the reads of a queue name two to a dozen candidates each, so a
+    lane per barcode (a warp per read, later eight lanes per read) leaves most lanes idle while every read still pays
+    the warp-wide set-up, a butterfly of comparisons and the decision. A thread instead
+
+      1. loads its 128-byte record and turns every position into the shared-memory address of its score: the CTA holds
+         ONE table of 512 doubles indexed by Phred byte | mismatch << 7 | no-call << 8 (phred.cpp:39-72: the true
+         positive quality when the base matches, the quality itself when it does not, UNIFORM_BASE_QUALITY for a base
+         that is not A / C / G / T, 0 at Phred 0; 4 KB aligned, so the mismatch bit is ORed into the address): a
+         candidate's position costs a shift, a LOP3 and an LDS.64 next to the four DADDs of its Kahan step;
+      2. walks its candidates — named in the record, in the pool, or the members of the flagged runs — and forms each
+         one's sigma_q exactly like Barcode::compensated_decoding_probability (barcode.h:147-162), keeping the one the
+         reference's strict > would keep (`beats` is a strict total order, so folding in any order finds the same one);
+      3. takes the decision and updates the accumulators.
+
+    A read whose candidates the scan could not bound (TIE_RESCAN: rare) is scanned by its whole warp afterwards, lanes =
+    barcodes, and handed back to its thread. */
+constexpr int TIE_THREADS = 128;
 constexpr int TIE_STAGE_ENTRIES = 1024;
-/* rows of the tie kernel's per-CTA accumulator tables (N + 1), 0 when they stay in global memory; the kernel's static
-   shared memory (workspaces, Phred tables) leaves room for 300 rows next to the staged barcodes at three CTAs per SM */
+/* CTAs per SM: the per-position addresses of a read stay in registers (4 G of them) */
+__host__ __device__ constexpr int tie_resident(int G) { return G <= 4 ? 6 : 4; }
+/* rows of the tie kernel's per-CTA accumulator tables (N + 1), 0 when they stay in global memory */
 __host__ __device__ constexpr int tie_accumulator_rows(int N) { return N + 1 <= 300 ? N + 1 : 0; }
-/* reads per warp: four (eight lanes each) for the small codecs, one (all 32 lanes) when the table is long, where the
-   scan over the barcodes is what takes the time and there are few queued reads to fill the machine with */
-constexpr int TIE_READS_SMALL = 4;
-constexpr int TIE_LONG_TABLE = 8192;
+constexpr int TIE_SCORE_ENTRIES = 512;
+__host__ __device__ constexpr size_t tie_shared_bytes(int N) {
+    return 4096                                                             /* alignment slack of the score table */
+         + TIE_SCORE_ENTRIES * 8 + 128 * 8                                  /* scores, mismatch ratios */
+         + (N <= TIE_STAGE_ENTRIES ? static_cast< size_t >(N) * sizeof(BarcodeEntry) : 0)
+         + static_cast< size_t >(tie_accumulator_rows(N)) * (ACC_F64_COLUMNS * 8 + ACC_U64_COLUMNS * 4);
+}
 
-/* per warp scratch of the tie kernel */
-template < int G, int TIE_READS >
-struct TieWorkspace {
-    double table[TIE_READS][G * 16];            /* linear subset product tables */
-    double match_value[TIE_READS][G * 4];       /* per position substitution lookup when the base matches (phred.cpp:39-72) */
-    double mismatch_value[TIE_READS][G * 4];    /* ... when it does not */
-    double ratio[TIE_READS][G * 4];
-    double sigma[WARP_SIZE];                    /* evaluated candidates */
-    double prior[WARP_SIZE];
-    uint32_t list[WARP_SIZE];                   /* candidate = read slot << 28 | barcode */
-    uint32_t o_lo[TIE_READS], o_hi[TIE_READS], nmask[TIE_READS];
-};
+/* sigma_q of a candidate: the Kahan sum of the per-position scores in position order, bit for bit barcode.h:147-162.
+   score_address[j] = table + 8 q_j + 2048 no-call_j; the mismatch bit j of m goes to bit 10 (128 entries of 8 bytes).
+   Two candidates at a time: a step is a chain of four dependent DADDs, and a thread with one chain waits on it. */
+template < int G >
+__device__ __forceinline__ void tie_sigma_pair(const uint32_t (&score_address)[4 * G], uint32_t m0, uint32_t m1, int L, double& sigma0, double& sigma1) {
+    double s0 = 0.0, c0 = 0.0, s1 = 0.0, c1 = 0.0;
+    #pragma unroll
+    for(int j = 0; j < 4 * G; ++j) {
+        if(j > 4 * (G - 1) && j >= L) { break; }
+        const uint32_t moved0 = j <= 10 ? (m0 << (j <= 10 ? 10 - j : 0)) : (m0 >> (j <= 10 ? 0 : j - 10));
+        const uint32_t moved1 = j <= 10 ? (m1 << (j <= 10 ? 10 - j : 0)) : (m1 >> (j <= 10 ? 0 : j - 10));
+        uint32_t address0, address1;
+        asm("lop3.b32 %0, %1, 0x400, %2, 0xEA;" : "=r"(address0) : "r"(moved0), "r"(score_address[j]));
+        asm("lop3.b32 %0, %1, 0x400, %2, 0xEA;" : "=r"(address1) : "r"(moved1), "r"(score_address[j]));
+        double value0, value1;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(value0) : "r"(address0));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(value1) : "r"(address1));
+        const double y0 = __dsub_rn(value0, c0);
+        const double y1 = __dsub_rn(value1, c1);
+        const double t0 = __dadd_rn(s0, y0);
+        const double t1 = __dadd_rn(s1, y1);
+        c0 = __dsub_rn(__dsub_rn(t0, s0), y0);
+        c1 = __dsub_rn(__dsub_rn(t1, s1), y1);
+        s0 = t0;
+        s1 = t1;
+    }
+    sigma0 = s0;
+    sigma1 = s1;
+}
+template < int G >
+__device__ __forceinline__ double tie_sigma(const uint32_t (&score_address)[4 * G], uint32_t m, int L) {
+    double sigma = 0.0, compensation = 0.0;
+    #pragma unroll
+    for(int j = 0; j < 4 * G; ++j) {
+        if(j > 4 * (G - 1) && j >= L) { break; }
+        const uint32_t moved = j <= 10 ? (m << (j <= 10 ? 10 - j : 0)) : (m >> (j <= 10 ? 0 : j - 10));
+        uint32_t address;
+        asm("lop3.b32 %0, %1, 0x400, %2, 0xEA;" : "=r"(address) : "r"(moved), "r"(score_address[j]));
+        double value;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(value) : "r"(address));
+        const double y = __dsub_rn(value, compensation);
+        const double t = __dadd_rn(sigma, y);
+        compensation = __dsub_rn(__dsub_rn(t, sigma), y);
+        sigma = t;
+    }
+    return sigma;
+}
+/* the mismatch product of a barcode over the mismatched, unambiguous positions (ascending), from the ratio table */
+template < int G >
+__device__ __forceinline__ double tie_product(const uint32_t (&score_address)[4 * G], uint32_t ratio_table, uint32_t counted, int L) {
+    double t = 1.0;
+    #pragma unroll
+    for(int j = 0; j < 4 * G; ++j) {
+        if(j > 4 * (G - 1) && j >= L) { break; }
+        if((counted >> j) & 1u) {
+            double value;
+            asm("ld.shared.f64 %0, [%1];" : "=d"(value) : "r"(ratio_table + (score_address[j] & 0x3f8u)));
+            t *= value;
+        }
+    }
+    return t;
+}
 
-template < int G, int TIE_READS >
-__global__ void __launch_bounds__(tie_warps(G) * WARP_SIZE, 4)
+template < int G >
+__global__ void __launch_bounds__(TIE_THREADS, tie_resident(G))
 pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
-    constexpr int TIE_LANES = WARP_SIZE / TIE_READS;
-    extern __shared__ __align__(16) unsigned char tie_smem[];   /* barcode table when it fits TIE_STAGE_ENTRIES */
-    __shared__ double phred_shared[PHRED_TABLE_SIZE];
-    constexpr int TIE_WARPS = tie_warps(G);
-    __shared__ TieWorkspace< G, TIE_READS > workspace[TIE_WARPS];
+    extern __shared__ __align__(16) unsigned char tie_smem[];
     __shared__ uint32_t block_counter[4];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int slot = lane / TIE_LANES;          /* which of the warp's reads this lane works on */
-    const int sub = lane % TIE_LANES;
     const int N = P.barcode_cardinality;
     const unsigned tie_cardinality = *P.tie_count;
-    if(blockIdx.x * TIE_WARPS * TIE_READS >= tie_cardinality) { return; }
+    if(blockIdx.x * TIE_THREADS >= tie_cardinality) { return; }
 
-    const bool staged = N <= TIE_STAGE_ENTRIES;
-    const BarcodeEntry* barcodes = P.barcodes;
-    if(staged) {
-        uint4* const stage = reinterpret_cast< uint4* >(tie_smem);
-        for(int i = tid; i < N; i += blockDim.x) { stage[i] = reinterpret_cast< const uint4* >(P.barcodes)[i]; }
-        barcodes = reinterpret_cast< const BarcodeEntry* >(tie_smem);
+    /* ---- shared memory: score table (4 KB aligned), mismatch ratios, the barcode table when it is small, accumulator rows */
+    const uint32_t window = shared_address(tie_smem);
+    const uint32_t slack = (4096u - (window & 4095u)) & 4095u;
+    double* const score = reinterpret_cast< double* >(tie_smem + slack);
+    double* const ratio = score + TIE_SCORE_ENTRIES;
+    unsigned char* cursor = reinterpret_cast< unsigned char* >(ratio + 128);
+    const uint32_t score_table = window + slack;
+    const uint32_t ratio_table = score_table + TIE_SCORE_ENTRIES * 8;
+    const double uniform_quality = P.phred[PHRED_UNIFORM_QUALITY];
+    const double base = P.phred[PHRED_BASE];
+    for(int i = tid; i < TIE_SCORE_ENTRIES; i += blockDim.x) {
+        const int q = i & 127;
+        score[i] = q == 0 ? 0.0 : ((i >> 8) ? uniform_quality : (((i >> 7) & 1) ? static_cast< double >(q) : P.phred[PHRED_TRUE_POSITIVE_QUALITY + q]));
     }
-    for(int i = tid; i < PHRED_TABLE_SIZE; i += blockDim.x) { phred_shared[i] = P.phred[i]; }
+    for(int i = tid; i < 128; i += blockDim.x) { ratio[i] = P.phred[PHRED_MISMATCH_RATIO + i]; }
+    const BarcodeEntry* barcodes = P.barcodes;
+    if(N <= TIE_STAGE_ENTRIES) {
+        uint4* const stage = reinterpret_cast< uint4* >(cursor);
+        for(int i = tid; i < N; i += blockDim.x) { stage[i] = reinterpret_cast< const uint4* >(P.barcodes)[i]; }
+        barcodes = reinterpret_cast< const BarcodeEntry* >(cursor);
+        cursor += static_cast< size_t >(N) * sizeof(BarcodeEntry);
+    }
     if(tid < 4) { block_counter[tid] = 0; }
-    /* per-CTA accumulator tables behind the staged barcodes (small codecs): the queued reads of a batch hit a handful
-       of rows — the undetermined one above all — and global atomics on one address serialise */
+    /* per-CTA accumulator tables (small codecs): the queued reads of a batch hit a handful of rows — the undetermined
+       one above all — and global atomics on one address serialise */
     const int accumulator_rows = tie_accumulator_rows(N);
     Accumulator accumulator;
     accumulator.shared_u32 = nullptr;
@@ -2290,7 +2437,7 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     accumulator.global_u64 = P.acc_u64;
     accumulator.global_f64 = P.acc_f64;
     if(accumulator_rows > 0) {
-        accumulator.shared_f64 = reinterpret_cast< double* >(tie_smem + static_cast< size_t >(N) * sizeof(BarcodeEntry));
+        accumulator.shared_f64 = reinterpret_cast< double* >(cursor);
         accumulator.shared_u32 = reinterpret_cast< uint32_t* >(accumulator.shared_f64 + accumulator_rows * ACC_F64_COLUMNS);
         for(int i = tid; i < accumulator_rows * ACC_F64_COLUMNS; i += blockDim.x) { accumulator.shared_f64[i] = 0.0; }
         for(int i = tid; i < accumulator_rows * ACC_U64_COLUMNS; i += blockDim.x) { accumulator.shared_u32[i] = 0u; }
@@ -2298,202 +2445,124 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     __syncthreads();
 
     const int L = P.nucleotide_cardinality;
-    const double uniform_quality = phred_shared[PHRED_UNIFORM_QUALITY];
-    const double base = phred_shared[PHRED_BASE];
-    TieWorkspace< G, TIE_READS >& W = workspace[warp];
-    const unsigned stride = gridDim.x * TIE_WARPS * TIE_READS;
-
-    for(unsigned first_item = (blockIdx.x * TIE_WARPS + warp) * TIE_READS; first_item < tie_cardinality; first_item += stride) {
-        const unsigned item = first_item + slot;
+    const unsigned stride = gridDim.x * TIE_THREADS;
+    for(unsigned first_item = blockIdx.x * TIE_THREADS + (tid & ~31); first_item < tie_cardinality; first_item += stride) {
+        const unsigned item = first_item + lane;
         const bool live = item < tie_cardinality;
-        /* everything the scan knew about the read travels in the record: one contiguous 80-byte read per item */
+        /* everything the scan knew about the read travels in the record: one 128-byte line per thread */
         TieRecord record;
-        if(live) { record = P.tie_record[item]; }
-        else { record.best = 0; record.rest = 0; record.base_probability = 1; record.o_lo = 0; record.o_hi = 0; record.nmask = 0; record.read = 0; record.uniform = 0; record.high_quality_mask = 0; }
-        const uint32_t o_lo = record.o_lo, o_hi = record.o_hi, nmask = record.nmask;
-        if(sub == 0) { W.o_lo[slot] = o_lo; W.o_hi[slot] = o_hi; W.nmask[slot] = nmask; }
-
-        /* ---- per-position scores: the eight lanes of a read share its positions */
-        #pragma unroll
-        for(int step = 0; step < (G * 4 + TIE_LANES - 1) / TIE_LANES; ++step) {
-            const int j = sub + step * TIE_LANES;
-            if(j >= G * 4) { break; }
-            /* word j >> 2 = 2 * step + (sub >> 2): picked with a select so the record stays in registers */
-            uint32_t word = record.quality[0];
+        {
+            uint4* const words = reinterpret_cast< uint4* >(&record);
+            const uint4* const source = reinterpret_cast< const uint4* >(P.tie_record + (live ? item : 0u));
             #pragma unroll
-            for(int g = 1; g < 8; ++g) { if((j >> 2) == g) { word = record.quality[g]; } }
-            uint32_t q = live ? (word >> (8 * (j & 3))) & 0xffu : 0u;
+            for(int i = 0; i < 8; ++i) { words[i] = source[i]; }
+        }
+        const uint32_t o_lo = record.o_lo, o_hi = record.o_hi, nmask = record.nmask;
+        uint32_t score_address[4 * G];
+        #pragma unroll
+        for(int j = 0; j < 4 * G; ++j) {
+            uint32_t q = (record.quality[j >> 2] >> (8 * (j & 3))) & 0xffu;
             q = q > 127u ? 127u : q;
-            const bool ambiguous = (nmask >> j) & 1u;
-            W.match_value[slot][j] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : phred_shared[PHRED_TRUE_POSITIVE_QUALITY + q]);
-            W.mismatch_value[slot][j] = (q == 0u) ? 0.0 : (ambiguous ? uniform_quality : static_cast< double >(q));
-            W.ratio[slot][j] = ambiguous ? 1.0 : phred_shared[PHRED_MISMATCH_RATIO + q];
+            score_address[j] = score_table + q * 8u + ((nmask >> j) & 1u) * 2048u;
         }
-        __syncwarp();
-        /*  The scan usually names the candidates (TieRecord::candidate): then only those are evaluated. A read whose
-            list overflowed, or that comes from a scan that does not collect (the whitelist scan), has its candidates
-            found here by a scan of the whole table; the subset product table is only built when the warp has one. */
-        const bool blocks = live && record.candidate_count == TIE_BLOCKS;      /* a mask over runs of barcodes (or grid entries) */
-        const bool pooled = live && !blocks && record.candidate_count != TIE_RESCAN && (record.candidate_count & TIE_POOLED) != 0u;
-        const uint32_t block_mask = record.candidate[0];
-        const uint32_t run = 4u << (record.candidate[1] & 31u);                 /* barcodes per bit of the mask */
-        const bool grid_entries = blocks && record.candidate[2] != 0u;
-        const uint32_t listed = !live ? 0u : (blocks ? static_cast< uint32_t >(__popc(block_mask)) * run : (pooled ? (record.candidate_count & 0xffffu) : record.candidate_count));
-        const bool rescan = live && record.candidate_count == TIE_RESCAN;
-        const uint32_t* const named = pooled ? P.tie_pool + record.candidate[0] : (live ? P.tie_record[item].candidate : nullptr);
-        const int scanned = grid_entries ? P.grid_entries : N;                   /* what the mask counts */
-        const bool any_rescan = __any_sync(FULL_MASK, rescan);
-        if(any_rescan) {
-            /* subset product table (linear: any lane -> entry mapping is conflict free or a broadcast), same
-               association as the scan kernel: ((w0 w1) w2) w3 */
-            for(int e = sub; e < G * 16; e += TIE_LANES) {
-                const int g = e >> 4;
-                double t = 1.0;
-                #pragma unroll
-                for(int k = 0; k < 4; ++k) {
-                    if((e >> k) & 1) { t *= W.ratio[slot][g * 4 + k]; }
-                }
-                W.table[slot][e] = t;
-            }
-        }
-        __syncwarp();
 
-        /* ---- candidates: barcodes within 2^-18 of the scan's maximum, compacted over the whole warp, then
-           each one's sigma_q evaluated exactly by one lane */
-        const double threshold = __hiloint2double(__double2hiint(record.best), 0) * (1.0 - 3.814697265625e-06);
+        /* ---- the candidates: a list (in the record or in the pool) or the members of the flagged runs */
+        const uint32_t count_word = record.candidate_count;
+        const bool rescan = live && count_word == TIE_RESCAN;
+        const bool blocks = live && count_word == TIE_BLOCKS;
+        const bool pooled = live && !blocks && !rescan && (count_word & TIE_POOLED) != 0u;
+        const uint32_t* const named = pooled ? P.tie_pool + record.candidate[0] : P.tie_record[live ? item : 0u].candidate;
+        const bool grid_entries = blocks && record.candidate[2] != 0u;
+        const uint32_t scanned = static_cast< uint32_t >(grid_entries ? P.grid_entries : N);      /* what a block mask counts */
+        const uint32_t run = 4u << (record.candidate[1] & 31u);
+        uint32_t pending_runs = blocks ? record.candidate[0] : 0u;
+        uint32_t next = 0u;
+        uint32_t last = (!live || rescan || blocks) ? 0u : (pooled ? (count_word & 0xffffu) : count_word);
         Candidate best;
         best.prior = 0; best.sigma = 0; best.index = -1;
-        int count = 0;
-        const double* const table = W.table[slot];
+        /* the next candidate of this thread, -1 when it has none left */
+        auto pull = [&]() -> int {
+            for(;;) {
+                if(next >= last) {
+                    if(pending_runs == 0u) { return -1; }
+                    const uint32_t bit = static_cast< uint32_t >(__ffs(static_cast< int >(pending_runs)) - 1);
+                    pending_runs &= pending_runs - 1u;
+                    next = bit * run;
+                    last = min(next + run, scanned);
+                    continue;
+                }
+                int b;
+                if(blocks) { b = grid_entries ? static_cast< int >(reinterpret_cast< const uint4* >(P.grid)[P.grid_a + P.grid_b + next].y) : static_cast< int >(next); }
+                else { b = static_cast< int >(named[next]); }
+                ++next;
+                if(b < N) { return b; }
+            }
+        };
+        for(;;) {
+            const int b0 = pull();
+            if(b0 < 0) { break; }
+            const int b1 = pull();
+            const uint4 raw0 = *reinterpret_cast< const uint4* >(barcodes + b0);
+            const uint4 raw1 = *reinterpret_cast< const uint4* >(barcodes + max(b1, 0));
+            const uint32_t m0 = ((o_lo ^ raw0.x) | (o_hi ^ raw0.y)) | nmask;
+            const uint32_t m1 = ((o_lo ^ raw1.x) | (o_hi ^ raw1.y)) | nmask;
+            Candidate first, second;
+            tie_sigma_pair< G >(score_address, m0, m1, L, first.sigma, second.sigma);
+            first.prior = __hiloint2double(static_cast< int >(raw0.w), static_cast< int >(raw0.z));
+            first.index = b0;
+            second.prior = __hiloint2double(static_cast< int >(raw1.w), static_cast< int >(raw1.z));
+            second.index = b1;                              /* -1 = none: beats() lets it lose */
+            if(beats(second, first, base)) { first = second; }
+            if(beats(first, best, base)) { best = first; }
+        }
 
-        auto evaluate = [&](int pending) {
-            if(lane < pending) {
-                const uint32_t packed = W.list[lane];
-                const int owner = packed >> 28;
-                const int b = packed & 0x0fffffff;
+        /* ---- reads without a bound on their candidates: the warp scans the whole table for one read at a time; barcodes
+           within 2^-18 of the scan's maximum are evaluated, every lane folds its own, a butterfly picks the winner */
+        unsigned unbounded = __ballot_sync(FULL_MASK, rescan);
+        while(unbounded != 0u) {
+            const int owner = __ffs(static_cast< int >(unbounded)) - 1;
+            unbounded &= unbounded - 1u;
+            const uint32_t r_lo = __shfl_sync(FULL_MASK, o_lo, owner), r_hi = __shfl_sync(FULL_MASK, o_hi, owner), r_n = __shfl_sync(FULL_MASK, nmask, owner);
+            uint32_t r_address[4 * G];
+            #pragma unroll
+            for(int j = 0; j < 4 * G; ++j) { r_address[j] = __shfl_sync(FULL_MASK, score_address[j], owner); }
+            const int scan_high = __shfl_sync(FULL_MASK, __double2hiint(record.best), owner);
+            const double threshold = __hiloint2double(scan_high, 0) * (1.0 - 3.814697265625e-06);
+            Candidate own;
+            own.prior = 0; own.sigma = 0; own.index = -1;
+            #pragma unroll 1
+            for(int b = lane; b < N; b += WARP_SIZE) {
                 const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
-                const uint32_t m = ((W.o_lo[owner] ^ raw.x) | (W.o_hi[owner] ^ raw.y)) | W.nmask[owner];
-                /* Barcode::compensated_decoding_probability's accumulation, bit for bit (barcode.h:147-162) */
-                const double* const on_match = W.match_value[owner];
-                const double* const on_mismatch = W.mismatch_value[owner];
-                double sigma = 0.0, compensation = 0.0;
-                #pragma unroll 4
-                for(int j = 0; j < L; ++j) {
-                    const double value = ((m >> j) & 1u) ? on_mismatch[j] : on_match[j];
-                    const double y = __dsub_rn(value, compensation);
-                    const double t = __dadd_rn(sigma, y);
-                    compensation = __dsub_rn(__dsub_rn(t, sigma), y);
-                    sigma = t;
-                }
-                W.sigma[lane] = sigma;
-                W.prior[lane] = __hiloint2double(raw.w, raw.z);
-            }
-            __syncwarp();
-            /* the first lane of every read folds in the candidates that belong to it */
-            if(sub == 0) {
-                for(int c = 0; c < pending; ++c) {
-                    const uint32_t packed = W.list[c];
-                    if(static_cast< int >(packed >> 28) == slot) {
-                        Candidate other;
-                        other.prior = W.prior[c]; other.sigma = W.sigma[c]; other.index = static_cast< int >(packed & 0x0fffffff);
-                        if(beats(other, best, base)) { best = other; }
-                    }
-                }
-            }
-            __syncwarp();
-        };
-
-        /* offer one barcode per lane (or none) to the pool of candidates the warp evaluates 32 at a time */
-        auto offer = [&](bool candidate, int b) {
-            const unsigned found = __ballot_sync(FULL_MASK, candidate);
-            if(found) {
-                const int fresh = __popc(found);
-                if(count + fresh > WARP_SIZE) {
-                    evaluate(count);
-                    count = 0;
-                }
-                if(candidate) { W.list[count + __popc(found & ((1u << lane) - 1u))] = (static_cast< uint32_t >(slot) << 28) | static_cast< uint32_t >(b); }
-                count += fresh;
-                __syncwarp();
-            }
-        };
-        /*  The candidates the scan named: lane `sub` of a read evaluates its candidate c + sub on the spot (no pooling),
-            then the read's lanes reduce to the one the reference's scan would keep (beats is a strict total order, so
-            the butterfly leaves every lane of the read with the same winner). */
-        {
-            const uint32_t mine = rescan ? 0u : listed;
-            const uint32_t most = __reduce_max_sync(FULL_MASK, mine);
-            for(uint32_t c = 0; c < most; c += TIE_LANES) {
-                Candidate own;
-                own.prior = 0; own.sigma = 0; own.index = -1;
-                if(c + sub < mine) {
-                    int b;
-                    if(blocks) {
-                        /* candidate c + sub = barcode (c + sub) % run of the ((c + sub) / run)-th flagged run */
-                        const uint32_t which = (c + sub) / run;
-                        const int e = static_cast< int >(__fns(block_mask, 0u, static_cast< int >(which) + 1) * run + (c + sub) % run);
-                        b = e < scanned ? (grid_entries ? static_cast< int >(reinterpret_cast< const uint4* >(P.grid)[P.grid_a + P.grid_b + e].y) : e) : N;
-                    } else {
-                        b = static_cast< int >(named[c + sub]);
-                    }
-                    if(b < N) {
-                        const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
-                        const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
-                        /* Barcode::compensated_decoding_probability's accumulation, bit for bit (barcode.h:147-162) */
-                        const double* const on_match = W.match_value[slot];
-                        const double* const on_mismatch = W.mismatch_value[slot];
-                        double sigma = 0.0, compensation = 0.0;
-                        #pragma unroll 4
-                        for(int j = 0; j < L; ++j) {
-                            const double value = ((m >> j) & 1u) ? on_mismatch[j] : on_match[j];
-                            const double y = __dsub_rn(value, compensation);
-                            const double t = __dadd_rn(sigma, y);
-                            compensation = __dsub_rn(__dsub_rn(t, sigma), y);
-                            sigma = t;
-                        }
-                        own.prior = __hiloint2double(raw.w, raw.z); own.sigma = sigma; own.index = b;
-                    }
-                }
-                #pragma unroll
-                for(int offset = TIE_LANES / 2; offset > 0; offset >>= 1) {
+                const uint32_t m = ((r_lo ^ raw.x) | (r_hi ^ raw.y)) | r_n;
+                const double prior = __hiloint2double(static_cast< int >(raw.w), static_cast< int >(raw.z));
+                if(tie_product< G >(r_address, ratio_table, m & ~r_n, L) * prior >= threshold) {
                     Candidate other;
-                    other.prior = __shfl_xor_sync(FULL_MASK, own.prior, offset);
-                    other.sigma = __shfl_xor_sync(FULL_MASK, own.sigma, offset);
-                    other.index = __shfl_xor_sync(FULL_MASK, own.index, offset);
+                    other.sigma = tie_sigma< G >(r_address, m, L);
+                    other.prior = prior;
+                    other.index = b;
                     if(beats(other, own, base)) { own = other; }
                 }
-                if(sub == 0 && beats(own, best, base)) { best = own; }
             }
-        }
-        if(any_rescan) {
-            #pragma unroll 1
-            for(int first = 0; first < N; first += TIE_LANES) {
-                const int b = first + sub;
-                bool candidate = false;
-                if(rescan && b < N) {
-                    const uint4 raw = *reinterpret_cast< const uint4* >(barcodes + b);
-                    const uint32_t m = ((o_lo ^ raw.x) | (o_hi ^ raw.y)) | nmask;
-                    double p = table[m & 15u];
-                    #pragma unroll
-                    for(int g = 1; g < G; ++g) { p *= table[g * 16 + ((m >> (4 * g)) & 15u)]; }
-                    candidate = p * __hiloint2double(raw.w, raw.z) >= threshold;
-                }
-                offer(candidate, b);
+            #pragma unroll
+            for(int offset = WARP_SIZE / 2; offset > 0; offset >>= 1) {
+                Candidate other;
+                other.prior = __shfl_xor_sync(FULL_MASK, own.prior, offset);
+                other.sigma = __shfl_xor_sync(FULL_MASK, own.sigma, offset);
+                other.index = __shfl_xor_sync(FULL_MASK, own.index, offset);
+                if(beats(other, own, base)) { own = other; }
             }
+            if(lane == owner) { best = own; }
         }
-        if(count) { evaluate(count); }
 
-        /* the winner's mismatch product, the read's lanes sharing its positions (ratio 1 where the base is ambiguous) */
-        const int winner = max(__shfl_sync(FULL_MASK, best.index, slot * TIE_LANES), 0);
-        const uint4 winner_entry = *reinterpret_cast< const uint4* >(barcodes + winner);
-        const uint32_t m = ((o_lo ^ winner_entry.x) | (o_hi ^ winner_entry.y)) | nmask;
-        double t = 1.0;
-        for(int j = sub; j < L; j += TIE_LANES) { if((m >> j) & 1u) { t *= W.ratio[slot][j]; } }
-        #pragma unroll
-        for(int offset = TIE_LANES / 2; offset > 0; offset >>= 1) { t *= __shfl_xor_sync(FULL_MASK, t, offset); }
-        if(sub == 0 && live) {
+        /* ---- the decision (pamld.cpp:87-122) */
+        bool passes = false;
+        if(live) {
+            const int winner = max(best.index, 0);
+            const uint4 winner_entry = *reinterpret_cast< const uint4* >(barcodes + winner);
+            const uint32_t m = ((o_lo ^ winner_entry.x) | (o_hi ^ winner_entry.y)) | nmask;
+            const double t = tie_product< G >(score_address, ratio_table, m & ~nmask, L);
             const long long r = record.read;
-            const double prior = __hiloint2double(winner_entry.w, winner_entry.z);
+            const double prior = __hiloint2double(static_cast< int >(winner_entry.w), static_cast< int >(winner_entry.z));
             /* everything but the winner: the scan's total minus the winner. The winner is within 2^-18 of
                the scan's maximum, so the first difference is exact (Sterbenz) and nothing cancels. */
             const double others = (record.best - t * prior) + record.rest;
@@ -2502,10 +2571,14 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
                                            record.uniform != 0u, record.high_quality_mask, qcfail);
             A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
             store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
-            atomicAdd(&block_counter[0], 1u);
-            if(!v.qcfail) { atomicAdd(&block_counter[1], 1u); }
+            passes = !v.qcfail;
         }
-        __syncwarp();
+        const unsigned decided = __ballot_sync(FULL_MASK, live);
+        const unsigned passing = __ballot_sync(FULL_MASK, passes);
+        if(lane == 0) {
+            atomicAdd(&block_counter[0], static_cast< uint32_t >(__popc(decided)));
+            if(passing) { atomicAdd(&block_counter[1], static_cast< uint32_t >(__popc(passing))); }
+        }
     }
     __syncthreads();
     if(tid < 2 && P.totals != nullptr && block_counter[tid]) { atomicAdd(&P.totals[tid], static_cast< unsigned long long >(block_counter[tid])); }
@@ -2832,19 +2905,12 @@ __global__ void reference_power_kernel(const double* __restrict__ sigma, double*
 /* the tie pass over the reads the scan queued; the queue length is only known on the device: a fixed grid strides over it */
 template < int G >
 cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, const LaunchGeometry& geometry, cudaStream_t stream) {
-    const size_t tie_bytes = (params.barcode_cardinality <= TIE_STAGE_ENTRIES ? static_cast< size_t >(params.barcode_cardinality) * sizeof(BarcodeEntry) : 0)
-                           + static_cast< size_t >(tie_accumulator_rows(params.barcode_cardinality)) * (ACC_F64_COLUMNS * 8 + ACC_U64_COLUMNS * 4);
-    /* static + dynamic shared memory can pass the 48 KB a kernel gets without opting in */
-    cudaError_t status = cudaFuncSetAttribute(pamld_tie_kernel< G, 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024);
-    if(status == cudaSuccess) { status = cudaFuncSetAttribute(pamld_tie_kernel< G, TIE_READS_SMALL >, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024); }
+    const size_t tie_bytes = tie_shared_bytes(params.barcode_cardinality);
+    const cudaError_t status = cudaFuncSetAttribute(pamld_tie_kernel< G >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(tie_bytes));
     if(status != cudaSuccess) { return status; }
-    /* as many CTAs as stay resident (four per SM): every CTA stages the table and flushes its accumulator rows once,
+    /* as many CTAs as stay resident: every CTA stages the tables and flushes its accumulator rows once,
        and the flushes of all CTAs meet on the same few hundred global addresses */
-    if(params.barcode_cardinality >= TIE_LONG_TABLE) {
-        pamld_tie_kernel< G, 1 ><<< geometry.multiprocessor_count * 4, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
-    } else {
-        pamld_tie_kernel< G, TIE_READS_SMALL ><<< geometry.multiprocessor_count * 4, tie_warps(G) * WARP_SIZE, tie_bytes, stream >>>(params, tile);
-    }
+    pamld_tie_kernel< G ><<< geometry.multiprocessor_count * tie_resident(G), TIE_THREADS, tie_bytes, stream >>>(params, tile);
     return cudaGetLastError();
 }
 
