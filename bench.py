@@ -304,7 +304,8 @@ class Bench:
             # keep the GPU under the same load a little longer when the timed region was too short to sample
             # (without the collective: every rank decides for itself how long it keeps going)
             extra = 0
-            while len(clocks.samples) < 3 and extra < 200:
+            deadline = time.time() + 2.0
+            while len(clocks.samples) < 3 and time.time() < deadline:
                 step(warm_reads or n, collect=False)
                 extra += 1
                 if extra % 4 == 0:

@@ -534,7 +534,10 @@ struct Verdict {
     uint32_t qcfail;
 };
 constexpr double WHITELIST_BAND = 4.76837158203125e-07;      /* = WHITELIST_TOLERANCE of pamld_whitelist_kernel */
-/* the branches of pamld.cpp:96-122 and the accumulator updates, once P(r|b) and the confidence of the winner are known */
+/* the branches of pamld.cpp:96-122 and the accumulator updates, once P(r|b) and the confidence of the winner are known.
+   GUARDED: the caller has already kept the confidence away from its threshold (the prefilter scans' 2^-38 guard is
+   wider than the diagnostic's band), so only the other threshold is watched */
+template < bool GUARDED = false >
 __device__ __forceinline__ Verdict pamld_apply(const DecoderParams& P, const Accumulator& accumulator, uint32_t* band_counter,
                                                int best_index, uint32_t m, double conditional_probability, double confidence,
                                                bool uniform, uint32_t high_quality_mask, uint32_t qcfail) {
@@ -548,8 +551,11 @@ __device__ __forceinline__ Verdict pamld_apply(const DecoderParams& P, const Acc
 
     /* diagnostic: reads whose decision sits within the accuracy of this path of a threshold. 1e-12 for the exact and
        prefilter scans; the pruned whitelist scan can move a confidence by up to 2^-21 (1 - confidence) */
-    const double confidence_band = P.whitelist != nullptr ? fmax(1e-12, WHITELIST_BAND * (1.0 - v.confidence)) : 1e-12;
-    bool band = fabs(v.confidence - P.confidence_threshold) <= confidence_band;
+    bool band = false;
+    if(!GUARDED) {
+        const double confidence_band = P.whitelist != nullptr ? fmax(1e-12, WHITELIST_BAND * (1.0 - v.confidence)) : 1e-12;
+        band = fabs(v.confidence - P.confidence_threshold) <= confidence_band;
+    }
     if(!uniform) { band = band || fabs(conditional_probability - P.random_barcode_probability) <= 1e-12 * P.random_barcode_probability; }
     if(band) { atomicAdd(band_counter, 1u); }
 
@@ -1187,8 +1193,7 @@ __device__ __forceinline__ void fast_store_group(float* t, const float* w) {
     const float w2 = COUNT > 2 ? w[COUNT > 2 ? 2 : 0] : 1.0f;
     const float w3 = COUNT > 3 ? w[COUNT > 3 ? 3 : 0] : 1.0f;
     const float w01 = w0 * w1;
-    t[0 * WARP_SIZE] = 1.0f;
-    t[1 * WARP_SIZE] = w0;
+    t[1 * WARP_SIZE] = w0;                  /* entry 0, the empty subset, is 1 for every read: the kernels store it once */
     if(COUNT > 1) {
         t[2 * WARP_SIZE] = w1;
         t[3 * WARP_SIZE] = w01;
@@ -1370,7 +1375,7 @@ __device__ __forceinline__ bool fast_decide(const DecoderParams& P, const TileAr
         high_quality_mask = quality_mask< G, POSITIONS >(quality, P.high_quality_threshold);
         high_quality_mask &= (P.nucleotide_cardinality >= 32) ? 0xffffffffu : ((1u << P.nucleotide_cardinality) - 1u);
     }
-    const Verdict v = pamld_apply(P, S.accumulator, &S.misc[3], winner, m, base_probability * t, confidence, false, high_quality_mask, qcfail);
+    const Verdict v = pamld_apply< true >(P, S.accumulator, &S.misc[3], winner, m, base_probability * t, confidence, false, high_quality_mask, qcfail);
     qcfail = v.qcfail;
     A.qcfail[r] = static_cast< uint8_t >(v.qcfail);
     store_result(A, r, v.decoded, v.distance, v.confidence, v.qcfail);
@@ -1399,6 +1404,8 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     hard.list = P.hard_list;
     hard.count = P.tie_count + 2;
     const bool by_block = P.barcode_cardinality >= FAST_BLOCK_SELECTION;
+    #pragma unroll
+    for(int g = 0; g < G; ++g) { table[g * FAST_GROUP_FLOATS] = 1.0f; }         /* the empty subset of every group */
 
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
     const long long my_tiles = tile_cardinality > blockIdx.x ? (tile_cardinality - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -1606,6 +1613,8 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
     hard.list = P.hard_list;
     hard.count = P.tie_count + 2;
     const float prior32 = static_cast< float >(entry[0].prior);
+    #pragma unroll
+    for(int g = 0; g < GA + GB; ++g) { table[g * FAST_GROUP_FLOATS] = 1.0f; }   /* the empty subset of every group */
     /* dense form: the priors of the grid entries in f32, behind the per-warp tables */
     float* const dense_prior = reinterpret_cast< float* >(smem + aligned_tables + static_cast< size_t >(blockDim.x >> 5) * ((GA + GB) * FAST_GROUP_FLOATS * sizeof(float)));
     if(KBP > 0) {
@@ -1669,8 +1678,9 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
                 const uint32_t m = mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y);
                 sb[k] = fast_product< GA, GB >(table_base, m);
             }
-            FastSelection selection;
-            selection.best = 0.0f; selection.index = 0; selection.rest = 0.0;
+            /* the index travels per block of four entries (fast_select_block); the leading block is formed once more below */
+            FastBlockSelection leader;
+            leader.best = 0.0f; leader.best_sum = 0.0f; leader.index = 0; leader.rest = 0.0;
             for(int a = 0; a < KA; ++a) {
                 const uint2 h = *reinterpret_cast< const uint2* >(header + a);
                 const uint32_t m = mismatch_mask(a_lo, a_hi, a_n, h.x, h.y);
@@ -1678,8 +1688,24 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
                 #pragma unroll
                 for(int k = 0; k < KBP; k += 4) {
                     const float4 prior = *reinterpret_cast< const float4* >(dense_prior + a * KBP + k);
-                    fast_select_four(selection, (sa * sb[k]) * prior.x, (sa * sb[k + 1]) * prior.y, (sa * sb[k + 2]) * prior.z, (sa * sb[k + 3]) * prior.w, a * KBP + k);
+                    const float p0 = (sa * sb[k]) * prior.x, p1 = (sa * sb[k + 1]) * prior.y, p2 = (sa * sb[k + 2]) * prior.z, p3 = (sa * sb[k + 3]) * prior.w;
+                    fast_select_block(leader, fmaxf(fmaxf(p0, p1), fmaxf(p2, p3)), (p0 + p1) + (p2 + p3), a * KBP + k);
                 }
+            }
+            FastSelection selection;
+            selection.best = 0.0f; selection.index = leader.index; selection.rest = leader.rest;
+            {
+                const int a = leader.index / KBP, k = leader.index % KBP;
+                const uint2 h = *reinterpret_cast< const uint2* >(header + a);
+                const float sa = fast_product< 0, GA >(table_base, mismatch_mask(a_lo, a_hi, a_n, h.x, h.y));
+                const float4 prior = *reinterpret_cast< const float4* >(dense_prior + leader.index);
+                float p[4];
+                #pragma unroll
+                for(int u = 0; u < 4; ++u) {
+                    const uint2 raw = *reinterpret_cast< const uint2* >(word + k + u);
+                    p[u] = sa * fast_product< GA, GB >(table_base, mismatch_mask(b_lo, b_hi, b_n, raw.x, raw.y));
+                }
+                fast_select_four(selection, p[0] * prior.x, p[1] * prior.y, p[2] * prior.z, p[3] * prior.w, leader.index);
             }
             best = selection.best;
             others = selection.rest;
