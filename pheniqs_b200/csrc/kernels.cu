@@ -1151,7 +1151,9 @@ constexpr float FAST_MINIMUM_BEST = 8.6736173798840355e-19f;        /* 2^-60: be
 constexpr double FAST_THRESHOLD_GUARD = 3.637978807091713e-12;      /* 2^-38 */
 constexpr int FAST_BLOCK_SELECTION = 32;                            /* codecs from this size on keep the index per block of four (fast_select_block) */
 constexpr int FAST_GROUP_FLOATS = 16 * WARP_SIZE;                   /* one table group: 16 subsets x 32 lanes, 2 KB */
-__host__ __device__ constexpr int fast_warps(int G) { return G <= 2 ? 24 : (G <= 4 ? 20 : 16); }
+/* warps per CTA (one CTA per SM): what the per-warp tables and the registers allow — 64 registers at 32 warps, which the
+   scan under one prior fits up to 8 nt; its prior multiply per pair costs the other form the registers for that */
+__host__ __device__ constexpr int fast_warps(int G, bool uniform) { return G <= 2 ? (uniform ? 32 : 24) : (G <= 4 ? 20 : 16); }
 
 /* subset product of table group TABLE_GROUP for the nibble at bits 4 * LOCAL of m: entry e of the lane at
    base + TABLE_GROUP * 2048 + e * 128; the warp's block is 2 KB aligned in the shared window, so (nibble << 7) | base */
@@ -1383,7 +1385,7 @@ __device__ __forceinline__ bool fast_decide(const DecoderParams& P, const TileAr
 }
 
 template < int G, bool UNIFORM >
-__global__ void __launch_bounds__(fast_warps(G) * WARP_SIZE, 1)
+__global__ void __launch_bounds__(fast_warps(G, UNIFORM) * WARP_SIZE, 1)
 pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     extern __shared__ __align__(256) unsigned char smem[];
     const BlockState S = block_prologue(smem, P, true, 0, true);
@@ -2471,8 +2473,13 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
     __syncthreads();
 
     const int L = P.nucleotide_cardinality;
-    const unsigned stride = gridDim.x * TIE_THREADS;
-    for(unsigned first_item = blockIdx.x * TIE_THREADS + (tid & ~31); first_item < tie_cardinality; first_item += stride) {
+    /* a warp takes the next 32 records of the queue: what a read costs varies with its candidates by an order of magnitude,
+       and a fixed split left a quarter of the SM cycles idle at the end */
+    for(;;) {
+        unsigned first_item = 0;
+        if(lane == 0) { first_item = atomicAdd(P.tie_count + 1, 32u); }
+        first_item = __shfl_sync(FULL_MASK, first_item, 0);
+        if(first_item >= tie_cardinality) { break; }
         const unsigned item = first_item + lane;
         const bool live = item < tie_cardinality;
         /* everything the scan knew about the read travels in the record: one 128-byte line per thread */
@@ -2936,6 +2943,11 @@ cudaError_t launch_tie(const DecoderParams& params, const TileArguments& tile, c
     if(status != cudaSuccess) { return status; }
     /* as many CTAs as stay resident: every CTA stages the tables and flushes its accumulator rows once,
        and the flushes of all CTAs meet on the same few hundred global addresses */
+    if(params.whitelist != nullptr) {
+        /* header word [1], the tie pass' work counter, was the whitelist scan's own: the other scans clear it with the queue length */
+        const cudaError_t cleared = cudaMemsetAsync(params.tie_count + 1, 0, sizeof(unsigned), stream);
+        if(cleared != cudaSuccess) { return cleared; }
+    }
     pamld_tie_kernel< G ><<< geometry.multiprocessor_count * tie_resident(G), TIE_THREADS, tie_bytes, stream >>>(params, tile);
     return cudaGetLastError();
 }
@@ -2953,7 +2965,7 @@ cudaError_t launch_pamld_groups(const DecoderParams& params, const TileArguments
     const int threads = warps * WARP_SIZE;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
-    status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
+    status = cudaMemsetAsync(params.tie_count, 0, 2 * sizeof(unsigned), stream);      /* the tie queue's length and the tie pass' work counter */
     if(status != cudaSuccess) { return status; }
     pamld_kernel< G ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
@@ -2981,7 +2993,7 @@ cudaError_t launch_pamld_grid_as(const DecoderParams& params, const TileArgument
     const int threads = warps * WARP_SIZE;
     const long long tiles = (tile.n_reads + threads - 1) / threads;
     const int grid = static_cast< int >(tiles < geometry.multiprocessor_count ? tiles : geometry.multiprocessor_count);
-    status = cudaMemsetAsync(params.tie_count, 0, sizeof(unsigned), stream);
+    status = cudaMemsetAsync(params.tie_count, 0, 2 * sizeof(unsigned), stream);      /* the tie queue's length and the tie pass' work counter */
     if(status != cudaSuccess) { return status; }
     pamld_grid_kernel< LA, LB, W, KBP, UNIFORM ><<< grid, threads, bytes, stream >>>(params, tile);
     status = cudaGetLastError();
@@ -3003,7 +3015,7 @@ cudaError_t launch_pamld_fast_groups_as(const DecoderParams& params, const TileA
     const size_t per_warp = static_cast< size_t >(G) * FAST_GROUP_FLOATS * sizeof(float);
     if(plan.fixed_bytes + per_warp > geometry.shared_memory_per_block_optin) { return cudaErrorInvalidConfiguration; }
     int warps = static_cast< int >((geometry.shared_memory_per_block_optin - plan.fixed_bytes) / per_warp);
-    warps = warps > fast_warps(G) ? fast_warps(G) : warps;
+    warps = warps > fast_warps(G, UNIFORM) ? fast_warps(G, UNIFORM) : warps;
     const size_t bytes = plan.fixed_bytes + per_warp * warps;
     cudaError_t status = cudaFuncSetAttribute(pamld_fast_kernel< G, UNIFORM >, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
     if(status != cudaSuccess) { return status; }

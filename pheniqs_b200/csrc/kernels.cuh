@@ -145,7 +145,7 @@ struct DecoderParams {
     int32_t whitelist_chunks;
     double prior_maximum;                       /* largest barcode prior: the pruning bound of pamld_whitelist_kernel */
     TieRecord* tie_record;                      /* [reads of the launch] queue of reads whose winner needs the exact tie path (PAMLD) */
-    unsigned* tie_count;                        /* queue header: [0] tie queue length, [1] work counter of the whitelist scan, [2] hard list length, [3] pool cursor */
+    unsigned* tie_count;                        /* queue header: [0] tie queue length, [1] work counter (of the whitelist scan, then of the tie pass), [2] hard list length, [3] pool cursor */
     const FastEntry* fast_barcodes;             /* [N] device; NULL = no f32 prefilter scan for this decoder (exact scan over every read) */
     const float* phred32;                       /* [128] mismatch ratios rounded to f32 */
     float fast_uniform_prior;                   /* the common prior (f32) when every barcode has the same one, else 0: the prefilter scan then multiplies once per read */
