@@ -3,6 +3,7 @@ profiles/ncu_summary.json that bench.py quotes in `roofline` (DRAM bytes per rea
 binding resource of the workload's dominant kernel).
 
 usage: ncu_to_profiles.py report.ncu-rep|raw.csv workload reads_per_launch kernel_substring output_name
+       (workload "-" : write the text summary only, e.g. for a kernel that is not its workload's dominant one)
 """
 import csv, json, os, subprocess, sys
 
@@ -52,6 +53,9 @@ def main():
                   "FP64 pipe (sm__inst_executed_pipe_fp64)": percent("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
                   "DRAM (gpu__dram_throughput)": percent("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
     resource = max(candidates, key=lambda k: candidates[k] or 0)
+    if workload == "-":
+        print(open(text_path).read())
+        return
     summary_path = os.path.join(root, "profiles", "ncu_summary.json")
     summary = json.load(open(summary_path)) if os.path.exists(summary_path) else {}
     summary[workload] = {"kernel": row[header.index("Kernel Name")], "dram_bytes_per_read": dram / reads,
