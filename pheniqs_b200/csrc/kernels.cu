@@ -1420,6 +1420,7 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
     const BarcodeEntry* resident_stage = nullptr;
     if(resident && total_iterations > 0) { resident_stage = stream.wait(0); }
 
+    uint32_t decided_reads = 0u, passing_reads = 0u;
     ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = tile * blockDim.x + tid;
@@ -1548,17 +1549,19 @@ pamld_fast_kernel(const DecoderParams P, const TileArguments A) {
             decided = fast_decide< G, 4 * G >(P, A, S, r, selection.index, o_lo, o_hi, nmask, quality, selection.rest, base_probability, qcfail);
         }
         hard.append(valid && !decided, r, lane);
-        if(P.totals != nullptr) {
-            const unsigned live = __ballot_sync(FULL_MASK, decided);
-            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
-            if(lane == 0) {
-                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
-                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
-            }
-        }
+        decided_reads += decided ? 1u : 0u;                 /* the chain's totals: counted per thread, added once per warp below */
+        passing_reads += (decided && !qcfail) ? 1u : 0u;
         __syncwarp();
     }
     hard.flush(lane);
+    if(P.totals != nullptr) {
+        decided_reads = __reduce_add_sync(FULL_MASK, decided_reads);
+        passing_reads = __reduce_add_sync(FULL_MASK, passing_reads);
+        if(lane == 0) {
+            atomicAdd(&S.misc[0], decided_reads);
+            atomicAdd(&S.misc[1], passing_reads);
+        }
+    }
     block_epilogue(S, P);
 }
 
@@ -1627,6 +1630,7 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
     }
 
     const long long tile_cardinality = (A.n_reads + blockDim.x - 1) / blockDim.x;
+    uint32_t decided_reads = 0u, passing_reads = 0u;
     ObservedRead< G > upcoming = fetch_read< G >(A, static_cast< long long >(blockIdx.x) * blockDim.x + tid);
     for(long long tile = blockIdx.x; tile < tile_cardinality; tile += gridDim.x) {
         const long long r = tile * blockDim.x + tid;
@@ -1722,17 +1726,19 @@ pamld_fast_grid_kernel(const DecoderParams P, const TileArguments A) {
             decided = fast_decide< G, L >(P, A, S, r, winner, o_lo, o_hi, nmask, quality, others, base_probability, qcfail);
         }
         hard.append(valid && !decided, r, lane);
-        if(P.totals != nullptr) {
-            const unsigned live = __ballot_sync(FULL_MASK, decided);
-            const unsigned pass = __ballot_sync(FULL_MASK, decided && !qcfail);
-            if(lane == 0) {
-                atomicAdd(&S.misc[0], static_cast< uint32_t >(__popc(live)));
-                atomicAdd(&S.misc[1], static_cast< uint32_t >(__popc(pass)));
-            }
-        }
+        decided_reads += decided ? 1u : 0u;                 /* the chain's totals: counted per thread, added once per warp below */
+        passing_reads += (decided && !qcfail) ? 1u : 0u;
         __syncwarp();
     }
     hard.flush(lane);
+    if(P.totals != nullptr) {
+        decided_reads = __reduce_add_sync(FULL_MASK, decided_reads);
+        passing_reads = __reduce_add_sync(FULL_MASK, passing_reads);
+        if(lane == 0) {
+            atomicAdd(&S.misc[0], decided_reads);
+            atomicAdd(&S.misc[1], passing_reads);
+        }
+    }
     block_epilogue(S, P);
 }
 
