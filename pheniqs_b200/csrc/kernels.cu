@@ -636,7 +636,7 @@ __device__ __forceinline__ void queue_ties(const DecoderParams& P, bool tied, in
             #pragma unroll
             for(int c = 0; c < TIE_CANDIDATES; ++c) { record.candidate[c] = c < LIST::capacity ? candidates.entry[c < LIST::capacity ? c : 0] : 0u; }
             record.candidate_count = candidates.count;
-            if(candidates.count > static_cast< uint32_t >(TIE_CANDIDATES) && candidates.count != TIE_BLOCKS) {
+            if(candidates.count > static_cast< uint32_t >(TIE_CANDIDATES) && candidates.count != TIE_BLOCKS && candidates.count != TIE_MASKS) {
                 record.candidate_count = TIE_RESCAN;
                 if(candidates.count <= static_cast< uint32_t >(LIST::capacity) && P.tie_pool != nullptr) {
                     /* more than a record holds: the list goes to the pool */
@@ -992,7 +992,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         Selection selection;
         selection.best = 0.0; selection.rest = 0.0; selection.index = 0; selection.second = 0;
-        CandidateList candidates;       /* separable form only: grid entry numbers until the queue step turns them into barcodes */
+        CandidateList candidates;       /* what the queue step hands to the tie pass: the separable form its two word masks, the pair loops their block mask */
         candidates.reset();
         #pragma unroll
         for(int c = 0; c < TIE_CANDIDATES; ++c) { candidates.entry[c] = 0u; }
@@ -1030,11 +1030,11 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
                 /* whatever ties with the maximum pairs a word that ties with the best A word and one that ties with the best B word */
                 if(KA > 32 || KB > 32) { candidates.count = TIE_CANDIDATES + 1; }
                 else {
-                    for(uint32_t wa = part_a.near; wa != 0u; wa &= wa - 1u) {
-                        for(uint32_t wb = part_b.near; wb != 0u; wb &= wb - 1u) {
-                            candidates.push(static_cast< uint32_t >((__ffs(static_cast< int >(wa)) - 1) * KB + (__ffs(static_cast< int >(wb)) - 1)));
-                        }
-                    }
+                    /* the two masks travel as they are (TIE_MASKS): the tie pass walks their cross product */
+                    candidates.count = TIE_MASKS;
+                    candidates.entry[0] = part_a.near;
+                    candidates.entry[1] = part_b.near;
+                    candidates.entry[2] = static_cast< uint32_t >(KB);
                 }
             }
         } else if constexpr(KBP > 0) {
@@ -1094,13 +1094,7 @@ pamld_grid_kernel(const DecoderParams P, const TileArguments A) {
 
         /* ---- ties are queued; everything else is decided here */
         const bool tied = valid && (selection.second + 1 >= __double2hiint(selection.best));
-        if constexpr(UNIFORM) {
-            if(tied && candidates.count <= static_cast< uint32_t >(TIE_CANDIDATES)) {
-                for(uint32_t c = 0; c < candidates.count; ++c) { candidates.entry[c] = entry[candidates.entry[c]].index; }
-            }
-        } else {
-            candidates = block_candidates(near_blocks, P.tie_block_shift, true);
-        }
+        if constexpr(!UNIFORM) { candidates = block_candidates(near_blocks, P.tie_block_shift, true); }
         queue_ties< G, CandidateList >(P, tied, lane, selection, base_probability, high_quality_mask, uniform_positions == L, o_lo, o_hi, nmask, r, quality, candidates);
         const bool decided = valid && !tied;
         if(decided) {
@@ -2511,19 +2505,35 @@ pamld_tie_kernel(const DecoderParams P, const TileArguments A) {
         const uint32_t count_word = record.candidate_count;
         const bool rescan = live && count_word == TIE_RESCAN;
         const bool blocks = live && count_word == TIE_BLOCKS;
-        const bool pooled = live && !blocks && !rescan && (count_word & TIE_POOLED) != 0u;
+        const bool masks = live && count_word == TIE_MASKS;        /* the separable scan: words of part A x words of part B */
+        const bool pooled = live && !blocks && !masks && !rescan && (count_word & TIE_POOLED) != 0u;
         const uint32_t* const named = pooled ? P.tie_pool + record.candidate[0] : P.tie_record[live ? item : 0u].candidate;
         const bool grid_entries = blocks && record.candidate[2] != 0u;
         const uint32_t scanned = static_cast< uint32_t >(grid_entries ? P.grid_entries : N);      /* what a block mask counts */
         const uint32_t run = 4u << (record.candidate[1] & 31u);
-        uint32_t pending_runs = blocks ? record.candidate[0] : 0u;
+        uint32_t pending_runs = (blocks || masks) ? record.candidate[0] : 0u;    /* flagged runs, or words of part A */
+        uint32_t pending_words = 0u;                                               /* words of part B still to pair with the current A word */
         uint32_t next = 0u;
-        uint32_t last = (!live || rescan || blocks) ? 0u : (pooled ? (count_word & 0xffffu) : count_word);
+        uint32_t last = (!live || rescan || blocks || masks) ? 0u : (pooled ? (count_word & 0xffffu) : count_word);
         Candidate best;
         best.prior = 0; best.sigma = 0; best.index = -1;
         /* the next candidate of this thread, -1 when it has none left */
         auto pull = [&]() -> int {
             for(;;) {
+                if(masks) {
+                    if(pending_words == 0u) {
+                        if(pending_runs == 0u) { return -1; }
+                        next = static_cast< uint32_t >(__ffs(static_cast< int >(pending_runs)) - 1) * record.candidate[2];     /* a x KB */
+                        pending_runs &= pending_runs - 1u;
+                        pending_words = record.candidate[1];
+                        continue;
+                    }
+                    const uint32_t e = next + static_cast< uint32_t >(__ffs(static_cast< int >(pending_words)) - 1);
+                    pending_words &= pending_words - 1u;
+                    const int b = static_cast< int >(reinterpret_cast< const uint4* >(P.grid)[P.grid_a + P.grid_b + e].y);
+                    if(b < N) { return b; }
+                    continue;
+                }
                 if(next >= last) {
                     if(pending_runs == 0u) { return -1; }
                     const uint32_t bit = static_cast< uint32_t >(__ffs(static_cast< int >(pending_runs)) - 1);

@@ -88,6 +88,7 @@ constexpr int WHITELIST_MINIMUM_BARCODES = 4096;    /* smaller codecs use the ex
 constexpr int TIE_CANDIDATES = 11;                  /* barcodes the scan can name as possible winners of a queued read */
 constexpr uint32_t TIE_RESCAN = 0xffffffffu;        /* candidate_count of a read whose candidates the tie kernel has to find itself */
 constexpr uint32_t TIE_BLOCKS = 0xfffffffeu;        /* candidate_count: candidate[0] is a bit mask over runs of (4 << candidate[1]) consecutive barcodes (grid entries when candidate[2]) that hold every possible winner */
+constexpr uint32_t TIE_MASKS = 0xfffffffdu;         /* candidate_count: candidate[0] x candidate[1] are bit masks over the distinct words of the two parts of a full grid of candidate[2] B words per A word */
 constexpr uint32_t TIE_POOLED = 0x40000000u;        /* candidate_count flag: the (count & 0xffff) candidates are in the pool from entry candidate[0] on */
 constexpr int TIE_POOLED_CANDIDATES = 64;           /* the most a scan names for one read (the whitelist scan: noise reads tie a dozen ways) */
 constexpr int TIE_POOL_PER_READ = 4;                /* pool entries per read of the launch */
