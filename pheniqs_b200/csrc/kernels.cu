@@ -21,11 +21,14 @@
     factors into a per-read constant P0 = prod_j B^s(match) times prod_{j in m} w_j with
     w_j = B^(q_j - tq[q_j]) (1 for N / q = 0 positions), and the product over the mismatch set
     is looked up four positions at a time in a per-lane table of the 16 subset products held in
-    shared memory ([entry][lane] layout: conflict free). All probability arithmetic is f64.
-    The first-maximum selection of the reference (strict >) is done on the high words of the
-    f64 products; whenever the runner-up is within 2^-19 of the winner (structural ties, which
-    the reference resolves by the rounding of its position-ordered Kahan sums) the warp
-    re-evaluates that read cooperatively with the reference's exact operation order.
+    shared memory ([entry][lane] layout: conflict free). The exact scans do all probability
+    arithmetic in f64; the prefilter scans (pamld_fast_kernel, pamld_fast_grid_kernel) walk the
+    same pairs in f32 first, decide the reads whose maximum stands alone by 2^20 and leave the
+    others to the exact scans through an index list. The first-maximum selection of the
+    reference (strict >) is done on the high words of the f64 products; whenever the runner-up
+    is within 2^-19 of the winner (structural ties, which the reference resolves by the
+    rounding of its position-ordered Kahan sums) the read is queued with its possible winners
+    and pamld_tie_kernel re-evaluates those in the reference's exact operation order.
 */
 #include "kernels.cuh"
 #include <cstdio>
