@@ -1,6 +1,6 @@
 #!/bin/bash
-# gpurun_out/<tag>_* (what scripts/gpu_r2u.sh brings back from the GPU box) -> profiles/r02_*: usage refresh_profiles.sh r2u
-tag=${1:-r2u}
+# gpurun_out/<tag>_* (what scripts/gpu_profiles.sh brings back from the GPU box) -> profiles/r02_*: usage: refresh_profiles.sh [tag]
+tag=${1:-profiles}
 cd "$(dirname "$0")/.."
 for w in c1 c2 c3 c4 c5; do cp gpurun_out/${tag}_launches_$w.csv profiles/r02_launches_$w.csv; done
 python scripts/ncu_to_profiles.py gpurun_out/${tag}_full_c1_raw.csv c1 16777216 pamld_fast_grid_kernel r02_ncu_fast_grid_c1 > /dev/null
